@@ -1,0 +1,216 @@
+/*
+ * inferix_b200 — C ABI of the B200-native (sm_100a) block-diffusion denoising hot path.
+ *
+ * Drop-in boundary for alibaba-damo-academy/Inferix's Self-Forcing / CausVid DiT block forward and the
+ * KV-cache append/evict that feeds it.  The reference has no FFI of its own (it is pure Python calling
+ * library kernels), so every entry point below names the reference Python call site it replaces
+ * (paths relative to the reference root, file:line).  Signatures are plain C: raw device pointers, sizes,
+ * a cudaStream_t passed as void*; every function returns an ifx_status and never throws across the ABI.
+ *
+ * Conventions
+ *   - activations are bf16, row-major [tokens, channels]; "ld*" arguments are row strides in ELEMENTS
+ *   - all kernels are enqueued on the caller's stream; nothing here synchronises the device
+ *   - handles are not thread-safe; one host thread drives one GPU (process per GPU)
+ *   - the library is CUDA-only: there is no CPU fallback, calls fail with IFX_ERR_CUDA without a device
+ */
+#ifndef INFERIX_B200_H_
+#define INFERIX_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IFX_ABI_VERSION 1
+
+typedef enum ifx_status {
+    IFX_OK = 0,
+    IFX_ERR_INVALID = 1,     /* bad argument / shape (reference: Python assert / ValueError) */
+    IFX_ERR_BOUNDS = 2,      /* index outside the cache (reference: IndexError on slice assignment) */
+    IFX_ERR_HANDLE = 3,      /* unknown / destroyed handle (reference: KeyError) */
+    IFX_ERR_OOM = 4,         /* host allocation failed */
+    IFX_ERR_CUDA = 5,        /* CUDA runtime / driver error; text via ifx_last_error() */
+    IFX_ERR_UNSUPPORTED = 6  /* valid in the reference but outside this build's envelope */
+} ifx_status;
+
+/* Human-readable description of the last failing call on this thread ("" if none). */
+const char* ifx_last_error(void);
+int ifx_abi_version(void);
+/* Number of CUDA kernels this library has launched since process start / last reset (bench "gpu_launches"). */
+uint64_t ifx_launch_count(void);
+void ifx_reset_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Paged KV cache with a frame-aligned block table.
+ *
+ * Replaces the tensor roll + slice-assign in CausalWanSelfAttention.forward
+ *   inferix/models/self_forcing/causal_model.py:277-304,328-329   (evict / roll / append / end indices)
+ * and the storage of inferix/kvcache_manager/kvcache_manager.py:222-244 (layout (2, nblk, blk, H, D)).
+ *
+ * The caller owns the memory: two bf16 buffers k_base / v_base of shape [num_pages * page_tokens, heads*head_dim].
+ * The handle owns only the block table (logical page -> physical page), the free list and the two end indices
+ * the reference keeps in kv_cache_meta["global_end_index"/"local_end_index"].  Eviction rotates the table
+ * (0 bytes moved) where the reference copies up to 4*(L-S)*C*2 bytes.  The allocator hands out pages so that
+ * the set of valid physical pages is always the prefix [0, valid_pages) — attention streams it as one extent.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct ifx_kv ifx_kv;
+
+#define IFX_KV_MAX_PLAN_PAGES 32
+
+typedef struct ifx_kv_plan {
+    int64_t local_start;   /* reference local_start_index  (causal_model.py:296,300) */
+    int64_t local_end;     /* reference local_end_index    (causal_model.py:294,299) */
+    int64_t global_end;    /* value the reference fill_()s into global_end_index (:328) */
+    int64_t num_evicted;   /* reference num_evicted_tokens (:287), 0 when no roll happened */
+    int32_t num_pages;     /* physical pages receiving the new tokens, in token order */
+    int32_t pages[IFX_KV_MAX_PLAN_PAGES];
+    int32_t first_offset;  /* token offset inside pages[0] where the new tokens start (0 when frame-aligned) */
+} ifx_kv_plan;
+
+ifx_status ifx_kv_create(ifx_kv** out, void* k_base, void* v_base, int32_t num_pages, int32_t page_tokens,
+                         int32_t heads, int32_t head_dim);
+ifx_status ifx_kv_destroy(ifx_kv* kv);
+/* Reference: pipeline resets global_end_index/local_end_index to 0 (CausalInferencePipeline.py:193-199). */
+ifx_status ifx_kv_reset(ifx_kv* kv);
+/* Index arithmetic of causal_model.py:277-300 on host integers (no device sync), plus the table rotation.
+ * `windowed` = (local_attn_size != -1).  Commits the new end indices (reference :328-329). */
+ifx_status ifx_kv_plan_append(ifx_kv* kv, int64_t current_start, int64_t num_new_tokens, int64_t sink_tokens,
+                              int32_t windowed, ifx_kv_plan* plan);
+/* Snapshot of the state: end indices and the logical->physical table (table_out may be NULL). */
+ifx_status ifx_kv_state(const ifx_kv* kv, int64_t* global_end, int64_t* local_end, int32_t* valid_pages,
+                        int32_t* table_out, int32_t table_cap);
+/* Gather tokens [start, start+length) in the reference's logical order into contiguous [length, H*D] buffers
+ * (kvcache_manager.py:145-169 get / get_range; self_forcing_kv_cache_manager.py:112-127).  16-byte vector
+ * loads through the block table; dst_k / dst_v may be NULL to skip one side. */
+ifx_status ifx_kv_export(const ifx_kv* kv, void* dst_k, void* dst_v, int64_t start, int64_t length, void* stream);
+/* Scatter contiguous tokens into logical positions [start, start+length)
+ * (kvcache_manager.py:192-220 set; self_forcing_kv_cache_manager.py:129-145).  Extends local_end if needed. */
+ifx_status ifx_kv_import(ifx_kv* kv, const void* src_k, const void* src_v, int64_t start, int64_t length,
+                         void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Per-op kernels of the DiT block.
+ * ------------------------------------------------------------------------------------------------ */
+
+/* LayerNorm (fp32 statistics, eps) followed by AdaLN modulation, one rounding to bf16 per reference op:
+ *   out = bf16(bf16(bf16(LN(x)) * bf16(1 + scale[f])) + shift[f]),  f = row / tokens_per_frame
+ * Replaces  norm1/norm2 + modulation  causal_model.py:433,451-452  (WanLayerNorm components.py:129-142).
+ * With ln_weight/ln_bias non-NULL and scale/shift NULL it is the affine norm3 of causal_model.py:448.
+ * scale/shift point at bf16 vectors of `cols`, frame f at  ptr + f * mod_frame_stride  (elements). */
+ifx_status ifx_ln_modulate(const void* x, void* out, const void* ln_weight, const void* ln_bias, const void* shift,
+                           const void* scale, int64_t mod_frame_stride, int64_t rows, int32_t cols,
+                           int64_t tokens_per_frame, float eps, void* stream);
+
+typedef enum ifx_epilogue {
+    IFX_EPI_BIAS = 0,          /* out = bf16(acc + bias)                                  nn.Linear            */
+    IFX_EPI_BIAS_GELU = 1,     /* out = bf16(gelu_tanh(bf16(acc + bias)))                 ffn[0:2]  :377-379   */
+    IFX_EPI_BIAS_GATE_RES = 2  /* out = bf16(res + bf16(bf16(acc + bias) * gate[f]))      :444, :455-456;      */
+                               /* gate == NULL -> out = bf16(res + bf16(acc + bias))      cross-attn  :448     */
+} ifx_epilogue;
+
+/* out[M,N] = epilogue(A[M,K] @ W[N,K]^T): tcgen05 BF16 MMA, FP32 accumulation in TMEM, TMA-fed pipeline.
+ * Replaces the cuBLAS nn.Linear calls of causal_model.py:171-175,333,378-379 and wan_base/model.py:77,98
+ * together with the eager bias / GELU / gate / residual ops around them.
+ * K % 8 == 0, N % 8 == 0; all pointers 16-byte aligned. `residual` may alias `out`. */
+ifx_status ifx_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, void* out,
+                         int64_t ldo, int64_t M, int32_t N, int32_t K, int32_t epilogue, const void* residual,
+                         int64_t ldr, const void* gate, int64_t gate_frame_stride, int64_t tokens_per_frame,
+                         void* stream);
+
+/* 3-D RoPE table: complex128 [1024, head_dim/2] exactly as CausalWanModel.freqs (causal_model.py:634-641,
+ * rope_params components.py:34-52), uploaded once by the host as interleaved (cos, sin) doubles. */
+typedef struct ifx_rope_grid {
+    int32_t frames;        /* F of grid_sizes */
+    int32_t height;        /* H of grid_sizes (patch grid) */
+    int32_t width;         /* W of grid_sizes */
+    int32_t start_frame;   /* current_start // frame_seqlen   (causal_model.py:256) */
+    int32_t hw_offset;     /* first h*w index owned by this rank (sequence parallel; causal_model.py:88) */
+    int32_t hw_count;      /* h*w tokens per frame owned by this rank (= height*width when world_size == 1) */
+} ifx_rope_grid;
+
+/* Fused  QK RMSNorm (full-C, fp32, components.py:107-126) -> x weight -> 3-D RoPE in fp64
+ * (causal_rope_apply causal_model.py:33-61 / _chunked :64-100) -> bf16, and the KV append of :303-304:
+ * q goes to q_out[rows, C]; roped k and raw v go straight into the cache pages named by `plan`.
+ * qkv is the [rows, 3C] output of the fused q|k|v projection.  k_dst/v_dst override the cache destination
+ * (contiguous [rows, C] staging for the sequence-parallel all-gather) when kv == NULL. */
+ifx_status ifx_qk_norm_rope_append(const void* qkv, int64_t ld_qkv, const void* norm_q_weight,
+                                   const void* norm_k_weight, const double* freqs, const ifx_rope_grid* grid,
+                                   void* q_out, int64_t ld_q, ifx_kv* kv, const ifx_kv_plan* plan, void* k_dst,
+                                   void* v_dst, int64_t rows, int32_t heads, int32_t head_dim, float eps,
+                                   void* stream);
+
+/* Copy already-normalised K / V rows (e.g. all-gathered from peers) into the pages named by `plan`. */
+ifx_status ifx_kv_append(ifx_kv* kv, const ifx_kv_plan* plan, const void* k_src, const void* v_src, int64_t ld_src,
+                         int64_t rows, void* stream);
+
+/* WanRMSNorm on its own (cross-attention q / text k, wan_base/model.py:77,82): out = bf16(bf16(x*rsqrt(ms+eps))*w) */
+ifx_status ifx_rmsnorm(const void* x, int64_t ldx, const void* weight, void* out, int64_t ldo, int64_t rows,
+                       int32_t cols, float eps, void* stream);
+
+/* Non-causal multi-head attention  out = softmax(q k^T * scale) v  with Lq = rows of q, Lk keys.
+ * tcgen05 flash attention: S and O accumulate in TMEM, P is fed back from TMEM, K/V tiles arrive by TMA.
+ * Replaces attention()/flash_attention()  inferix/models/attention/flash_attention.py:42-200 as called from
+ * causal_model.py:307-315 (self-attention over cache[0:local_end]) and wan_base/model.py:94-95 (cross-attn).
+ * q/k/v/out are [tokens, heads*head_dim] with row strides ld*; head_dim must be 128. */
+ifx_status ifx_attention(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, void* out,
+                         int64_t ldo, int64_t q_rows, int64_t kv_rows, int32_t heads, int32_t head_dim,
+                         float softmax_scale, void* stream);
+/* Same, keys/values taken from the valid prefix of a paged cache (rows [0, local_end)). */
+ifx_status ifx_attention_kv(const void* q, int64_t ldq, const ifx_kv* kv, void* out, int64_t ldo, int64_t q_rows,
+                            float softmax_scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Whole DiT block: CausalWanAttentionBlock.forward  causal_model.py:384-484  in one call (13 launches).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct ifx_wan_block_weights {
+    int32_t dim, ffn_dim, heads, head_dim;
+    float eps;
+    const void* qkv_w;      /* [3*dim, dim]  rows: q | k | v  (self_attn.q/k/v.weight concatenated) */
+    const void* qkv_b;      /* [3*dim] */
+    const void* norm_q_w;   /* [dim] */
+    const void* norm_k_w;   /* [dim] */
+    const void* o_w;        /* [dim, dim] */
+    const void* o_b;
+    const void* norm3_w;    /* [dim] affine LN before cross-attn (NULL: identity, cross_attn_norm=False) */
+    const void* norm3_b;
+    const void* cq_w;       /* cross_attn.q */
+    const void* cq_b;
+    const void* cnorm_q_w;  /* cross_attn.norm_q */
+    const void* co_w;       /* cross_attn.o */
+    const void* co_b;
+    const void* ffn1_w;     /* [ffn_dim, dim] */
+    const void* ffn1_b;
+    const void* ffn2_w;     /* [dim, ffn_dim] */
+    const void* ffn2_b;
+} ifx_wan_block_weights;
+
+typedef struct ifx_wan_block_io {
+    void* x;                    /* [rows, dim] residual stream, updated in place */
+    int64_t rows;
+    int64_t tokens_per_frame;   /* frame_seqlen (per rank) */
+    const void* mod;            /* bf16 [frames, 6, dim] = modulation + e   (causal_model.py:412) */
+    const double* freqs;
+    ifx_rope_grid grid;
+    ifx_kv* kv;                 /* self-attention cache of this layer */
+    int64_t current_start;      /* token offset of this block, as the reference passes it */
+    int64_t sink_tokens;
+    int32_t windowed;
+    const void* cross_k;        /* [text_len, dim] cached text K (RMS-normed) */
+    const void* cross_v;
+    int64_t text_len;
+    /* scratch, all bf16, caller-allocated: */
+    void* ws_h;                 /* [rows, dim] */
+    void* ws_qkv;               /* [rows, 3*dim] */
+    void* ws_q;                 /* [rows, dim] */
+    void* ws_attn;              /* [rows, dim] */
+    void* ws_ffn;               /* [rows, ffn_dim] */
+} ifx_wan_block_io;
+
+ifx_status ifx_wan_block_forward(const ifx_wan_block_weights* w, const ifx_wan_block_io* io, ifx_kv_plan* plan_out,
+                                 void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* INFERIX_B200_H_ */

@@ -1,0 +1,132 @@
+// ABI plumbing: error text, launch counter, TMA tensor-map encoding, and the whole-block entry point that
+// strings the 13 kernels of CausalWanAttentionBlock.forward (causal_model.py:384-484) together.
+#include <atomic>
+#include <cmath>
+#include <cstring>
+
+#include "ifx_internal.h"
+
+namespace ifx {
+
+static thread_local char g_error[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+ifx_status set_error(ifx_status code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+    return code;
+}
+void count_launch(int n) { g_launches.fetch_add(static_cast<uint64_t>(n), std::memory_order_relaxed); }
+
+int sm_count() {
+    static int cached = 0;
+    if (cached == 0) {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+            cached = n;
+        else
+            cached = 148;
+    }
+    return cached;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+ifx_status make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t inner_elems, uint64_t outer_rows,
+                             uint64_t row_stride_elems, uint32_t box_inner, uint32_t box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return set_error(IFX_ERR_CUDA, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+    cuuint64_t dims[2] = {inner_elems, outer_rows};
+    cuuint64_t strides[1] = {row_stride_elems * 2};
+    cuuint32_t box[2] = {box_inner, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return set_error(IFX_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d): inner=%llu rows=%llu stride=%llu", (int)r,
+                         (unsigned long long)inner_elems, (unsigned long long)outer_rows,
+                         (unsigned long long)row_stride_elems);
+    return IFX_OK;
+}
+
+}  // namespace ifx
+
+using namespace ifx;
+
+extern "C" const char* ifx_last_error(void) { return g_error; }
+extern "C" int ifx_abi_version(void) { return IFX_ABI_VERSION; }
+extern "C" uint64_t ifx_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+extern "C" void ifx_reset_launch_count(void) { g_launches.store(0, std::memory_order_relaxed); }
+
+#define IFX_TRY(expr)                     \
+    do {                                  \
+        ifx_status _s = (expr);           \
+        if (_s != IFX_OK) return _s;      \
+    } while (0)
+
+extern "C" ifx_status ifx_wan_block_forward(const ifx_wan_block_weights* w, const ifx_wan_block_io* io,
+                                            ifx_kv_plan* plan_out, void* stream) {
+    IFX_CHECK_ARG(w && io, "ifx_wan_block_forward: null argument");
+    IFX_CHECK_ARG(io->x && io->mod && io->freqs && io->kv && io->cross_k && io->cross_v,
+                  "ifx_wan_block_forward: null tensor");
+    IFX_CHECK_ARG(io->ws_h && io->ws_qkv && io->ws_q && io->ws_attn && io->ws_ffn,
+                  "ifx_wan_block_forward: null workspace");
+    IFX_CHECK_ARG(w->dim == w->heads * w->head_dim, "ifx_wan_block_forward: dim != heads*head_dim");
+    if (!w->norm3_w || !w->norm3_b)
+        return set_error(IFX_ERR_UNSUPPORTED, "ifx_wan_block_forward: cross_attn_norm=False is not built");
+    const int C = w->dim, F = w->ffn_dim;
+    const int64_t S = io->rows, fs = io->tokens_per_frame;
+    IFX_CHECK_ARG(S > 0 && fs > 0 && S % fs == 0, "ifx_wan_block_forward: rows must be whole frames");
+    const __nv_bfloat16* mod = static_cast<const __nv_bfloat16*>(io->mod);
+    const int64_t mstride = 6ll * C;  // per-frame stride of [frames, 6, C]
+    const float scale = 1.0f / std::sqrt(static_cast<float>(w->head_dim));
+
+    // --- self-attention (causal_model.py:431-444)
+    ifx_kv_plan plan;
+    IFX_TRY(ifx_kv_plan_append(io->kv, io->current_start, S, io->sink_tokens, io->windowed, &plan));
+    if (plan_out) *plan_out = plan;
+    IFX_TRY(ifx_ln_modulate(io->x, io->ws_h, nullptr, nullptr, mod + 0 * C, mod + 1 * C, mstride, S, C, fs, w->eps,
+                            stream));
+    IFX_TRY(ifx_gemm_bf16(io->ws_h, C, w->qkv_w, C, w->qkv_b, io->ws_qkv, 3 * C, S, 3 * C, C, IFX_EPI_BIAS, nullptr, 0,
+                          nullptr, 0, 0, stream));
+    IFX_TRY(ifx_qk_norm_rope_append(io->ws_qkv, 3 * C, w->norm_q_w, w->norm_k_w, io->freqs, &io->grid, io->ws_q, C,
+                                    io->kv, &plan, nullptr, nullptr, S, w->heads, w->head_dim, w->eps, stream));
+    IFX_TRY(ifx_attention_kv(io->ws_q, C, io->kv, io->ws_attn, C, S, scale, stream));
+    IFX_TRY(ifx_gemm_bf16(io->ws_attn, C, w->o_w, C, w->o_b, io->x, C, S, C, C, IFX_EPI_BIAS_GATE_RES, io->x, C,
+                          mod + 2 * C, mstride, fs, stream));
+    // --- cross-attention (causal_model.py:448, wan_base/model.py:66-100)
+    IFX_TRY(ifx_ln_modulate(io->x, io->ws_h, w->norm3_w, w->norm3_b, nullptr, nullptr, 0, S, C, fs, w->eps, stream));
+    IFX_TRY(ifx_gemm_bf16(io->ws_h, C, w->cq_w, C, w->cq_b, io->ws_qkv, C, S, C, C, IFX_EPI_BIAS, nullptr, 0, nullptr,
+                          0, 0, stream));
+    IFX_TRY(ifx_rmsnorm(io->ws_qkv, C, w->cnorm_q_w, io->ws_q, C, S, C, w->eps, stream));
+    IFX_TRY(ifx_attention(io->ws_q, C, io->cross_k, io->cross_v, C, io->ws_attn, C, S, io->text_len, w->heads,
+                          w->head_dim, scale, stream));
+    IFX_TRY(ifx_gemm_bf16(io->ws_attn, C, w->co_w, C, w->co_b, io->x, C, S, C, C, IFX_EPI_BIAS_GATE_RES, io->x, C,
+                          nullptr, 0, 0, stream));
+    // --- FFN (causal_model.py:450-456)
+    IFX_TRY(ifx_ln_modulate(io->x, io->ws_h, nullptr, nullptr, mod + 3 * C, mod + 4 * C, mstride, S, C, fs, w->eps,
+                            stream));
+    IFX_TRY(ifx_gemm_bf16(io->ws_h, C, w->ffn1_w, C, w->ffn1_b, io->ws_ffn, F, S, F, C, IFX_EPI_BIAS_GELU, nullptr, 0,
+                          nullptr, 0, 0, stream));
+    IFX_TRY(ifx_gemm_bf16(io->ws_ffn, F, w->ffn2_w, F, w->ffn2_b, io->x, C, S, C, F, IFX_EPI_BIAS_GATE_RES, io->x, C,
+                          mod + 5 * C, mstride, fs, stream));
+    return IFX_OK;
+}

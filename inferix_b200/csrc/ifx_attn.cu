@@ -1,0 +1,354 @@
+// Non-causal flash attention for sm_100a:  out = softmax(q k^T * scale) v,  head_dim = 128, bf16 in/out.
+//
+// One CTA owns 256 query rows of one head (two 128-row tiles, "ping-pong") and streams all keys/values:
+//   warp 0        TMA producer: Q once, then K_j / V_j tiles (128 keys x 128 dims, two SWIZZLE_128B boxes each)
+//                 into a ring of kSlots 32-KiB shared-memory slots
+//   warp 1        MMA issuer (one thread):  S_w = Q_w K_j^T  (SS, 128x128x16 x 8)  -> TMEM
+//                                           O_w += P_w V_j   (TS: P read from TMEM, V MN-major from smem)
+//   warp 2        TMEM allocator (512 columns: S0 | S1 | O0 | O1, P_w aliases the first 64 columns of S_w)
+//   warps 4..7    softmax for tile 0, warps 8..11 softmax for tile 1: one thread per query row
+//                 (tcgen05.ld 32x32b: no cross-thread reductions), online softmax in the log2 domain with
+//                 lazy rescaling of O (only when the running max grows by more than 2^8), P written back to
+//                 TMEM as packed bf16, final O / l epilogue straight from TMEM to global memory.
+// While the softmax warps of one tile work, the tensor core runs the other tile's MMAs.
+//
+// Replaces flash_attention()/attention() (inferix/models/attention/flash_attention.py:42-200) at the two call
+// sites of the block: self-attention over cache[0:local_end] (causal_model.py:307-315) and text
+// cross-attention (wan_base/model.py:94-95).  Numerics follow FlashAttention-2: fp32 scores and running
+// sum (of the un-rounded probabilities), bf16 P for the PV product, one division by l at the end.
+#include "ifx_internal.h"
+#include "ifx_ptx.cuh"
+
+namespace ifx {
+
+constexpr int kQT = 128;         // query rows per tile
+constexpr int kKT = 128;         // keys per tile
+constexpr int kHD = 128;         // head dim
+constexpr int kSlots = 4;        // K/V ring slots
+constexpr int kTileBytes = 128 * 128 * 2;  // 32 KiB
+constexpr int kHalfBytes = kTileBytes / 2; // one 64-wide SWIZZLE_128B box
+constexpr int kAttnThreads = 384;
+constexpr int kAttnSmem = 2 * kTileBytes + kSlots * kTileBytes + 1024 + 256;
+constexpr float kRescaleThreshold = 8.0f;  // log2 units
+
+struct AttnParams {
+    int32_t q_rows;
+    int32_t kv_rows;
+    int32_t heads;
+    int32_t num_q_pairs;
+    float scale_log2;
+    __nv_bfloat16* out;
+    int64_t ldo;
+};
+
+__global__ void __launch_bounds__(kAttnThreads, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem;                    // [2][32 KiB]
+    uint8_t* sKV = smem + 2 * kTileBytes;  // [kSlots][32 KiB]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (2 + kSlots) * kTileBytes);
+    uint64_t* kv_full = bars;              // [kSlots]
+    uint64_t* kv_empty = bars + kSlots;    // [kSlots]
+    uint64_t* q_full = bars + 2 * kSlots;  // [1]
+    uint64_t* s_full = q_full + 1;         // [2]
+    uint64_t* p_full = s_full + 2;         // [2]
+    uint64_t* o_full = p_full + 2;         // [1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int head = blockIdx.x / p.num_q_pairs;
+    const int q0 = (blockIdx.x % p.num_q_pairs) * (2 * kQT);
+    const int n_kv = (p.kv_rows + kKT - 1) / kKT;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmQ);
+        tma_prefetch_desc(&tmK);
+        tma_prefetch_desc(&tmV);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < kSlots; ++i) {
+            mbar_init(&kv_full[i], 1);
+            mbar_init(&kv_empty[i], 1);
+        }
+        mbar_init(q_full, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&s_full[i], 1);
+            mbar_init(&p_full[i], 128);
+        }
+        mbar_init(o_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    // TMEM columns
+    const uint32_t tS[2] = {tmem_base + 0, tmem_base + 128};
+    const uint32_t tO[2] = {tmem_base + 256, tmem_base + 384};
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // Q: two tiles x two 64-wide halves
+            mbar_expect_tx(q_full, 2 * kTileBytes);
+#pragma unroll
+            for (int w = 0; w < 2; ++w)
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+                    tma_load_2d_hint(sQ + w * kTileBytes + h * kHalfBytes, &tmQ, q_full, head * kHD + h * 64,
+                                     q0 + w * kQT, kEvictFirst);
+            int idx = 0;
+            for (int j = 0; j < n_kv; ++j) {
+#pragma unroll
+                for (int kv = 0; kv < 2; ++kv, ++idx) {
+                    const int s = idx % kSlots;
+                    const uint32_t ph = (idx / kSlots) & 1;
+                    mbar_wait(&kv_empty[s], ph ^ 1);
+                    mbar_expect_tx(&kv_full[s], kTileBytes);
+                    const CUtensorMap* tm = kv == 0 ? &tmK : &tmV;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+                        tma_load_2d_hint(sKV + s * kTileBytes + h * kHalfBytes, tm, &kv_full[s],
+                                         head * kHD + h * 64, j * kKT, kEvictLast);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // S = Q K^T : A = Q (K-major), B = K (K-major), M = N = 128
+            constexpr uint32_t idesc_qk = make_idesc_bf16(kQT, kKT, 0, 0);
+            // O += P V  : A = P (TMEM),   B = V (MN-major: dims contiguous), M = 128, N = head_dim
+            constexpr uint32_t idesc_pv = make_idesc_bf16(kQT, kHD, 0, 1);
+            auto issue_qk = [&](int w, int slot) {
+                const uint32_t qa = smem_u32(sQ + w * kTileBytes);
+                const uint32_t ka = smem_u32(sKV + slot * kTileBytes);
+#pragma unroll
+                for (int k = 0; k < kHD / 16; ++k) {
+                    const uint32_t off = (k >> 2) * kHalfBytes + (k & 3) * 32;
+                    umma_ss(tS[w], make_smem_desc_sw128(qa + off, 16, 1024), make_smem_desc_sw128(ka + off, 16, 1024),
+                            idesc_qk, k != 0);
+                }
+            };
+            auto issue_pv = [&](int w, int slot, bool accumulate) {
+                const uint32_t va = smem_u32(sKV + slot * kTileBytes);
+#pragma unroll
+                for (int k = 0; k < kKT / 16; ++k) {
+                    // 16 keys = 16 rows of 128 bytes; the two 64-dim halves are kHalfBytes apart (LBO), 8-key
+                    // groups 1024 bytes apart (SBO).  P: 16 bf16 = 8 TMEM columns per step.
+                    umma_ts(tO[w], tS[w] + k * 8, make_smem_desc_sw128(va + k * 16 * 128, kHalfBytes, 1024), idesc_pv,
+                            accumulate || k != 0);
+                }
+            };
+            auto slot_of = [](int idx) { return idx % kSlots; };
+            auto phase_of = [](int idx) { return static_cast<uint32_t>((idx / kSlots) & 1); };
+
+            mbar_wait(q_full, 0);
+            mbar_wait(&kv_full[slot_of(0)], phase_of(0));
+            tc_fence_after();
+            issue_qk(0, slot_of(0));
+            umma_commit(&s_full[0]);
+            issue_qk(1, slot_of(0));
+            umma_commit(&s_full[1]);
+            umma_commit(&kv_empty[slot_of(0)]);
+            for (int j = 0; j < n_kv; ++j) {
+                const int vi = 2 * j + 1;
+                const int kn = 2 * j + 2;
+                const bool more = (j + 1 < n_kv);
+                mbar_wait(&kv_full[slot_of(vi)], phase_of(vi));
+                mbar_wait(&p_full[0], j & 1);
+                tc_fence_after();
+                issue_pv(0, slot_of(vi), j > 0);
+                if (more) {
+                    mbar_wait(&kv_full[slot_of(kn)], phase_of(kn));
+                    tc_fence_after();
+                    issue_qk(0, slot_of(kn));
+                    umma_commit(&s_full[0]);
+                }
+                mbar_wait(&p_full[1], j & 1);
+                tc_fence_after();
+                issue_pv(1, slot_of(vi), j > 0);
+                umma_commit(&kv_empty[slot_of(vi)]);
+                if (more) {
+                    issue_qk(1, slot_of(kn));
+                    umma_commit(&s_full[1]);
+                    umma_commit(&kv_empty[slot_of(kn)]);
+                }
+            }
+            umma_commit(o_full);
+        }
+    } else if (warp >= 4) {
+        const int w = (warp - 4) >> 2;  // which query tile
+        const int quad = warp & 3;      // TMEM lane quadrant
+        const uint32_t lane_sel = static_cast<uint32_t>(quad * 32) << 16;
+        const uint32_t tS_row = tS[w] + lane_sel;
+        const uint32_t tO_row = tO[w] + lane_sel;
+        const int row = q0 + w * kQT + quad * 32 + lane;
+        const float sl2 = p.scale_log2;
+
+        float m_used = -INFINITY;  // max (raw score units) the probabilities are currently referenced to
+        float l = 0.f;
+        for (int j = 0; j < n_kv; ++j) {
+            mbar_wait(&s_full[w], j & 1);
+            tc_fence_after();
+            uint32_t s[4][32];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) tmem_ld32(tS_row + c * 32, s[c]);
+            tmem_wait_ld();
+            const int valid = p.kv_rows - j * kKT;
+            if (valid < kKT) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (c * 32 + i >= valid) s[c][i] = __float_as_uint(-INFINITY);
+            }
+            float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    mx0 = fmaxf(mx0, __uint_as_float(s[c][i]));
+                    mx1 = fmaxf(mx1, __uint_as_float(s[c][i + 1]));
+                    mx2 = fmaxf(mx2, __uint_as_float(s[c][i + 2]));
+                    mx3 = fmaxf(mx3, __uint_as_float(s[c][i + 3]));
+                }
+            const float m_new = fmaxf(fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)), m_used);
+            if (j == 0) {
+                m_used = m_new;
+            } else {
+                const bool need = (m_new - m_used) * sl2 > kRescaleThreshold;
+                if (__any_sync(0xffffffffu, need)) {
+                    // whole warp rescales (tcgen05.ld/st are warp-collective); rows that did not need it use
+                    // their exact (possibly tiny) correction as well, which keeps every row consistent.
+                    const float alpha = ex2_approx((m_used - m_new) * sl2);
+                    m_used = m_new;
+                    l *= alpha;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        uint32_t o[32];
+                        tmem_ld32(tO_row + c * 32, o);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                        tmem_st32(tO_row + c * 32, o);
+                    }
+                }
+            }
+            const float ms = m_used * sl2;
+            float l0 = 0.f, l1 = 0.f;
+            uint32_t pk[2][32];
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    const float p0 = ex2_approx(fmaf(__uint_as_float(s[c][i]), sl2, -ms));
+                    const float p1 = ex2_approx(fmaf(__uint_as_float(s[c][i + 1]), sl2, -ms));
+                    l0 += p0;
+                    l1 += p1;
+                    pk[c >> 1][(c & 1) * 16 + (i >> 1)] = pack_bf16x2(p0, p1);
+                }
+            l += l0 + l1;
+            tmem_st32(tS_row, pk[0]);
+            tmem_st32(tS_row + 32, pk[1]);
+            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive(&p_full[w]);
+        }
+
+        // epilogue: O / l -> bf16 -> global
+        mbar_wait(o_full, 0);
+        tc_fence_after();
+        const float inv_l = 1.0f / l;
+        __nv_bfloat16* optr = p.out + static_cast<int64_t>(row) * p.ldo + head * kHD;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            uint32_t o[32];
+            tmem_ld32(tO_row + c * 32, o);
+            tmem_wait_ld();
+            if (row < p.q_rows) {
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    uint4 pkt;
+                    pkt.x = pack_bf16x2(__uint_as_float(o[v * 8 + 0]) * inv_l, __uint_as_float(o[v * 8 + 1]) * inv_l);
+                    pkt.y = pack_bf16x2(__uint_as_float(o[v * 8 + 2]) * inv_l, __uint_as_float(o[v * 8 + 3]) * inv_l);
+                    pkt.z = pack_bf16x2(__uint_as_float(o[v * 8 + 4]) * inv_l, __uint_as_float(o[v * 8 + 5]) * inv_l);
+                    pkt.w = pack_bf16x2(__uint_as_float(o[v * 8 + 6]) * inv_l, __uint_as_float(o[v * 8 + 7]) * inv_l);
+                    *reinterpret_cast<uint4*>(optr + c * 32 + v * 8) = pkt;
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+static ifx_status attention_launch(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, void* out,
+                                   int64_t ldo, int64_t q_rows, int64_t kv_rows, int32_t heads, int32_t head_dim,
+                                   float softmax_scale, cudaStream_t stream) {
+    IFX_CHECK_ARG(q && k && v && out, "ifx_attention: null pointer");
+    IFX_CHECK_ARG(head_dim == kHD, "ifx_attention: head_dim must be 128 (got %d)", head_dim);
+    IFX_CHECK_ARG(q_rows > 0 && kv_rows > 0 && heads > 0, "ifx_attention: empty problem (q_rows=%lld kv_rows=%lld)",
+                  (long long)q_rows, (long long)kv_rows);
+    IFX_CHECK_ARG(q_rows < (1ll << 31) && kv_rows < (1ll << 31), "ifx_attention: sequence too long");
+    const int64_t width = static_cast<int64_t>(heads) * head_dim;
+    IFX_CHECK_ARG(ldq >= width && ldkv >= width && ldo >= width, "ifx_attention: stride smaller than heads*head_dim");
+    IFX_CHECK_ARG(ldq % 8 == 0 && ldkv % 8 == 0 && ldo % 8 == 0, "ifx_attention: strides must be multiples of 8");
+    IFX_CHECK_ARG(softmax_scale > 0.f, "ifx_attention: softmax_scale must be positive");
+
+    CUtensorMap tmQ, tmK, tmV;
+    ifx_status st = make_tmap_bf16_2d(&tmQ, q, (uint64_t)width, (uint64_t)q_rows, (uint64_t)ldq, 64, kQT);
+    if (st != IFX_OK) return st;
+    st = make_tmap_bf16_2d(&tmK, k, (uint64_t)width, (uint64_t)kv_rows, (uint64_t)ldkv, 64, kKT);
+    if (st != IFX_OK) return st;
+    st = make_tmap_bf16_2d(&tmV, v, (uint64_t)width, (uint64_t)kv_rows, (uint64_t)ldkv, 64, kKT);
+    if (st != IFX_OK) return st;
+
+    static bool configured = false;
+    if (!configured) {
+        IFX_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+        configured = true;
+    }
+    AttnParams p;
+    p.q_rows = static_cast<int32_t>(q_rows);
+    p.kv_rows = static_cast<int32_t>(kv_rows);
+    p.heads = heads;
+    p.num_q_pairs = static_cast<int32_t>((q_rows + 2 * kQT - 1) / (2 * kQT));
+    p.scale_log2 = softmax_scale * 1.4426950408889634f;
+    p.out = static_cast<__nv_bfloat16*>(out);
+    p.ldo = ldo;
+    const int grid = p.num_q_pairs * heads;
+    attn_fwd_kernel<<<grid, kAttnThreads, kAttnSmem, stream>>>(tmQ, tmK, tmV, p);
+    IFX_LAUNCH_OK("attn_fwd_kernel");
+    return IFX_OK;
+}
+
+}  // namespace ifx
+
+using namespace ifx;
+
+extern "C" ifx_status ifx_attention(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, void* out,
+                                    int64_t ldo, int64_t q_rows, int64_t kv_rows, int32_t heads, int32_t head_dim,
+                                    float softmax_scale, void* stream) {
+    return attention_launch(q, ldq, k, v, ldkv, out, ldo, q_rows, kv_rows, heads, head_dim, softmax_scale,
+                            static_cast<cudaStream_t>(stream));
+}
+
+extern "C" ifx_status ifx_attention_kv(const void* q, int64_t ldq, const ifx_kv* kv_, void* out, int64_t ldo,
+                                       int64_t q_rows, float softmax_scale, void* stream) {
+    const KvImpl* kv = kv_cast(kv_);
+    if (!kv) return set_error(IFX_ERR_HANDLE, "ifx_attention_kv: bad kv handle");
+    IFX_CHECK_ARG(kv->local_end > 0, "ifx_attention_kv: cache is empty");
+    // the allocator keeps valid pages as the physical prefix, and attention is invariant to key order,
+    // so the logical window [0, local_end) is read as one dense extent.
+    const int64_t width = static_cast<int64_t>(kv->heads) * kv->head_dim;
+    return attention_launch(q, ldq, kv->k_base, kv->v_base, width, out, ldo, q_rows, kv->local_end, kv->heads,
+                            kv->head_dim, softmax_scale, static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,425 @@
+// HBM-bound row kernels of the DiT block: LayerNorm+AdaLN modulation, WanRMSNorm, and the fused
+// QK-RMSNorm -> 3-D RoPE (fp64) -> paged KV append.  One CTA per token row, 16-byte vector accesses,
+// fp32 statistics; every reference rounding point (bf16 after each eager op) is reproduced explicitly.
+#include "ifx_internal.h"
+#include "ifx_ptx.cuh"
+
+namespace ifx {
+
+constexpr int kRowThreads = 256;
+constexpr int kMaxVecPerThread = 4;  // cols <= 256 * 4 * 8 = 8192
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// block-wide sum of up to two values; result broadcast to all threads
+template <int kN>
+__device__ __forceinline__ void block_sum(float (&v)[kN], float* scratch /* [kN][32] */) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+#pragma unroll
+    for (int i = 0; i < kN; ++i) v[i] = warp_sum(v[i]);
+    if (lane == 0)
+#pragma unroll
+        for (int i = 0; i < kN; ++i) scratch[i * 32 + warp] = v[i];
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kN; ++i) {
+        float t = lane < nwarps ? scratch[i * 32 + lane] : 0.f;
+        v[i] = warp_sum(t);
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void unpack8(const uint4& raw, float (&f)[8]) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        float2 t = __bfloat1622float2(h[e]);
+        f[2 * e] = t.x;
+        f[2 * e + 1] = t.y;
+    }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+    uint4 o;
+    o.x = pack_bf16x2(f[0], f[1]);
+    o.y = pack_bf16x2(f[2], f[3]);
+    o.z = pack_bf16x2(f[4], f[5]);
+    o.w = pack_bf16x2(f[6], f[7]);
+    return o;
+}
+
+// ------------------------------------------------------------------ LayerNorm + modulation
+__global__ void __launch_bounds__(kRowThreads)
+ln_modulate_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                   const __nv_bfloat16* __restrict__ ln_w, const __nv_bfloat16* __restrict__ ln_b,
+                   const __nv_bfloat16* __restrict__ shift, const __nv_bfloat16* __restrict__ scale,
+                   int64_t mod_frame_stride, int cols, int64_t tokens_per_frame, float eps) {
+    __shared__ float scratch[2 * 32];
+    const int64_t row = blockIdx.x;
+    const int nvec = cols >> 3;
+    const uint4* xr = reinterpret_cast<const uint4*>(x + row * cols);
+    float v[kMaxVecPerThread][8];
+    float acc[2] = {0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < kMaxVecPerThread; ++i) {
+        const int vi = threadIdx.x + i * kRowThreads;
+        if (vi < nvec) {
+            unpack8(xr[vi], v[i]);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[0] += v[i][e];
+        }
+    }
+    float s1[1] = {acc[0]};
+    block_sum<1>(s1, scratch);
+    const float mean = s1[0] / cols;
+    // two-pass variance (matches at::native RowwiseMoments to fp32 rounding)
+#pragma unroll
+    for (int i = 0; i < kMaxVecPerThread; ++i) {
+        const int vi = threadIdx.x + i * kRowThreads;
+        if (vi < nvec)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float d = v[i][e] - mean;
+                acc[1] += d * d;
+            }
+    }
+    float s2[1] = {acc[1]};
+    block_sum<1>(s2, scratch);
+    const float rstd = rsqrtf(s2[0] / cols + eps);
+
+    const int64_t frame = row / tokens_per_frame;
+    const uint4* sh = shift ? reinterpret_cast<const uint4*>(shift + frame * mod_frame_stride) : nullptr;
+    const uint4* sc = scale ? reinterpret_cast<const uint4*>(scale + frame * mod_frame_stride) : nullptr;
+    uint4* orow = reinterpret_cast<uint4*>(out + row * cols);
+#pragma unroll
+    for (int i = 0; i < kMaxVecPerThread; ++i) {
+        const int vi = threadIdx.x + i * kRowThreads;
+        if (vi < nvec) {
+            float y[8];
+            if (ln_w) {
+                float w[8], b[8];
+                unpack8(__ldg(reinterpret_cast<const uint4*>(ln_w) + vi), w);
+                unpack8(__ldg(reinterpret_cast<const uint4*>(ln_b) + vi), b);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) y[e] = bf16_round((v[i][e] - mean) * rstd * w[e] + b[e]);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) y[e] = bf16_round((v[i][e] - mean) * rstd);
+            }
+            if (sc) {
+                float a[8], b[8];
+                unpack8(__ldg(sc + vi), a);
+                unpack8(__ldg(sh + vi), b);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const float one_plus = bf16_round(1.0f + a[e]);
+                    y[e] = bf16_round(y[e] * one_plus) + b[e];  // final rounding happens in pack8
+                }
+            }
+            orow[vi] = pack8(y);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ WanRMSNorm
+__global__ void __launch_bounds__(kRowThreads)
+rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const __nv_bfloat16* __restrict__ w,
+               __nv_bfloat16* __restrict__ out, int64_t ldo, int cols, float eps) {
+    __shared__ float scratch[32];
+    const int64_t row = blockIdx.x;
+    const int nvec = cols >> 3;
+    const uint4* xr = reinterpret_cast<const uint4*>(x + row * ldx);
+    float v[kMaxVecPerThread][8];
+    float ss[1] = {0.f};
+#pragma unroll
+    for (int i = 0; i < kMaxVecPerThread; ++i) {
+        const int vi = threadIdx.x + i * kRowThreads;
+        if (vi < nvec) {
+            unpack8(xr[vi], v[i]);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) ss[0] += v[i][e] * v[i][e];
+        }
+    }
+    block_sum<1>(ss, scratch);
+    const float r = rsqrtf(ss[0] / cols + eps);
+    uint4* orow = reinterpret_cast<uint4*>(out + row * ldo);
+#pragma unroll
+    for (int i = 0; i < kMaxVecPerThread; ++i) {
+        const int vi = threadIdx.x + i * kRowThreads;
+        if (vi < nvec) {
+            float wv[8], y[8];
+            unpack8(__ldg(reinterpret_cast<const uint4*>(w) + vi), wv);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) y[e] = bf16_round(v[i][e] * r) * wv[e];
+            orow[vi] = pack8(y);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ QK RMSNorm + RoPE + KV append
+struct NormRopeParams {
+    const __nv_bfloat16* qkv;
+    int64_t ld_qkv;
+    const __nv_bfloat16* wq;
+    const __nv_bfloat16* wk;
+    const double2* freqs;  // [1024][hd/2] (cos, sin)
+    ifx_rope_grid grid;
+    __nv_bfloat16* q_out;
+    int64_t ld_q;
+    __nv_bfloat16* k_dst;  // cache base or contiguous staging
+    __nv_bfloat16* v_dst;
+    int32_t paged;         // 1: destination row = pages[t / page_tokens] * page_tokens + t % page_tokens
+    int32_t page_tokens;
+    PageList pl;
+    int32_t C, heads, head_dim;
+    float eps;
+};
+
+// pair index inside a head -> which RoPE axis it rotates with (causal_model.py:37: split [c-2(c/3), c/3, c/3])
+__device__ __forceinline__ int rope_pos(int pair, int half, int t_pos, int h_pos, int w_pos) {
+    const int third = half / 3;
+    const int n_t = half - 2 * third;
+    return pair < n_t ? t_pos : (pair < n_t + third ? h_pos : w_pos);
+}
+
+__global__ void __launch_bounds__(kRowThreads)
+qk_norm_rope_append_kernel(const NormRopeParams p) {
+    __shared__ float scratch[2 * 32];
+    const int64_t t = blockIdx.x;  // token row
+    const int C = p.C;
+    const int nvec = C >> 3;
+    const uint4* qr = reinterpret_cast<const uint4*>(p.qkv + t * p.ld_qkv);
+    const uint4* kr = reinterpret_cast<const uint4*>(p.qkv + t * p.ld_qkv + C);
+    const uint4* vr = reinterpret_cast<const uint4*>(p.qkv + t * p.ld_qkv + 2 * C);
+
+    // destination row in the cache
+    int64_t drow;
+    if (p.paged) {
+        const int pg = static_cast<int>(t / p.page_tokens);
+        drow = static_cast<int64_t>(p.pl.pages[pg]) * p.page_tokens + (t % p.page_tokens);
+    } else {
+        drow = t;
+    }
+    // (frame, h, w) of this token; under sequence parallelism the rank owns hw indices [hw_offset, +hw_count)
+    const int f = static_cast<int>(t / p.grid.hw_count);
+    const int hw = p.grid.hw_offset + static_cast<int>(t % p.grid.hw_count);
+    const int t_pos = p.grid.start_frame + f;
+    const int h_pos = hw / p.grid.width;
+    const int w_pos = hw % p.grid.width;
+
+    float q[kMaxVecPerThread][8], k[kMaxVecPerThread][8];
+    float ss[2] = {0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < kMaxVecPerThread; ++i) {
+        const int vi = threadIdx.x + i * kRowThreads;
+        if (vi < nvec) {
+            unpack8(qr[vi], q[i]);
+            unpack8(kr[vi], k[i]);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                ss[0] += q[i][e] * q[i][e];
+                ss[1] += k[i][e] * k[i][e];
+            }
+            // V is appended untouched
+            reinterpret_cast<uint4*>(p.v_dst + drow * C)[vi] = vr[vi];
+        }
+    }
+    block_sum<2>(ss, scratch);
+    const float rq = rsqrtf(ss[0] / C + p.eps);
+    const float rk = rsqrtf(ss[1] / C + p.eps);
+    const int half = p.head_dim >> 1;
+#pragma unroll
+    for (int i = 0; i < kMaxVecPerThread; ++i) {
+        const int vi = threadIdx.x + i * kRowThreads;
+        if (vi < nvec) {
+            float wq[8], wk[8], qo[8], ko[8];
+            unpack8(__ldg(reinterpret_cast<const uint4*>(p.wq) + vi), wq);
+            unpack8(__ldg(reinterpret_cast<const uint4*>(p.wk) + vi), wk);
+            const int col0 = vi * 8;
+            const int pair0 = (col0 % p.head_dim) >> 1;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int pair = pair0 + e;
+                const double2 cs = __ldg(&p.freqs[rope_pos(pair, half, t_pos, h_pos, w_pos) * half + pair]);
+                // RMSNorm: bf16(x * rsqrt) then bf16(.. * weight)  (components.py:118-126)
+                const double qa = bf16_round(bf16_round(q[i][2 * e] * rq) * wq[2 * e]);
+                const double qb = bf16_round(bf16_round(q[i][2 * e + 1] * rq) * wq[2 * e + 1]);
+                const double ka = bf16_round(bf16_round(k[i][2 * e] * rk) * wk[2 * e]);
+                const double kb = bf16_round(bf16_round(k[i][2 * e + 1] * rk) * wk[2 * e + 1]);
+                // complex multiply in fp64 (causal_model.py:46-56), rounded once to bf16
+                qo[2 * e] = static_cast<float>(qa * cs.x - qb * cs.y);
+                qo[2 * e + 1] = static_cast<float>(qa * cs.y + qb * cs.x);
+                ko[2 * e] = static_cast<float>(ka * cs.x - kb * cs.y);
+                ko[2 * e + 1] = static_cast<float>(ka * cs.y + kb * cs.x);
+            }
+            reinterpret_cast<uint4*>(p.q_out + t * p.ld_q)[vi] = pack8(qo);
+            reinterpret_cast<uint4*>(p.k_dst + drow * C)[vi] = pack8(ko);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ paged copy kernels (append / export / import)
+__global__ void __launch_bounds__(256)
+paged_copy_kernel(const PagedCopyParams p) {
+    const int nvec = p.C >> 3;
+    const int64_t total = p.rows * nvec;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t r = i / nvec;
+        const int vi = static_cast<int>(i % nvec);
+        const int64_t lt = p.first_logical + r;
+        const int64_t lp = lt / p.page_tokens;
+        const int phys = p.pl.pages[lp - p.first_logical / p.page_tokens];
+        const int64_t crow = static_cast<int64_t>(phys) * p.page_tokens + lt % p.page_tokens;
+        if (p.mode == 0) {
+            if (p.lin_k)
+                reinterpret_cast<uint4*>(p.cache_k + crow * p.C)[vi] =
+                    reinterpret_cast<const uint4*>(p.lin_k + r * p.ld_lin)[vi];
+            if (p.lin_v)
+                reinterpret_cast<uint4*>(p.cache_v + crow * p.C)[vi] =
+                    reinterpret_cast<const uint4*>(p.lin_v + r * p.ld_lin)[vi];
+        } else {
+            if (p.lin_k)
+                reinterpret_cast<uint4*>(p.lin_k + r * p.ld_lin)[vi] =
+                    reinterpret_cast<const uint4*>(p.cache_k + crow * p.C)[vi];
+            if (p.lin_v)
+                reinterpret_cast<uint4*>(p.lin_v + r * p.ld_lin)[vi] =
+                    reinterpret_cast<const uint4*>(p.cache_v + crow * p.C)[vi];
+        }
+    }
+}
+
+}  // namespace ifx
+
+using namespace ifx;
+
+extern "C" ifx_status ifx_ln_modulate(const void* x, void* out, const void* ln_weight, const void* ln_bias,
+                                      const void* shift, const void* scale, int64_t mod_frame_stride, int64_t rows,
+                                      int32_t cols, int64_t tokens_per_frame, float eps, void* stream) {
+    IFX_CHECK_ARG(x && out, "ifx_ln_modulate: null pointer");
+    IFX_CHECK_ARG(rows > 0 && cols > 0 && cols % 8 == 0 && cols <= kRowThreads * kMaxVecPerThread * 8,
+                  "ifx_ln_modulate: cols must be a multiple of 8 and <= %d (got %d)",
+                  kRowThreads * kMaxVecPerThread * 8, cols);
+    IFX_CHECK_ARG((ln_weight == nullptr) == (ln_bias == nullptr), "ifx_ln_modulate: weight and bias go together");
+    IFX_CHECK_ARG((shift == nullptr) == (scale == nullptr), "ifx_ln_modulate: shift and scale go together");
+    IFX_CHECK_ARG(!scale || (tokens_per_frame > 0 && mod_frame_stride % 8 == 0),
+                  "ifx_ln_modulate: bad modulation layout");
+    ln_modulate_kernel<<<static_cast<unsigned>(rows), kRowThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(out),
+        static_cast<const __nv_bfloat16*>(ln_weight), static_cast<const __nv_bfloat16*>(ln_bias),
+        static_cast<const __nv_bfloat16*>(shift), static_cast<const __nv_bfloat16*>(scale), mod_frame_stride, cols,
+        tokens_per_frame > 0 ? tokens_per_frame : 1, eps);
+    IFX_LAUNCH_OK("ln_modulate_kernel");
+    return IFX_OK;
+}
+
+extern "C" ifx_status ifx_rmsnorm(const void* x, int64_t ldx, const void* weight, void* out, int64_t ldo,
+                                  int64_t rows, int32_t cols, float eps, void* stream) {
+    IFX_CHECK_ARG(x && out && weight, "ifx_rmsnorm: null pointer");
+    IFX_CHECK_ARG(rows > 0 && cols > 0 && cols % 8 == 0 && cols <= kRowThreads * kMaxVecPerThread * 8,
+                  "ifx_rmsnorm: bad cols %d", cols);
+    IFX_CHECK_ARG(ldx % 8 == 0 && ldo % 8 == 0 && ldx >= cols && ldo >= cols, "ifx_rmsnorm: bad strides");
+    rmsnorm_kernel<<<static_cast<unsigned>(rows), kRowThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(x), ldx, static_cast<const __nv_bfloat16*>(weight),
+        static_cast<__nv_bfloat16*>(out), ldo, cols, eps);
+    IFX_LAUNCH_OK("rmsnorm_kernel");
+    return IFX_OK;
+}
+
+extern "C" ifx_status ifx_qk_norm_rope_append(const void* qkv, int64_t ld_qkv, const void* norm_q_weight,
+                                              const void* norm_k_weight, const double* freqs,
+                                              const ifx_rope_grid* grid, void* q_out, int64_t ld_q, ifx_kv* kv_,
+                                              const ifx_kv_plan* plan, void* k_dst, void* v_dst, int64_t rows,
+                                              int32_t heads, int32_t head_dim, float eps, void* stream) {
+    IFX_CHECK_ARG(qkv && norm_q_weight && norm_k_weight && freqs && grid && q_out, "ifx_qk_norm_rope_append: null");
+    const int C = heads * head_dim;
+    IFX_CHECK_ARG(rows > 0 && C % 8 == 0 && C <= kRowThreads * kMaxVecPerThread * 8 && head_dim % 8 == 0,
+                  "ifx_qk_norm_rope_append: bad shape heads=%d head_dim=%d", heads, head_dim);
+    IFX_CHECK_ARG(ld_qkv >= 3 * C && ld_qkv % 8 == 0 && ld_q >= C && ld_q % 8 == 0,
+                  "ifx_qk_norm_rope_append: bad strides");
+    IFX_CHECK_ARG(grid->hw_count > 0 && grid->width > 0 && rows == (int64_t)grid->frames * grid->hw_count,
+                  "ifx_qk_norm_rope_append: rows (%lld) != frames*hw_count (%d*%d)", (long long)rows, grid->frames,
+                  grid->hw_count);
+    IFX_CHECK_ARG(grid->start_frame >= 0 && grid->start_frame + grid->frames <= 1024 && grid->height <= 1024 &&
+                      grid->width <= 1024,
+                  "ifx_qk_norm_rope_append: RoPE table has 1024 positions");
+    NormRopeParams p;
+    p.qkv = static_cast<const __nv_bfloat16*>(qkv);
+    p.ld_qkv = ld_qkv;
+    p.wq = static_cast<const __nv_bfloat16*>(norm_q_weight);
+    p.wk = static_cast<const __nv_bfloat16*>(norm_k_weight);
+    p.freqs = reinterpret_cast<const double2*>(freqs);
+    p.grid = *grid;
+    p.q_out = static_cast<__nv_bfloat16*>(q_out);
+    p.ld_q = ld_q;
+    p.C = C;
+    p.heads = heads;
+    p.head_dim = head_dim;
+    p.eps = eps;
+    if (kv_ != nullptr) {
+        KvImpl* kv = kv_cast(kv_);
+        if (!kv) return set_error(IFX_ERR_HANDLE, "ifx_qk_norm_rope_append: bad kv handle");
+        IFX_CHECK_ARG(plan != nullptr, "ifx_qk_norm_rope_append: plan required with kv");
+        IFX_CHECK_ARG(kv->heads == heads && kv->head_dim == head_dim, "ifx_qk_norm_rope_append: kv shape mismatch");
+        IFX_CHECK_ARG(plan->local_end - plan->local_start == rows, "ifx_qk_norm_rope_append: plan covers %lld rows",
+                      (long long)(plan->local_end - plan->local_start));
+        IFX_CHECK_ARG((int64_t)plan->num_pages * kv->page_tokens == rows && plan->first_offset == 0,
+                      "ifx_qk_norm_rope_append: append must be page aligned");
+        p.k_dst = static_cast<__nv_bfloat16*>(kv->k_base);
+        p.v_dst = static_cast<__nv_bfloat16*>(kv->v_base);
+        p.paged = 1;
+        p.page_tokens = kv->page_tokens;
+        p.pl.n = plan->num_pages;
+        for (int i = 0; i < plan->num_pages; ++i) p.pl.pages[i] = plan->pages[i];
+    } else {
+        IFX_CHECK_ARG(k_dst && v_dst, "ifx_qk_norm_rope_append: need kv or k_dst/v_dst");
+        p.k_dst = static_cast<__nv_bfloat16*>(k_dst);
+        p.v_dst = static_cast<__nv_bfloat16*>(v_dst);
+        p.paged = 0;
+        p.page_tokens = 1;
+        p.pl.n = 0;
+    }
+    qk_norm_rope_append_kernel<<<static_cast<unsigned>(rows), kRowThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    IFX_LAUNCH_OK("qk_norm_rope_append_kernel");
+    return IFX_OK;
+}
+
+namespace ifx {
+ifx_status launch_paged_copy(const PagedCopyParams& p, cudaStream_t stream) {
+    const int64_t total = p.rows * (p.C >> 3);
+    int64_t blocks = (total + 255) / 256;
+    const int64_t cap = static_cast<int64_t>(sm_count()) * 16;
+    if (blocks > cap) blocks = cap;
+    paged_copy_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(p);
+    IFX_LAUNCH_OK("paged_copy_kernel");
+    return IFX_OK;
+}
+}  // namespace ifx
+
+extern "C" ifx_status ifx_kv_append(ifx_kv* kv_, const ifx_kv_plan* plan, const void* k_src, const void* v_src,
+                                    int64_t ld_src, int64_t rows, void* stream) {
+    KvImpl* kv = kv_cast(kv_);
+    if (!kv) return set_error(IFX_ERR_HANDLE, "ifx_kv_append: bad kv handle");
+    IFX_CHECK_ARG(plan && (k_src || v_src), "ifx_kv_append: null pointer");
+    const int C = kv->heads * kv->head_dim;
+    IFX_CHECK_ARG(ld_src >= C && ld_src % 8 == 0, "ifx_kv_append: bad stride");
+    IFX_CHECK_ARG(rows == plan->local_end - plan->local_start && rows == (int64_t)plan->num_pages * kv->page_tokens,
+                  "ifx_kv_append: rows do not match plan");
+    PagedCopyParams p;
+    p.cache_k = static_cast<__nv_bfloat16*>(kv->k_base);
+    p.cache_v = static_cast<__nv_bfloat16*>(kv->v_base);
+    p.lin_k = const_cast<__nv_bfloat16*>(static_cast<const __nv_bfloat16*>(k_src));
+    p.lin_v = const_cast<__nv_bfloat16*>(static_cast<const __nv_bfloat16*>(v_src));
+    p.ld_lin = ld_src;
+    p.rows = rows;
+    p.first_logical = 0;
+    p.page_tokens = kv->page_tokens;
+    p.C = C;
+    p.mode = 0;
+    p.pl.n = plan->num_pages;
+    for (int i = 0; i < plan->num_pages; ++i) p.pl.pages[i] = plan->pages[i];
+    return launch_paged_copy(p, static_cast<cudaStream_t>(stream));
+}

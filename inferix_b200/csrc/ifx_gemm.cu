@@ -1,0 +1,299 @@
+// out[M,N] = epilogue(A[M,K] @ W[N,K]^T)   bf16 in, fp32 accumulate in TMEM, bf16 out.
+//
+// Persistent warp-specialised tcgen05 GEMM for sm_100a:
+//   warp 0      TMA producer  (cp.async.bulk.tensor 2D, SWIZZLE_128B, kStages-deep mbarrier ring)
+//   warp 1      MMA issuer    (one thread, tcgen05.mma.cta_group::1.kind::f16, 128 x 256 x 16 per instruction)
+//   warp 2      TMEM allocator (512 columns = two 128x256 fp32 accumulators, double-buffered)
+//   warps 4..7  epilogue      (tcgen05.ld 32x32b -> registers -> bias / GELU / gate+residual -> 16-byte stores)
+// The epilogue of tile i overlaps the main loop of tile i+1 through the second TMEM accumulator.
+//
+// Replaces the cuBLAS nn.Linear calls + eager elementwise ops of the reference block
+// (inferix/models/self_forcing/causal_model.py:171-175,333,378-379,444,455-456; wan_base/model.py:77,98).
+#include "ifx_internal.h"
+#include "ifx_ptx.cuh"
+
+namespace ifx {
+
+constexpr int kBM = 128;
+constexpr int kBN = 256;
+constexpr int kBK = 64;  // 64 bf16 = 128 bytes = one swizzle atom row
+constexpr int kStages = 4;
+constexpr int kABytes = kBM * kBK * 2;  // 16 KiB
+constexpr int kBBytes = kBN * kBK * 2;  // 32 KiB
+constexpr int kStageBytes = kABytes + kBBytes;
+constexpr int kGemmThreads = 256;
+constexpr int kGemmSmem = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+
+struct GemmParams {
+    int64_t M;
+    int32_t N, K;
+    const __nv_bfloat16* bias;
+    __nv_bfloat16* out;
+    int64_t ldo;
+    const __nv_bfloat16* residual;
+    int64_t ldr;
+    const __nv_bfloat16* gate;
+    int64_t gate_frame_stride;
+    int64_t tokens_per_frame;
+    int32_t num_m_tiles, num_n_tiles;
+};
+
+__device__ __forceinline__ float gelu_tanh_f(float x) {
+    // 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3))), tanh(u) = 1 - 2 / (1 + e^{2u})
+    const float kBeta = 0.7978845608028654f;
+    const float kKappa = 0.044715f;
+    float u = kBeta * (x + kKappa * x * x * x);
+    float e = __expf(2.0f * u);
+    float t = 1.0f - __fdividef(2.0f, 1.0f + e);
+    return 0.5f * x * (1.0f + t);
+}
+
+template <int kEpi>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    // SWIZZLE_128B tiles need 1024-byte alignment
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + kStages * kABytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+    uint64_t* full = bars;                    // [kStages]
+    uint64_t* empty = bars + kStages;         // [kStages]
+    uint64_t* tmem_full = bars + 2 * kStages; // [2]
+    uint64_t* tmem_empty = tmem_full + 2;     // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+    const int num_kb = (p.K + kBK - 1) / kBK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < kStages; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full[i], 1);
+            mbar_init(&tmem_empty[i], 128);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m_blk = tile / p.num_n_tiles;
+                const int n_blk = tile % p.num_n_tiles;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    mbar_expect_tx(&full[stage], kStageBytes);
+                    tma_load_2d(sA + stage * kABytes, &tmA, &full[stage], kb * kBK, m_blk * kBM);
+                    tma_load_2d(sB + stage * kBBytes, &tmB, &full[stage], kb * kBK, n_blk * kBN);
+                    if (++stage == kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(kBM, kBN, 0, 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                const int as = it & 1;
+                const uint32_t aphase = (it >> 1) & 1;
+                mbar_wait(&tmem_empty[as], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * kBN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint64_t adesc = make_smem_desc_sw128(smem_u32(sA + stage * kABytes), 16, 1024);
+                    const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sB + stage * kBBytes), 16, 1024);
+#pragma unroll
+                    for (int k = 0; k < kBK / 16; ++k) {
+                        // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the (addr >> 4) field
+                        umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                    }
+                    umma_commit(&empty[stage]);
+                    if (++stage == kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                umma_commit(&tmem_full[as]);
+            }
+        }
+    } else if (warp >= 4) {
+        const int q = warp & 3;  // TMEM lane quadrant this warp may access
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            const int m_blk = tile / p.num_n_tiles;
+            const int n_blk = tile % p.num_n_tiles;
+            const int64_t row = static_cast<int64_t>(m_blk) * kBM + q * 32 + lane;
+            const bool row_ok = row < p.M;
+            const __nv_bfloat16* gate_row = nullptr;
+            if (kEpi == IFX_EPI_BIAS_GATE_RES && p.gate != nullptr && row_ok)
+                gate_row = p.gate + (row / p.tokens_per_frame) * p.gate_frame_stride;
+
+            mbar_wait(&tmem_full[as], aphase);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kBN;
+#pragma unroll 1
+            for (int c = 0; c < kBN / 32; ++c) {
+                const int col0 = n_blk * kBN + c * 32;
+                if (col0 >= p.N) break;  // warp-uniform
+                uint32_t acc[32];
+                tmem_ld32(t_row + c * 32, acc);
+                tmem_wait_ld();
+                if (row_ok) {
+                    __nv_bfloat16* optr = p.out + row * p.ldo + col0;
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) {
+                        if (col0 + v * 8 >= p.N) break;
+                        float bv[8];
+                        {
+                            uint4 braw = p.bias ? __ldg(reinterpret_cast<const uint4*>(p.bias + col0 + v * 8))
+                                                : make_uint4(0, 0, 0, 0);
+                            const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&braw);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                float2 f = __bfloat1622float2(b2[e]);
+                                bv[2 * e] = f.x;
+                                bv[2 * e + 1] = f.y;
+                            }
+                        }
+                        float val[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) val[e] = bf16_round(__uint_as_float(acc[v * 8 + e]) + bv[e]);
+                        if (kEpi == IFX_EPI_BIAS_GELU) {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) val[e] = gelu_tanh_f(val[e]);
+                        }
+                        if (kEpi == IFX_EPI_BIAS_GATE_RES) {
+                            if (gate_row != nullptr) {
+                                uint4 graw = __ldg(reinterpret_cast<const uint4*>(gate_row + col0 + v * 8));
+                                const __nv_bfloat162* g2 = reinterpret_cast<const __nv_bfloat162*>(&graw);
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    float2 f = __bfloat1622float2(g2[e]);
+                                    val[2 * e] = bf16_round(val[2 * e] * f.x);
+                                    val[2 * e + 1] = bf16_round(val[2 * e + 1] * f.y);
+                                }
+                            }
+                            uint4 rraw = *reinterpret_cast<const uint4*>(p.residual + row * p.ldr + col0 + v * 8);
+                            const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rraw);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                float2 f = __bfloat1622float2(r2[e]);
+                                val[2 * e] = f.x + val[2 * e];
+                                val[2 * e + 1] = f.y + val[2 * e + 1];
+                            }
+                        }
+                        uint4 o;
+                        o.x = pack_bf16x2(val[0], val[1]);
+                        o.y = pack_bf16x2(val[2], val[3]);
+                        o.z = pack_bf16x2(val[4], val[5]);
+                        o.w = pack_bf16x2(val[6], val[7]);
+                        *reinterpret_cast<uint4*>(optr + v * 8) = o;
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tmem_empty[as]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+template <int kEpi>
+static ifx_status launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p,
+                              cudaStream_t stream) {
+    static bool configured = false;
+    if (!configured) {
+        IFX_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tn_kernel<kEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         kGemmSmem));
+        configured = true;
+    }
+    const int tiles = p.num_m_tiles * p.num_n_tiles;
+    const int grid = tiles < sm_count() ? tiles : sm_count();
+    gemm_bf16_tn_kernel<kEpi><<<grid, kGemmThreads, kGemmSmem, stream>>>(tmA, tmB, p);
+    IFX_LAUNCH_OK("gemm_bf16_tn_kernel");
+    return IFX_OK;
+}
+
+}  // namespace ifx
+
+using namespace ifx;
+
+extern "C" ifx_status ifx_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias,
+                                    void* out, int64_t ldo, int64_t M, int32_t N, int32_t K, int32_t epilogue,
+                                    const void* residual, int64_t ldr, const void* gate, int64_t gate_frame_stride,
+                                    int64_t tokens_per_frame, void* stream) {
+    IFX_CHECK_ARG(A && W && out, "ifx_gemm_bf16: null pointer");
+    IFX_CHECK_ARG(M > 0 && N > 0 && K > 0, "ifx_gemm_bf16: empty problem M=%lld N=%d K=%d", (long long)M, N, K);
+    IFX_CHECK_ARG(N % 8 == 0 && K % 8 == 0, "ifx_gemm_bf16: N and K must be multiples of 8 (N=%d K=%d)", N, K);
+    IFX_CHECK_ARG(lda % 8 == 0 && ldw % 8 == 0 && ldo % 8 == 0, "ifx_gemm_bf16: strides must be multiples of 8");
+    IFX_CHECK_ARG(lda >= K && ldw >= K && ldo >= N, "ifx_gemm_bf16: stride smaller than row");
+    IFX_CHECK_ARG(epilogue >= IFX_EPI_BIAS && epilogue <= IFX_EPI_BIAS_GATE_RES, "ifx_gemm_bf16: bad epilogue %d",
+                  epilogue);
+    if (epilogue == IFX_EPI_BIAS_GATE_RES) {
+        IFX_CHECK_ARG(residual != nullptr && ldr >= N && ldr % 8 == 0, "ifx_gemm_bf16: residual required");
+        IFX_CHECK_ARG(gate == nullptr || tokens_per_frame > 0, "ifx_gemm_bf16: tokens_per_frame must be > 0");
+    }
+    auto aligned16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    IFX_CHECK_ARG(aligned16(A) && aligned16(W) && aligned16(out) && aligned16(bias) && aligned16(residual) &&
+                      aligned16(gate),
+                  "ifx_gemm_bf16: pointers must be 16-byte aligned");
+
+    CUtensorMap tmA, tmB;
+    ifx_status st = make_tmap_bf16_2d(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, kBK, kBM);
+    if (st != IFX_OK) return st;
+    st = make_tmap_bf16_2d(&tmB, W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw, kBK, kBN);
+    if (st != IFX_OK) return st;
+
+    GemmParams p;
+    p.M = M;
+    p.N = N;
+    p.K = K;
+    p.bias = static_cast<const __nv_bfloat16*>(bias);
+    p.out = static_cast<__nv_bfloat16*>(out);
+    p.ldo = ldo;
+    p.residual = static_cast<const __nv_bfloat16*>(residual);
+    p.ldr = ldr;
+    p.gate = static_cast<const __nv_bfloat16*>(gate);
+    p.gate_frame_stride = gate_frame_stride;
+    p.tokens_per_frame = tokens_per_frame > 0 ? tokens_per_frame : 1;
+    p.num_m_tiles = static_cast<int32_t>((M + kBM - 1) / kBM);
+    p.num_n_tiles = (N + kBN - 1) / kBN;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    switch (epilogue) {
+        case IFX_EPI_BIAS: return launch_gemm<IFX_EPI_BIAS>(tmA, tmB, p, s);
+        case IFX_EPI_BIAS_GELU: return launch_gemm<IFX_EPI_BIAS_GELU>(tmA, tmB, p, s);
+        default: return launch_gemm<IFX_EPI_BIAS_GATE_RES>(tmA, tmB, p, s);
+    }
+}

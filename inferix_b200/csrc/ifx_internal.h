@@ -1,0 +1,86 @@
+// Internal host-side helpers shared by the .cu translation units (not part of the ABI).
+#pragma once
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <vector>
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "../../include/inferix_b200.h"
+
+namespace ifx {
+
+// thread-local error text; set_error returns `code` so call sites can `return set_error(...)`.
+ifx_status set_error(ifx_status code, const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define IFX_CHECK_ARG(cond, ...)                                  \
+    do {                                                          \
+        if (!(cond)) return ::ifx::set_error(IFX_ERR_INVALID, __VA_ARGS__); \
+    } while (0)
+
+#define IFX_CUDA_OK(expr)                                                                             \
+    do {                                                                                              \
+        cudaError_t _e = (expr);                                                                      \
+        if (_e != cudaSuccess)                                                                        \
+            return ::ifx::set_error(IFX_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e));    \
+    } while (0)
+
+// After a kernel launch: surfaces launch-configuration errors without synchronising.
+#define IFX_LAUNCH_OK(name)                                                                          \
+    do {                                                                                             \
+        cudaError_t _e = cudaGetLastError();                                                         \
+        if (_e != cudaSuccess)                                                                       \
+            return ::ifx::set_error(IFX_ERR_CUDA, "launch %s failed: %s", name, cudaGetErrorString(_e)); \
+        ::ifx::count_launch();                                                                       \
+    } while (0)
+
+// 2-D bf16 tensor map, 128-byte swizzle, box = [box_rows, 64 elements].
+ifx_status make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t inner_elems, uint64_t outer_rows,
+                             uint64_t row_stride_elems, uint32_t box_inner, uint32_t box_rows);
+
+int sm_count();
+
+struct KvImpl {
+    uint32_t magic;
+    void* k_base;
+    void* v_base;
+    int32_t num_pages;
+    int32_t page_tokens;
+    int32_t heads;
+    int32_t head_dim;
+    int64_t global_end;
+    int64_t local_end;
+    std::vector<int32_t> table;      // logical page -> physical page, size = ceil(local_end / page_tokens)
+    std::vector<int32_t> free_pages; // recycled pages, reused LIFO-last (FIFO order) before fresh ones
+    int32_t next_fresh;              // physical pages [0, next_fresh) have been handed out at least once
+};
+// by-value page list handed to kernels (no device-side table, no host sync)
+struct PageList {
+    int32_t n;
+    int32_t pages[IFX_KV_MAX_PLAN_PAGES];
+};
+// mode 0: contiguous rows -> cache pages (append / import); mode 1: cache pages -> contiguous rows (export)
+struct PagedCopyParams {
+    __nv_bfloat16* cache_k;
+    __nv_bfloat16* cache_v;
+    __nv_bfloat16* lin_k;  // contiguous side (either may be null)
+    __nv_bfloat16* lin_v;
+    int64_t ld_lin;
+    int64_t rows;           // rows in this launch
+    int64_t first_logical;  // logical token index of row 0
+    int32_t page_tokens;
+    int32_t C;
+    int32_t mode;
+    PageList pl;            // pages[i] backs logical page (first_logical / page_tokens + i)
+};
+ifx_status launch_paged_copy(const PagedCopyParams& p, cudaStream_t stream);
+
+constexpr uint32_t kKvMagic = 0x4B564958u;  // "XIVK"
+KvImpl* kv_cast(ifx_kv* kv);
+const KvImpl* kv_cast(const ifx_kv* kv);
+
+}  // namespace ifx

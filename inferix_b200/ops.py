@@ -1,0 +1,232 @@
+"""Torch-tensor front end of the C ABI: validates dtype / layout, passes raw pointers and the current stream.
+
+PyTorch is used for device memory and streams only; every function below runs a hand-written sm_100a kernel
+from ``libinferix_b200.so`` and raises if the library or a CUDA device is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import EPI_BIAS, EPI_BIAS_GATE_RES, EPI_BIAS_GELU, KvPlan, RopeGrid
+
+__all__ = [
+    "ln_modulate", "gemm", "rmsnorm", "attention", "qk_norm_rope_append", "PagedKV", "rope_table",
+    "EPI_BIAS", "EPI_BIAS_GELU", "EPI_BIAS_GATE_RES",
+]
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _bf16_2d(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise ValueError(f"{name}: expected a CUDA tensor (inferix_b200 has no CPU path)")
+    if t.dtype != torch.bfloat16:
+        raise ValueError(f"{name}: expected bfloat16, got {t.dtype}")
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise ValueError(f"{name}: expected a 2-D tensor with unit inner stride, got {tuple(t.shape)}/{t.stride()}")
+    return t
+
+
+def _bf16_vec(t: Optional[torch.Tensor], n: int, name: str) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    if not t.is_cuda or t.dtype != torch.bfloat16 or t.numel() != n or not t.is_contiguous():
+        raise ValueError(f"{name}: expected a contiguous CUDA bfloat16 vector of {n} elements")
+    return t
+
+
+def rope_table(freqs: torch.Tensor, device) -> torch.Tensor:
+    """complex128 [1024, D/2] (CausalWanModel.freqs) -> float64 [1024, D/2, 2] (cos, sin) on `device`."""
+    if freqs.dtype != torch.complex128:
+        raise ValueError("freqs must be complex128 as built by rope_params")
+    return torch.view_as_real(freqs).contiguous().to(device)
+
+
+def ln_modulate(x, out=None, *, weight=None, bias=None, shift=None, scale=None, tokens_per_frame=0, eps=1e-6):
+    """LayerNorm (+affine) (+AdaLN modulate).  shift/scale: [frames, C] views with a common frame stride."""
+    x = _bf16_2d(x, "x")
+    if not x.is_contiguous():
+        raise ValueError("x must be contiguous")
+    rows, cols = x.shape
+    out = torch.empty_like(x) if out is None else _bf16_2d(out, "out")
+    stride = 0
+    if scale is not None:
+        if shift is None or scale.shape != shift.shape or scale.dim() != 2 or scale.shape[1] != cols:
+            raise ValueError("shift/scale must both be [frames, C]")
+        if scale.stride(1) != 1 or shift.stride(1) != 1 or scale.stride(0) != shift.stride(0):
+            raise ValueError("shift/scale must share a frame stride and have unit inner stride")
+        if rows != scale.shape[0] * tokens_per_frame:
+            raise ValueError("rows != frames * tokens_per_frame")
+        stride = scale.stride(0)
+    _lib.check(_lib.load().ifx_ln_modulate(
+        x.data_ptr(), out.data_ptr(), _ptr(_bf16_vec(weight, cols, "weight")), _ptr(_bf16_vec(bias, cols, "bias")),
+        _ptr(shift), _ptr(scale), stride, rows, cols, tokens_per_frame, eps, _stream()))
+    return out
+
+
+def gemm(a, w, bias=None, out=None, *, epilogue=EPI_BIAS, residual=None, gate=None, tokens_per_frame=0):
+    """out = epilogue(a @ w.T + bias); a [M,K], w [N,K] (nn.Linear layout), gate [frames, N] or None."""
+    a = _bf16_2d(a, "a")
+    w = _bf16_2d(w, "w")
+    M, K = a.shape
+    N = w.shape[0]
+    if w.shape[1] != K:
+        raise ValueError(f"gemm: a is [{M},{K}] but w is {tuple(w.shape)}")
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+    out = _bf16_2d(out, "out")
+    gstride = 0
+    if gate is not None:
+        if gate.dim() != 2 or gate.shape[1] != N or gate.stride(1) != 1:
+            raise ValueError("gate must be [frames, N] with unit inner stride")
+        gstride = gate.stride(0)
+    if residual is not None:
+        residual = _bf16_2d(residual, "residual")
+    _lib.check(_lib.load().ifx_gemm_bf16(
+        a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), _ptr(_bf16_vec(bias, N, "bias")), out.data_ptr(),
+        out.stride(0), M, N, K, epilogue, _ptr(residual), residual.stride(0) if residual is not None else 0,
+        _ptr(gate), gstride, tokens_per_frame, _stream()))
+    return out
+
+
+def rmsnorm(x, weight, out=None, *, eps=1e-6):
+    x = _bf16_2d(x, "x")
+    rows, cols = x.shape
+    out = torch.empty((rows, cols), dtype=torch.bfloat16, device=x.device) if out is None else _bf16_2d(out, "out")
+    _lib.check(_lib.load().ifx_rmsnorm(x.data_ptr(), x.stride(0), _bf16_vec(weight, cols, "weight").data_ptr(),
+                                       out.data_ptr(), out.stride(0), rows, cols, eps, _stream()))
+    return out
+
+
+def attention(q, k, v, heads, out=None, *, softmax_scale=None):
+    """q [Lq, H*D], k/v [Lk, H*D] (same row stride) -> [Lq, H*D]; full (non-causal) softmax attention."""
+    q = _bf16_2d(q, "q")
+    k = _bf16_2d(k, "k")
+    v = _bf16_2d(v, "v")
+    width = q.shape[1]
+    if k.shape != v.shape or k.shape[1] != width or k.stride(0) != v.stride(0):
+        raise ValueError("attention: k and v must have identical shape/stride and match q's width")
+    head_dim = width // heads
+    if out is None:
+        out = torch.empty((q.shape[0], width), dtype=torch.bfloat16, device=q.device)
+    scale = softmax_scale if softmax_scale is not None else head_dim ** -0.5
+    _lib.check(_lib.load().ifx_attention(q.data_ptr(), q.stride(0), k.data_ptr(), v.data_ptr(), k.stride(0),
+                                         out.data_ptr(), out.stride(0), q.shape[0], k.shape[0], heads, head_dim,
+                                         scale, _stream()))
+    return out
+
+
+class PagedKV:
+    """One layer's self-attention cache: two bf16 buffers + the native block table (ifx_kv)."""
+
+    def __init__(self, num_pages: int, page_tokens: int, heads: int, head_dim: int, device):
+        self.num_pages, self.page_tokens, self.heads, self.head_dim = num_pages, page_tokens, heads, head_dim
+        width = heads * head_dim
+        # like the reference (torch.empty, kvcache_manager.py:232) the memory starts uninitialised
+        self.k = torch.empty((num_pages * page_tokens, width), dtype=torch.bfloat16, device=device)
+        self.v = torch.empty_like(self.k)
+        h = C.c_void_p()
+        _lib.check(_lib.load().ifx_kv_create(C.byref(h), self.k.data_ptr(), self.v.data_ptr(), num_pages, page_tokens,
+                                             heads, head_dim))
+        self._h = h
+
+    @property
+    def handle(self) -> int:
+        if self._h is None:
+            raise KeyError("PagedKV has been freed")
+        return self._h.value
+
+    def free(self) -> None:
+        if self._h is not None:
+            _lib.check(_lib.load().ifx_kv_destroy(self._h))
+            self._h = None
+            self.k = self.v = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    def reset(self) -> None:
+        _lib.check(_lib.load().ifx_kv_reset(self.handle))
+
+    def plan_append(self, current_start: int, num_new: int, sink_tokens: int = 0, windowed: bool = True) -> KvPlan:
+        plan = KvPlan()
+        _lib.check(_lib.load().ifx_kv_plan_append(self.handle, current_start, num_new, sink_tokens, int(windowed),
+                                                  C.byref(plan)))
+        return plan
+
+    def state(self):
+        g, l, n = C.c_int64(), C.c_int64(), C.c_int32()
+        table = (C.c_int32 * self.num_pages)()
+        _lib.check(_lib.load().ifx_kv_state(self.handle, C.byref(g), C.byref(l), C.byref(n), table, self.num_pages))
+        return g.value, l.value, list(table[: n.value])
+
+    def append(self, plan: KvPlan, k_rows: torch.Tensor, v_rows: torch.Tensor) -> None:
+        k_rows, v_rows = _bf16_2d(k_rows, "k_rows"), _bf16_2d(v_rows, "v_rows")
+        if k_rows.stride(0) != v_rows.stride(0) or k_rows.shape != v_rows.shape:
+            raise ValueError("k_rows / v_rows must share shape and stride")
+        _lib.check(_lib.load().ifx_kv_append(self.handle, C.byref(plan), k_rows.data_ptr(), v_rows.data_ptr(),
+                                             k_rows.stride(0), k_rows.shape[0], _stream()))
+
+    def export(self, start: int, length: int):
+        """Tokens [start, start+length) in the reference's logical order -> (k, v) each [length, H*D]."""
+        width = self.heads * self.head_dim
+        k = torch.empty((length, width), dtype=torch.bfloat16, device=self.k.device)
+        v = torch.empty_like(k)
+        _lib.check(_lib.load().ifx_kv_export(self.handle, k.data_ptr(), v.data_ptr(), start, length, _stream()))
+        return k, v
+
+    def import_(self, start: int, k_rows: torch.Tensor, v_rows: torch.Tensor) -> None:
+        k_rows, v_rows = _bf16_2d(k_rows, "k_rows"), _bf16_2d(v_rows, "v_rows")
+        if not (k_rows.is_contiguous() and v_rows.is_contiguous()) or k_rows.shape != v_rows.shape:
+            raise ValueError("import_: contiguous [length, H*D] tensors expected")
+        _lib.check(_lib.load().ifx_kv_import(self.handle, k_rows.data_ptr(), v_rows.data_ptr(), start,
+                                             k_rows.shape[0], _stream()))
+
+    def attention(self, q: torch.Tensor, out=None, *, softmax_scale=None):
+        q = _bf16_2d(q, "q")
+        if out is None:
+            out = torch.empty((q.shape[0], self.heads * self.head_dim), dtype=torch.bfloat16, device=q.device)
+        scale = softmax_scale if softmax_scale is not None else self.head_dim ** -0.5
+        _lib.check(_lib.load().ifx_attention_kv(q.data_ptr(), q.stride(0), self.handle, out.data_ptr(), out.stride(0),
+                                                q.shape[0], scale, _stream()))
+        return out
+
+
+def qk_norm_rope_append(qkv, norm_q_w, norm_k_w, freqs_table, grid: RopeGrid, heads, head_dim, *, kv: PagedKV = None,
+                        plan: KvPlan = None, q_out=None, k_out=None, v_out=None, eps=1e-6):
+    """Fused QK-RMSNorm + RoPE + append.  With kv/plan the K/V rows land in the cache pages; otherwise in
+    k_out/v_out (contiguous staging for the sequence-parallel all-gather)."""
+    qkv = _bf16_2d(qkv, "qkv")
+    rows = qkv.shape[0]
+    C_ = heads * head_dim
+    if qkv.shape[1] != 3 * C_:
+        raise ValueError("qkv must be [rows, 3*heads*head_dim]")
+    if freqs_table.dtype != torch.float64 or not freqs_table.is_cuda or not freqs_table.is_contiguous():
+        raise ValueError("freqs_table: use ops.rope_table(model.freqs, device)")
+    if q_out is None:
+        q_out = torch.empty((rows, C_), dtype=torch.bfloat16, device=qkv.device)
+    if kv is None:
+        if k_out is None:
+            k_out = torch.empty((rows, C_), dtype=torch.bfloat16, device=qkv.device)
+            v_out = torch.empty_like(k_out)
+        if not (k_out.is_contiguous() and v_out.is_contiguous()):
+            raise ValueError("k_out / v_out must be contiguous")
+    _lib.check(_lib.load().ifx_qk_norm_rope_append(
+        qkv.data_ptr(), qkv.stride(0), _bf16_vec(norm_q_w, C_, "norm_q").data_ptr(),
+        _bf16_vec(norm_k_w, C_, "norm_k").data_ptr(), freqs_table.data_ptr(), C.byref(grid), q_out.data_ptr(),
+        q_out.stride(0), kv.handle if kv is not None else None, C.byref(plan) if plan is not None else None,
+        _ptr(k_out), _ptr(v_out), rows, heads, head_dim, eps, _stream()))
+    return q_out, k_out, v_out

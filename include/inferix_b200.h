@@ -41,6 +41,15 @@ int ifx_abi_version(void);
 uint64_t ifx_launch_count(void);
 void ifx_reset_launch_count(void);
 
+/* Optional per-kernel device timing for bench.py's roofline line: when enabled every kernel launch of this library
+ * is bracketed by two cudaEvents on the launch stream.  ifx_prof_read synchronises those events and returns the
+ * summed duration and launch count of all kernels whose label starts with `prefix` ("" = everything);
+ * ifx_prof_labels writes the distinct labels seen, '\n'-separated.  Off by default (no events, no overhead). */
+void ifx_prof_enable(int32_t on);
+void ifx_prof_reset(void);
+ifx_status ifx_prof_read(const char* prefix, double* total_ms, uint64_t* launches);
+ifx_status ifx_prof_labels(char* buf, int32_t cap);
+
 /* ------------------------------------------------------------------------------------------------
  * Paged KV cache with a frame-aligned block table.
  *
@@ -143,6 +152,12 @@ ifx_status ifx_qk_norm_rope_append(const void* qkv, int64_t ld_qkv, const void* 
 /* Copy already-normalised K / V rows (e.g. all-gathered from peers) into the pages named by `plan`. */
 ifx_status ifx_kv_append(ifx_kv* kv, const ifx_kv_plan* plan, const void* k_src, const void* v_src, int64_t ld_src,
                          int64_t rows, void* stream);
+
+/* Sequence-parallel append: k_src / v_src hold the all-gathered new rows rank-major, [world, frames*chunk, H*D]
+ * (rank r owns hw indices [r*chunk, (r+1)*chunk) of every frame, causal_model.py:939-942); they are written in the
+ * single-process token order (frame, rank, hw) == 'b (cp f hw) c -> b (f cp hw) c' of causal_model.py:1018. */
+ifx_status ifx_kv_append_sp(ifx_kv* kv, const ifx_kv_plan* plan, const void* k_src, const void* v_src,
+                            int32_t world, int32_t frames, int32_t chunk, void* stream);
 
 /* WanRMSNorm on its own (cross-attention q / text k, wan_base/model.py:77,82): out = bf16(bf16(x*rsqrt(ms+eps))*w) */
 ifx_status ifx_rmsnorm(const void* x, int64_t ldx, const void* weight, void* out, int64_t ldo, int64_t rows,

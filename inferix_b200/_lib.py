@@ -82,6 +82,10 @@ SIGNATURES = {
     "ifx_abi_version": (C.c_int, []),
     "ifx_launch_count": (C.c_uint64, []),
     "ifx_reset_launch_count": (None, []),
+    "ifx_prof_enable": (None, [_i32]),
+    "ifx_prof_reset": (None, []),
+    "ifx_prof_read": (C.c_int, [C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
+    "ifx_prof_labels": (C.c_int, [C.c_char_p, _i32]),
     "ifx_kv_create": (C.c_int, [C.POINTER(_vp), _vp, _vp, _i32, _i32, _i32, _i32]),
     "ifx_kv_destroy": (C.c_int, [_vp]),
     "ifx_kv_reset": (C.c_int, [_vp]),
@@ -95,6 +99,7 @@ SIGNATURES = {
     "ifx_qk_norm_rope_append": (C.c_int, [_vp, _i64, _vp, _vp, _vp, C.POINTER(RopeGrid), _vp, _i64, _vp,
                                           C.POINTER(KvPlan), _vp, _vp, _i64, _i32, _i32, _f32, _vp]),
     "ifx_kv_append": (C.c_int, [_vp, C.POINTER(KvPlan), _vp, _vp, _i64, _i64, _vp]),
+    "ifx_kv_append_sp": (C.c_int, [_vp, C.POINTER(KvPlan), _vp, _vp, _i32, _i32, _i32, _vp]),
     "ifx_rmsnorm": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _i64, _i32, _f32, _vp]),
     "ifx_attention": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _vp, _i64, _i64, _i64, _i32, _i32, _f32, _vp]),
     "ifx_attention_kv": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _i64, _f32, _vp]),
@@ -148,3 +153,24 @@ def launch_count() -> int:
 
 def reset_launch_count() -> None:
     load().ifx_reset_launch_count()
+
+
+def prof_enable(on: bool) -> None:
+    load().ifx_prof_enable(int(on))
+
+
+def prof_reset() -> None:
+    load().ifx_prof_reset()
+
+
+def prof_read(prefix: str = ""):
+    """(total_ms, launches) of all profiled kernels whose label starts with `prefix`."""
+    ms, n = C.c_double(), C.c_uint64()
+    check(load().ifx_prof_read(prefix.encode(), C.byref(ms), C.byref(n)))
+    return ms.value, n.value
+
+
+def prof_labels():
+    buf = C.create_string_buffer(1 << 16)
+    check(load().ifx_prof_labels(buf, len(buf)))
+    return [s for s in buf.value.decode().split("\n") if s]

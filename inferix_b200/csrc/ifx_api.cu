@@ -4,9 +4,36 @@
 #include <cmath>
 #include <cstring>
 
+#include <string>
+
 #include "ifx_internal.h"
 
 namespace ifx {
+
+// ---------------------------------------------------------------- optional per-kernel timing
+struct ProfRecord {
+    std::string label;
+    cudaEvent_t start, stop;
+};
+static bool g_prof_on = false;
+static std::vector<ProfRecord> g_prof;
+
+ProfScope::ProfScope(const char* label, cudaStream_t s) : slot(-1), stream(s) {
+    if (!g_prof_on) return;
+    ProfRecord r;
+    r.label = label;
+    if (cudaEventCreate(&r.start) != cudaSuccess) return;
+    if (cudaEventCreate(&r.stop) != cudaSuccess) {
+        cudaEventDestroy(r.start);
+        return;
+    }
+    cudaEventRecord(r.start, s);
+    g_prof.push_back(r);
+    slot = static_cast<int>(g_prof.size()) - 1;
+}
+ProfScope::~ProfScope() {
+    if (slot >= 0) cudaEventRecord(g_prof[slot].stop, stream);
+}
 
 static thread_local char g_error[512] = "";
 static std::atomic<uint64_t> g_launches{0};
@@ -75,6 +102,49 @@ extern "C" const char* ifx_last_error(void) { return g_error; }
 extern "C" int ifx_abi_version(void) { return IFX_ABI_VERSION; }
 extern "C" uint64_t ifx_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 extern "C" void ifx_reset_launch_count(void) { g_launches.store(0, std::memory_order_relaxed); }
+
+extern "C" void ifx_prof_enable(int32_t on) { g_prof_on = on != 0; }
+extern "C" void ifx_prof_reset(void) {
+    for (auto& r : g_prof) {
+        cudaEventDestroy(r.start);
+        cudaEventDestroy(r.stop);
+    }
+    g_prof.clear();
+}
+extern "C" ifx_status ifx_prof_read(const char* prefix, double* total_ms, uint64_t* launches) {
+    IFX_CHECK_ARG(prefix && total_ms && launches, "ifx_prof_read: null pointer");
+    const size_t n = std::strlen(prefix);
+    double tot = 0.0;
+    uint64_t cnt = 0;
+    for (auto& r : g_prof) {
+        if (r.label.compare(0, n, prefix) != 0) continue;
+        IFX_CUDA_OK(cudaEventSynchronize(r.stop));
+        float ms = 0.f;
+        IFX_CUDA_OK(cudaEventElapsedTime(&ms, r.start, r.stop));
+        tot += ms;
+        ++cnt;
+    }
+    *total_ms = tot;
+    *launches = cnt;
+    return IFX_OK;
+}
+extern "C" ifx_status ifx_prof_labels(char* buf, int32_t cap) {
+    IFX_CHECK_ARG(buf && cap > 0, "ifx_prof_labels: bad buffer");
+    std::string out;
+    std::vector<std::string> seen;
+    for (auto& r : g_prof) {
+        bool dup = false;
+        for (auto& s : seen) dup = dup || (s == r.label);
+        if (!dup) {
+            seen.push_back(r.label);
+            out += r.label;
+            out += '\n';
+        }
+    }
+    IFX_CHECK_ARG(static_cast<int32_t>(out.size()) < cap, "ifx_prof_labels: buffer too small (%zu needed)", out.size() + 1);
+    std::memcpy(buf, out.c_str(), out.size() + 1);
+    return IFX_OK;
+}
 
 #define IFX_TRY(expr)                     \
     do {                                  \

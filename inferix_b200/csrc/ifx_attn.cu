@@ -325,7 +325,12 @@ static ifx_status attention_launch(const void* q, int64_t ldq, const void* k, co
     p.out = static_cast<__nv_bfloat16*>(out);
     p.ldo = ldo;
     const int grid = p.num_q_pairs * heads;
-    attn_fwd_kernel<<<grid, kAttnThreads, kAttnSmem, stream>>>(tmQ, tmK, tmV, p);
+    {
+        char label[96];
+        snprintf(label, sizeof(label), "attn_fwd_kernel[Lq=%d,Lk=%d,H=%d]", p.q_rows, p.kv_rows, heads);
+        ProfScope prof(label, stream);
+        attn_fwd_kernel<<<grid, kAttnThreads, kAttnSmem, stream>>>(tmQ, tmK, tmV, p);
+    }
     IFX_LAUNCH_OK("attn_fwd_kernel");
     return IFX_OK;
 }

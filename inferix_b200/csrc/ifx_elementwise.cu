@@ -272,8 +272,13 @@ paged_copy_kernel(const PagedCopyParams p) {
         const int vi = static_cast<int>(i % nvec);
         const int64_t lt = p.first_logical + r;
         const int64_t lp = lt / p.page_tokens;
-        const int phys = p.pl.pages[lp - p.first_logical / p.page_tokens];
-        const int64_t crow = static_cast<int64_t>(phys) * p.page_tokens + lt % p.page_tokens;
+        int64_t crow;
+        if (p.pl.n == 0) {
+            crow = p.linear_row0 + r;
+        } else {
+            const int phys = p.pl.pages[lp - p.first_logical / p.page_tokens];
+            crow = static_cast<int64_t>(phys) * p.page_tokens + lt % p.page_tokens;
+        }
         if (p.mode == 0) {
             if (p.lin_k)
                 reinterpret_cast<uint4*>(p.cache_k + crow * p.C)[vi] =
@@ -292,9 +297,69 @@ paged_copy_kernel(const PagedCopyParams p) {
     }
 }
 
+struct SpAppendParams {
+    __nv_bfloat16* cache_k;
+    __nv_bfloat16* cache_v;
+    const __nv_bfloat16* src_k;
+    const __nv_bfloat16* src_v;
+    int32_t world, frames, chunk, page_tokens, C;
+    PageList pl;
+};
+
+__global__ void __launch_bounds__(256)
+sp_append_kernel(const SpAppendParams p) {
+    const int nvec = p.C >> 3;
+    const int64_t rows_per_rank = static_cast<int64_t>(p.frames) * p.chunk;
+    const int64_t total = rows_per_rank * p.world * nvec;
+    const int64_t fs = static_cast<int64_t>(p.world) * p.chunk;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t row = i / nvec;
+        const int vi = static_cast<int>(i % nvec);
+        const int64_t r = row / rows_per_rank, rem = row % rows_per_rank;
+        const int64_t t = (rem / p.chunk) * fs + r * p.chunk + rem % p.chunk;  // token index inside the block
+        const int64_t crow = static_cast<int64_t>(p.pl.pages[t / p.page_tokens]) * p.page_tokens + t % p.page_tokens;
+        reinterpret_cast<uint4*>(p.cache_k + crow * p.C)[vi] = reinterpret_cast<const uint4*>(p.src_k + row * p.C)[vi];
+        reinterpret_cast<uint4*>(p.cache_v + crow * p.C)[vi] = reinterpret_cast<const uint4*>(p.src_v + row * p.C)[vi];
+    }
+}
+
 }  // namespace ifx
 
 using namespace ifx;
+
+extern "C" ifx_status ifx_kv_append_sp(ifx_kv* kv_, const ifx_kv_plan* plan, const void* k_src, const void* v_src,
+                                       int32_t world, int32_t frames, int32_t chunk, void* stream) {
+    KvImpl* kv = kv_cast(kv_);
+    if (!kv) return set_error(IFX_ERR_HANDLE, "ifx_kv_append_sp: bad kv handle");
+    IFX_CHECK_ARG(plan && k_src && v_src, "ifx_kv_append_sp: null pointer");
+    IFX_CHECK_ARG(world > 0 && frames > 0 && chunk > 0, "ifx_kv_append_sp: bad geometry");
+    const int64_t rows = static_cast<int64_t>(world) * frames * chunk;
+    IFX_CHECK_ARG(rows == plan->local_end - plan->local_start && rows == (int64_t)plan->num_pages * kv->page_tokens,
+                  "ifx_kv_append_sp: world*frames*chunk (%lld) does not match the plan", (long long)rows);
+    SpAppendParams p;
+    p.cache_k = static_cast<__nv_bfloat16*>(kv->k_base);
+    p.cache_v = static_cast<__nv_bfloat16*>(kv->v_base);
+    p.src_k = static_cast<const __nv_bfloat16*>(k_src);
+    p.src_v = static_cast<const __nv_bfloat16*>(v_src);
+    p.world = world;
+    p.frames = frames;
+    p.chunk = chunk;
+    p.page_tokens = kv->page_tokens;
+    p.C = kv->heads * kv->head_dim;
+    p.pl.n = plan->num_pages;
+    for (int i = 0; i < plan->num_pages; ++i) p.pl.pages[i] = plan->pages[i];
+    const int64_t total = rows * (p.C >> 3);
+    int64_t blocks = (total + 255) / 256;
+    const int64_t cap = static_cast<int64_t>(sm_count()) * 16;
+    if (blocks > cap) blocks = cap;
+    {
+        ProfScope prof("sp_append_kernel", static_cast<cudaStream_t>(stream));
+        sp_append_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    }
+    IFX_LAUNCH_OK("sp_append_kernel");
+    return IFX_OK;
+}
 
 extern "C" ifx_status ifx_ln_modulate(const void* x, void* out, const void* ln_weight, const void* ln_bias,
                                       const void* shift, const void* scale, int64_t mod_frame_stride, int64_t rows,
@@ -307,11 +372,14 @@ extern "C" ifx_status ifx_ln_modulate(const void* x, void* out, const void* ln_w
     IFX_CHECK_ARG((shift == nullptr) == (scale == nullptr), "ifx_ln_modulate: shift and scale go together");
     IFX_CHECK_ARG(!scale || (tokens_per_frame > 0 && mod_frame_stride % 8 == 0),
                   "ifx_ln_modulate: bad modulation layout");
-    ln_modulate_kernel<<<static_cast<unsigned>(rows), kRowThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(out),
-        static_cast<const __nv_bfloat16*>(ln_weight), static_cast<const __nv_bfloat16*>(ln_bias),
-        static_cast<const __nv_bfloat16*>(shift), static_cast<const __nv_bfloat16*>(scale), mod_frame_stride, cols,
-        tokens_per_frame > 0 ? tokens_per_frame : 1, eps);
+    {
+        ProfScope prof("ln_modulate_kernel", static_cast<cudaStream_t>(stream));
+        ln_modulate_kernel<<<static_cast<unsigned>(rows), kRowThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+            static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(out),
+            static_cast<const __nv_bfloat16*>(ln_weight), static_cast<const __nv_bfloat16*>(ln_bias),
+            static_cast<const __nv_bfloat16*>(shift), static_cast<const __nv_bfloat16*>(scale), mod_frame_stride, cols,
+            tokens_per_frame > 0 ? tokens_per_frame : 1, eps);
+    }
     IFX_LAUNCH_OK("ln_modulate_kernel");
     return IFX_OK;
 }
@@ -322,9 +390,12 @@ extern "C" ifx_status ifx_rmsnorm(const void* x, int64_t ldx, const void* weight
     IFX_CHECK_ARG(rows > 0 && cols > 0 && cols % 8 == 0 && cols <= kRowThreads * kMaxVecPerThread * 8,
                   "ifx_rmsnorm: bad cols %d", cols);
     IFX_CHECK_ARG(ldx % 8 == 0 && ldo % 8 == 0 && ldx >= cols && ldo >= cols, "ifx_rmsnorm: bad strides");
-    rmsnorm_kernel<<<static_cast<unsigned>(rows), kRowThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const __nv_bfloat16*>(x), ldx, static_cast<const __nv_bfloat16*>(weight),
-        static_cast<__nv_bfloat16*>(out), ldo, cols, eps);
+    {
+        ProfScope prof("rmsnorm_kernel", static_cast<cudaStream_t>(stream));
+        rmsnorm_kernel<<<static_cast<unsigned>(rows), kRowThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+            static_cast<const __nv_bfloat16*>(x), ldx, static_cast<const __nv_bfloat16*>(weight),
+            static_cast<__nv_bfloat16*>(out), ldo, cols, eps);
+    }
     IFX_LAUNCH_OK("rmsnorm_kernel");
     return IFX_OK;
 }
@@ -382,7 +453,10 @@ extern "C" ifx_status ifx_qk_norm_rope_append(const void* qkv, int64_t ld_qkv, c
         p.page_tokens = 1;
         p.pl.n = 0;
     }
-    qk_norm_rope_append_kernel<<<static_cast<unsigned>(rows), kRowThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    {
+        ProfScope prof("qk_norm_rope_append_kernel", static_cast<cudaStream_t>(stream));
+        qk_norm_rope_append_kernel<<<static_cast<unsigned>(rows), kRowThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    }
     IFX_LAUNCH_OK("qk_norm_rope_append_kernel");
     return IFX_OK;
 }
@@ -393,7 +467,10 @@ ifx_status launch_paged_copy(const PagedCopyParams& p, cudaStream_t stream) {
     int64_t blocks = (total + 255) / 256;
     const int64_t cap = static_cast<int64_t>(sm_count()) * 16;
     if (blocks > cap) blocks = cap;
-    paged_copy_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(p);
+    {
+        ProfScope prof("paged_copy_kernel", stream);
+        paged_copy_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(p);
+    }
     IFX_LAUNCH_OK("paged_copy_kernel");
     return IFX_OK;
 }
@@ -419,6 +496,7 @@ extern "C" ifx_status ifx_kv_append(ifx_kv* kv_, const ifx_kv_plan* plan, const 
     p.page_tokens = kv->page_tokens;
     p.C = C;
     p.mode = 0;
+    p.linear_row0 = 0;
     p.pl.n = plan->num_pages;
     for (int i = 0; i < plan->num_pages; ++i) p.pl.pages[i] = plan->pages[i];
     return launch_paged_copy(p, static_cast<cudaStream_t>(stream));

@@ -241,7 +241,12 @@ static ifx_status launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, co
     }
     const int tiles = p.num_m_tiles * p.num_n_tiles;
     const int grid = tiles < sm_count() ? tiles : sm_count();
-    gemm_bf16_tn_kernel<kEpi><<<grid, kGemmThreads, kGemmSmem, stream>>>(tmA, tmB, p);
+    {
+        char label[96];
+        snprintf(label, sizeof(label), "gemm_bf16_tn_kernel<%d>[M=%lld,N=%d,K=%d]", kEpi, (long long)p.M, p.N, p.K);
+        ProfScope prof(label, stream);
+        gemm_bf16_tn_kernel<kEpi><<<grid, kGemmThreads, kGemmSmem, stream>>>(tmA, tmB, p);
+    }
     IFX_LAUNCH_OK("gemm_bf16_tn_kernel");
     return IFX_OK;
 }

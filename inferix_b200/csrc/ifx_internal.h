@@ -38,6 +38,14 @@ void count_launch(int n = 1);
         ::ifx::count_launch();                                                                       \
     } while (0)
 
+// RAII bracket around a kernel launch; records two events on `stream` when profiling is enabled.
+struct ProfScope {
+    ProfScope(const char* label, cudaStream_t stream);
+    ~ProfScope();
+    int slot;
+    cudaStream_t stream;
+};
+
 // 2-D bf16 tensor map, 128-byte swizzle, box = [box_rows, 64 elements].
 ifx_status make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t inner_elems, uint64_t outer_rows,
                              uint64_t row_stride_elems, uint32_t box_inner, uint32_t box_rows);
@@ -76,6 +84,7 @@ struct PagedCopyParams {
     int32_t C;
     int32_t mode;
     PageList pl;            // pages[i] backs logical page (first_logical / page_tokens + i)
+    int64_t linear_row0;    // pl.n == 0: the rows are physically contiguous starting at this cache row
 };
 ifx_status launch_paged_copy(const PagedCopyParams& p, cudaStream_t stream);
 

@@ -190,25 +190,37 @@ static ifx_status paged_io(const KvImpl* kv, void* lin_k, void* lin_v, int64_t s
     const int64_t pt = kv->page_tokens;
     const int C = kv->heads * kv->head_dim;
     int64_t done = 0;
+    const int64_t last_page = (start + length + pt - 1) / pt;  // exclusive
     while (done < length) {
         const int64_t lt = start + done;
         const int64_t lp0 = lt / pt;
-        // up to IFX_KV_MAX_PLAN_PAGES pages per launch
-        const int64_t chunk_end_page = std::min<int64_t>(lp0 + IFX_KV_MAX_PLAN_PAGES, (start + length + pt - 1) / pt);
-        const int64_t chunk_end_tok = std::min<int64_t>(chunk_end_page * pt, start + length);
         PagedCopyParams p;
         p.cache_k = static_cast<__nv_bfloat16*>(kv->k_base);
         p.cache_v = static_cast<__nv_bfloat16*>(kv->v_base);
         p.lin_k = lin_k ? static_cast<__nv_bfloat16*>(lin_k) + done * C : nullptr;
         p.lin_v = lin_v ? static_cast<__nv_bfloat16*>(lin_v) + done * C : nullptr;
         p.ld_lin = C;
-        p.rows = chunk_end_tok - lt;
         p.first_logical = lt;
         p.page_tokens = kv->page_tokens;
         p.C = C;
         p.mode = mode;
-        p.pl.n = static_cast<int32_t>(chunk_end_page - lp0);
-        for (int i = 0; i < p.pl.n; ++i) p.pl.pages[i] = kv->table[static_cast<size_t>(lp0 + i)];
+        p.linear_row0 = 0;
+        // run of physically consecutive pages -> one dense extent (always the case for never-evicted caches)
+        int64_t run = 1;
+        while (lp0 + run < last_page &&
+               kv->table[static_cast<size_t>(lp0 + run)] == kv->table[static_cast<size_t>(lp0)] + run)
+            ++run;
+        int64_t chunk_end_page;
+        if (run >= 2 || last_page - lp0 == 1) {
+            chunk_end_page = lp0 + run;
+            p.pl.n = 0;
+            p.linear_row0 = static_cast<int64_t>(kv->table[static_cast<size_t>(lp0)]) * pt + lt % pt;
+        } else {
+            chunk_end_page = std::min<int64_t>(lp0 + IFX_KV_MAX_PLAN_PAGES, last_page);
+            p.pl.n = static_cast<int32_t>(chunk_end_page - lp0);
+            for (int i = 0; i < p.pl.n; ++i) p.pl.pages[i] = kv->table[static_cast<size_t>(lp0 + i)];
+        }
+        p.rows = std::min<int64_t>(chunk_end_page * pt, start + length) - lt;
         ifx_status st = launch_paged_copy(p, stream);
         if (st != IFX_OK) return st;
         done += p.rows;

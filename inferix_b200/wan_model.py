@@ -1,0 +1,402 @@
+"""Causal Wan DiT (Self-Forcing / CausVid) on the native kernels, with the reference's module surface.
+
+Mirrors ``inferix/models/self_forcing/causal_model.py`` (inference branch): same class names, constructor arguments,
+parameter names (a reference checkpoint's state_dict loads as is) and forward signatures —
+``CausalWanModel.forward`` (:866-880,1186-1194), ``CausalWanAttentionBlock.forward`` (:384-400).  The nn.Linear /
+LayerNorm children are parameter containers only: a block forward is ONE call into the C ABI
+(``ifx_wan_block_forward``: 13 hand-written sm_100a kernels), or the same kernels op by op when the block is sharded
+over ranks (one NCCL all-gather of the new K/V in the middle).
+
+Differences from the reference, all deliberate:
+  * bf16 only (the production dtype, base_pipeline.py:351-352); other dtypes raise.
+  * the KV window lives in a paged cache (frame-sized pages, block table) instead of a rolled tensor; end indices are
+    host integers mirrored into ``kv_cache_meta`` with ``fill_`` (no ``.item()`` syncs, reference :280-300,328-329).
+  * the text embedding MLP runs once per prompt, not once per forward (reference :948-953 recomputes it although only
+    the first forward consumes it, via the cross-attention K/V cache).
+  * training branches (_forward_train, flex-attention masks) are out of scope.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib, ops
+from ._lib import KvPlan, RopeGrid, WanBlockIO, WanBlockWeights
+from .kvcache_manager import KVCacheManager, KVCacheRequest
+from .kvcache_manager.model import SelfForcingKVCacheManagerFactory
+from .parallel import ParallelConfig, all_gather_rows, all_gather_tokens, scatter_tokens
+
+
+# ----------------------------------------------------------------------------- small components (wan_base/components.py)
+def sinusoidal_embedding_1d(dim, position):
+    """wan_base/components.py:11-31 (fp64)."""
+    assert dim % 2 == 0
+    half = dim // 2
+    position = position.type(torch.float64)
+    sinusoid = torch.outer(position, torch.pow(10000, -torch.arange(half).to(position).div(half)))
+    return torch.cat([torch.cos(sinusoid), torch.sin(sinusoid)], dim=1)
+
+
+def rope_params(max_seq_len, dim, theta=10000):
+    """wan_base/components.py:34-52 (complex128)."""
+    assert dim % 2 == 0
+    freqs = torch.outer(torch.arange(max_seq_len),
+                        1.0 / torch.pow(theta, torch.arange(0, dim, 2).to(torch.float64).div(dim)))
+    return torch.polar(torch.ones_like(freqs), freqs)
+
+
+class WanRMSNorm(nn.Module):
+    """Parameter holder for components.py:107-126; the arithmetic is in ifx_rmsnorm / ifx_qk_norm_rope_append."""
+
+    def __init__(self, dim, eps=1e-5):
+        super().__init__()
+        self.dim, self.eps = dim, eps
+        self.weight = nn.Parameter(torch.ones(dim))
+
+    def forward(self, x):
+        shp = x.shape
+        return ops.rmsnorm(x.reshape(-1, shp[-1]), self.weight, eps=self.eps).view(shp)
+
+
+class WanLayerNorm(nn.LayerNorm):
+    """components.py:129-142; forward runs ifx_ln_modulate (LN only)."""
+
+    def __init__(self, dim, eps=1e-6, elementwise_affine=False):
+        super().__init__(dim, elementwise_affine=elementwise_affine, eps=eps)
+
+    def forward(self, x):
+        shp = x.shape
+        w, b = (self.weight, self.bias) if self.elementwise_affine else (None, None)
+        return ops.ln_modulate(x.reshape(-1, shp[-1]).contiguous(), weight=w, bias=b, eps=self.eps).view(shp)
+
+
+class _Attn(nn.Module):
+    """q/k/v/o + norm_q/norm_k parameter layout shared by self- and cross-attention (causal_model.py:124-130)."""
+
+    def __init__(self, dim, num_heads, eps):
+        super().__init__()
+        self.dim, self.num_heads, self.head_dim, self.eps = dim, num_heads, dim // num_heads, eps
+        self.q, self.k, self.v, self.o = (nn.Linear(dim, dim) for _ in range(4))
+        self.norm_q = WanRMSNorm(dim, eps=eps)
+        self.norm_k = WanRMSNorm(dim, eps=eps)
+
+
+class CausalWanSelfAttention(_Attn):
+    def __init__(self, dim, num_heads, local_attn_size=-1, sink_size=0, qk_norm=True, eps=1e-6,
+                 parallel_config: Optional[ParallelConfig] = None):
+        assert dim % num_heads == 0
+        if not qk_norm:
+            raise NotImplementedError("qk_norm=False is not built (every shipped Wan config uses qk_norm=True)")
+        super().__init__(dim, num_heads, eps)
+        self.local_attn_size, self.sink_size, self.qk_norm = local_attn_size, sink_size, qk_norm
+        self.parallel_config = parallel_config
+
+
+class WanT2VCrossAttention(_Attn):
+    """wan_base/model.py:63-100."""
+
+    def __init__(self, dim, num_heads, window_size=(-1, -1), qk_norm=True, eps=1e-6):
+        super().__init__(dim, num_heads, eps)
+
+    def text_kv(self, context: torch.Tensor):
+        """K = RMSNorm(k(context)), V = v(context): computed once per prompt (wan_base/model.py:79-88)."""
+        ctx = context.reshape(-1, context.shape[-1]).contiguous()
+        k = ops.rmsnorm(ops.gemm(ctx, self.k.weight, self.k.bias), self.norm_k.weight, eps=self.eps)
+        v = ops.gemm(ctx, self.v.weight, self.v.bias)
+        return k, v
+
+
+class CausalWanAttentionBlock(nn.Module):
+    def __init__(self, cross_attn_type, dim, ffn_dim, num_heads, layer_idx, local_attn_size=-1, sink_size=0,
+                 qk_norm=True, cross_attn_norm=False, eps=1e-6, enable_kv_offload=True,
+                 parallel_config: Optional[ParallelConfig] = None):
+        super().__init__()
+        if cross_attn_type != "t2v_cross_attn":
+            raise NotImplementedError("i2v cross-attention is outside the T2V hot path")
+        if not cross_attn_norm:
+            raise NotImplementedError("cross_attn_norm=False is not built (Wan T2V configs use True)")
+        self.dim, self.ffn_dim, self.num_heads, self.layer_idx = dim, ffn_dim, num_heads, layer_idx
+        self.local_attn_size, self.sink_size = local_attn_size, sink_size
+        self.qk_norm, self.cross_attn_norm, self.eps = qk_norm, cross_attn_norm, eps
+        self.enable_kv_offload = enable_kv_offload
+        self.parallel_config = parallel_config
+        self.kv_cache_manager = SelfForcingKVCacheManagerFactory.create_manager(
+            layer_idx, num_heads, dim // num_heads, enable_kv_offload=enable_kv_offload)
+
+        self.norm1 = WanLayerNorm(dim, eps)
+        self.self_attn = CausalWanSelfAttention(dim, num_heads, local_attn_size, sink_size, qk_norm, eps,
+                                                parallel_config=parallel_config)
+        self.norm3 = WanLayerNorm(dim, eps, elementwise_affine=True)
+        self.cross_attn = WanT2VCrossAttention(dim, num_heads, (-1, -1), qk_norm, eps)
+        self.norm2 = WanLayerNorm(dim, eps)
+        self.ffn = nn.Sequential(nn.Linear(dim, ffn_dim), nn.GELU(approximate="tanh"), nn.Linear(ffn_dim, dim))
+        self.modulation = nn.Parameter(torch.randn(1, 6, dim) / dim ** 0.5)
+        self._packed = None
+
+    # ------------------------------------------------------------------ weight packing for the C ABI
+    def _pack(self):
+        sa, ca = self.self_attn, self.cross_attn
+        ps = [p for p in self.parameters()]
+        if any(p.dtype != torch.bfloat16 or not p.is_cuda for p in ps):
+            raise ValueError("inferix_b200 blocks run in bfloat16 on CUDA: call model.to(torch.bfloat16).cuda() first")
+        qkv_w = torch.cat([sa.q.weight, sa.k.weight, sa.v.weight], dim=0).contiguous()
+        qkv_b = torch.cat([sa.q.bias, sa.k.bias, sa.v.bias], dim=0).contiguous()
+        w = WanBlockWeights()
+        w.dim, w.ffn_dim, w.heads, w.head_dim, w.eps = self.dim, self.ffn_dim, self.num_heads, self.dim // self.num_heads, self.eps
+        keep = [qkv_w, qkv_b]
+
+        def ptr(t):
+            t = t.detach()
+            if not t.is_contiguous():
+                t = t.contiguous()
+                keep.append(t)
+            return t.data_ptr()
+
+        w.qkv_w, w.qkv_b = qkv_w.data_ptr(), qkv_b.data_ptr()
+        w.norm_q_w, w.norm_k_w = ptr(sa.norm_q.weight), ptr(sa.norm_k.weight)
+        w.o_w, w.o_b = ptr(sa.o.weight), ptr(sa.o.bias)
+        w.norm3_w, w.norm3_b = ptr(self.norm3.weight), ptr(self.norm3.bias)
+        w.cq_w, w.cq_b, w.cnorm_q_w = ptr(ca.q.weight), ptr(ca.q.bias), ptr(ca.norm_q.weight)
+        w.co_w, w.co_b = ptr(ca.o.weight), ptr(ca.o.bias)
+        w.ffn1_w, w.ffn1_b = ptr(self.ffn[0].weight), ptr(self.ffn[0].bias)
+        w.ffn2_w, w.ffn2_b = ptr(self.ffn[2].weight), ptr(self.ffn[2].bias)
+        self._packed = (w, keep, qkv_w, qkv_b)
+        return self._packed
+
+    def invalidate_packed(self):
+        self._packed = None
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, x, e, seq_lens, grid_sizes, freqs, context, context_lens, block_mask, kv_cache_meta=None,
+                crossattn_cache_meta=None, current_start=0, cache_start=None,
+                kv_cache_manager: Optional[KVCacheManager] = None,
+                kv_cache_requests: Optional[List[KVCacheRequest]] = None, workspace=None):
+        """x [B, L, C]; e [B, F, 6, C]; freqs: float64 (cos, sin) table from ops.rope_table.  Updates x in place and
+        returns it.  kv_cache_meta / crossattn_cache_meta are the reference's per-layer dicts (mutated in place)."""
+        if kv_cache_meta is None:
+            raise NotImplementedError("only the KV-cached inference branch is built")
+        assert kv_cache_manager is not None and kv_cache_requests is not None
+        w, _keep, qkv_w, qkv_b = self._packed or self._pack()
+        b, rows, c = x.shape
+        frames, fs = e.shape[1], rows // e.shape[1]
+        pc = self.parallel_config
+        world = pc.world_size if pc is not None else 1
+        rank = pc.rank if pc is not None else 0
+        f_, h_, w_ = (int(v) for v in grid_sizes[0])
+        frame_seqlen = h_ * w_                                    # global tokens per frame (causal_model.py:255)
+        mod = (self.modulation.unsqueeze(1) + e).contiguous()     # [B, F, 6, C]   causal_model.py:412
+        ws = workspace if workspace is not None else _Workspace(rows, c, self.ffn_dim, x.device)
+        stream = torch.cuda.current_stream().cuda_stream
+        lib = _lib.load()
+        windowed = self.local_attn_size != -1
+        sink_tokens = self.sink_size * frame_seqlen
+        grid = RopeGrid(f_, h_, w_, current_start // frame_seqlen, rank * (frame_seqlen // world), frame_seqlen // world)
+
+        for bi, req in enumerate(kv_cache_requests):
+            store = self.kv_cache_manager.store(kv_cache_manager, req)
+            cstore = self.kv_cache_manager.crossattn_store(kv_cache_manager, req)
+            if crossattn_cache_meta is not None and not crossattn_cache_meta["is_init"]:
+                k_txt, v_txt = self.cross_attn.text_kv(context[bi])
+                cstore.import_(0, k_txt, v_txt)
+            xb = x[bi]
+            if not xb.is_contiguous():
+                raise ValueError("x must be contiguous per sample")
+            if world == 1:
+                io = WanBlockIO()
+                io.x, io.rows, io.tokens_per_frame = xb.data_ptr(), rows, fs
+                io.mod, io.freqs, io.grid = mod[bi].data_ptr(), freqs.data_ptr(), grid
+                io.kv, io.current_start, io.sink_tokens, io.windowed = store.handle, current_start, sink_tokens, int(windowed)
+                io.cross_k, io.cross_v, io.text_len = cstore.k.data_ptr(), cstore.v.data_ptr(), cstore.k.shape[0]
+                io.ws_h, io.ws_qkv, io.ws_q = ws.h.data_ptr(), ws.qkv.data_ptr(), ws.q.data_ptr()
+                io.ws_attn, io.ws_ffn = ws.attn.data_ptr(), ws.ffn.data_ptr()
+                plan = KvPlan()
+                _lib.check(lib.ifx_wan_block_forward(C.byref(w), C.byref(io), C.byref(plan), stream))
+            else:
+                plan = self._forward_sharded(xb, mod[bi], fs, frames, grid, freqs, store, cstore, current_start,
+                                             sink_tokens, windowed, ws, qkv_w, qkv_b, pc)
+            # mirror of causal_model.py:328-329 (host ints -> device scalars, no sync)
+            kv_cache_meta["global_end_index"].fill_(plan.global_end)
+            kv_cache_meta["local_end_index"].fill_(plan.local_end)
+            kv_cache_meta["_ifx_plan"] = (plan.local_start, plan.local_end, plan.global_end, plan.num_evicted)
+        if crossattn_cache_meta is not None:
+            crossattn_cache_meta["is_init"] = True
+        return x
+
+    def _forward_sharded(self, x, mod, fs, frames, grid, freqs, store, cstore, current_start, sink_tokens, windowed,
+                         ws, qkv_w, qkv_b, pc: ParallelConfig):
+        """Same 13 kernels, op by op, with the all-gather of this rank's new K/V between the QKV epilogue and the
+        attention.  x [S/P, C] holds this rank's hw slice of every frame."""
+        rows, c = x.shape
+        sa, ca = self.self_attn, self.cross_attn
+        heads, hd = self.num_heads, self.dim // self.num_heads
+        m = mod.view(frames, 6, c)
+        plan = store.plan_append(current_start, rows * pc.world_size, sink_tokens, windowed)
+        ops.ln_modulate(x, ws.h, shift=m[:, 0], scale=m[:, 1], tokens_per_frame=fs, eps=self.eps)
+        ops.gemm(ws.h, qkv_w, qkv_b, ws.qkv)
+        ops.qk_norm_rope_append(ws.qkv, sa.norm_q.weight, sa.norm_k.weight, freqs, grid, heads, hd, q_out=ws.q,
+                                k_out=ws.k_new, v_out=ws.v_new, eps=self.eps)
+        kg = all_gather_rows(ws.k_new, pc, ws.k_all)
+        vg = all_gather_rows(ws.v_new, pc, ws.v_all)
+        store.append_sp(plan, kg, vg, frames)
+        store.attention(ws.q, ws.attn)
+        ops.gemm(ws.attn, sa.o.weight, sa.o.bias, x, epilogue=ops.EPI_BIAS_GATE_RES, residual=x, gate=m[:, 2],
+                 tokens_per_frame=fs)
+        ops.ln_modulate(x, ws.h, weight=self.norm3.weight, bias=self.norm3.bias, eps=self.eps)
+        ops.gemm(ws.h, ca.q.weight, ca.q.bias, ws.qkv[:, :c])
+        ops.rmsnorm(ws.qkv[:, :c], ca.norm_q.weight, ws.q, eps=self.eps)
+        ops.attention(ws.q, cstore.k, cstore.v, heads, ws.attn)
+        ops.gemm(ws.attn, ca.o.weight, ca.o.bias, x, epilogue=ops.EPI_BIAS_GATE_RES, residual=x)
+        ops.ln_modulate(x, ws.h, shift=m[:, 3], scale=m[:, 4], tokens_per_frame=fs, eps=self.eps)
+        ops.gemm(ws.h, self.ffn[0].weight, self.ffn[0].bias, ws.ffn, epilogue=ops.EPI_BIAS_GELU)
+        ops.gemm(ws.ffn, self.ffn[2].weight, self.ffn[2].bias, x, epilogue=ops.EPI_BIAS_GATE_RES, residual=x,
+                 gate=m[:, 5], tokens_per_frame=fs)
+        return plan
+
+
+class _Workspace:
+    """Scratch activations of one block forward, reused by every layer (all bf16)."""
+
+    def __init__(self, rows, dim, ffn_dim, device, world=1):
+        def buf(*shape):
+            return torch.empty(shape, dtype=torch.bfloat16, device=device)
+        self.rows = rows
+        self.h, self.qkv, self.q, self.attn, self.ffn = buf(rows, dim), buf(rows, 3 * dim), buf(rows, dim), buf(rows, dim), buf(rows, ffn_dim)
+        if world > 1:
+            self.k_new, self.v_new = buf(rows, dim), buf(rows, dim)
+            self.k_all, self.v_all = buf(world, rows, dim), buf(world, rows, dim)
+
+
+class CausalHead(nn.Module):
+    """causal_model.py:487-515.  [S, C] -> [S, 64]: 0.03 % of the layer FLOPs; stays on torch ops."""
+
+    def __init__(self, dim, out_dim, patch_size, eps=1e-6):
+        super().__init__()
+        self.dim, self.out_dim, self.patch_size, self.eps = dim, out_dim, patch_size, eps
+        self.norm = WanLayerNorm(dim, eps)
+        self.head = nn.Linear(dim, math.prod(patch_size) * out_dim)
+        self.modulation = nn.Parameter(torch.randn(1, 2, dim) / dim ** 0.5)
+
+    def forward(self, x, e):
+        """x [B, L1, C]; e [B, F, 1, C]."""
+        num_frames, frame_seqlen = e.shape[1], x.shape[1] // e.shape[1]
+        e = (self.modulation.unsqueeze(1) + e).chunk(2, dim=2)
+        h = F.layer_norm(x, (self.dim,), None, None, self.eps).unflatten(dim=1, sizes=(num_frames, frame_seqlen))
+        return self.head(h * (1 + e[1]) + e[0])
+
+
+class CausalWanModel(nn.Module):
+    """causal_model.py:518-654 (constructor) and :866-1026 (_forward_inference)."""
+
+    def __init__(self, model_type="t2v", patch_size=(1, 2, 2), text_len=512, in_dim=16, dim=2048, ffn_dim=8192,
+                 freq_dim=256, text_dim=4096, out_dim=16, num_heads=16, num_layers=32, local_attn_size=-1, sink_size=0,
+                 qk_norm=True, cross_attn_norm=True, eps=1e-6, enable_kv_offload=True,
+                 parallel_config: Optional[ParallelConfig] = None):
+        super().__init__()
+        if model_type != "t2v":
+            raise NotImplementedError("only the t2v variant is on the hot path")
+        assert (dim % num_heads) == 0 and (dim // num_heads) % 2 == 0
+        if dim // num_heads != 128:
+            raise NotImplementedError("the tcgen05 attention kernel is built for head_dim 128 (all Wan models)")
+        self.model_type, self.patch_size, self.text_len = model_type, tuple(patch_size), text_len
+        self.in_dim, self.dim, self.ffn_dim, self.freq_dim, self.text_dim = in_dim, dim, ffn_dim, freq_dim, text_dim
+        self.out_dim, self.num_heads, self.num_layers = out_dim, num_heads, num_layers
+        self.local_attn_size, self.sink_size = local_attn_size, sink_size
+        self.qk_norm, self.cross_attn_norm, self.eps = qk_norm, cross_attn_norm, eps
+        self.parallel_config = parallel_config if parallel_config is not None else ParallelConfig()
+
+        self.patch_embedding = nn.Conv3d(in_dim, dim, kernel_size=self.patch_size, stride=self.patch_size)
+        self.text_embedding = nn.Sequential(nn.Linear(text_dim, dim), nn.GELU(approximate="tanh"), nn.Linear(dim, dim))
+        self.time_embedding = nn.Sequential(nn.Linear(freq_dim, dim), nn.SiLU(), nn.Linear(dim, dim))
+        self.time_projection = nn.Sequential(nn.SiLU(), nn.Linear(dim, dim * 6))
+        self.blocks = nn.ModuleList([
+            CausalWanAttentionBlock("t2v_cross_attn", dim, ffn_dim, num_heads, i, local_attn_size, sink_size, qk_norm,
+                                    cross_attn_norm, eps, enable_kv_offload=enable_kv_offload,
+                                    parallel_config=self.parallel_config) for i in range(num_layers)])
+        self.head = CausalHead(dim, out_dim, self.patch_size, eps)
+
+        d = dim // num_heads
+        self.freqs = torch.cat([rope_params(1024, d - 4 * (d // 6)), rope_params(1024, 2 * (d // 6)),
+                                rope_params(1024, 2 * (d // 6))], dim=1)          # complex128, causal_model.py:634-641
+        self._freqs_table = None
+        self._workspace = None
+        self.block_mask = None
+        self.num_frame_per_block = 1
+        self.independent_first_frame = False
+
+    def load_state_dict(self, state_dict, strict=True, assign=False):
+        out = super().load_state_dict(state_dict, strict=strict, assign=assign)
+        for blk in self.blocks:
+            blk.invalidate_packed()
+        return out
+
+    def _apply(self, fn, *a, **k):
+        out = super()._apply(fn, *a, **k)
+        for blk in self.blocks:
+            blk.invalidate_packed()
+        self._freqs_table = None
+        self._workspace = None
+        return out
+
+    def _get_workspace(self, rows, device):
+        ws = self._workspace
+        if ws is None or ws.rows != rows or ws.h.device != device:
+            ws = self._workspace = _Workspace(rows, self.dim, self.ffn_dim, device, self.parallel_config.world_size)
+        return ws
+
+    def forward(self, x, t, context, seq_len, clip_fea=None, y=None, kv_cache_meta: list = None,
+                crossattn_cache_meta: list = None, current_start: int = 0, cache_start: int = 0,
+                kv_cache_manager: Optional[KVCacheManager] = None, kv_cache_requests: Optional[list] = None):
+        """x: list of [C_in, F, H, W] (or a [B, C_in, F, H, W] tensor); t [B, F]; context: list of [L, text_dim]
+        (or [B, L, text_dim]).  Returns the flow prediction [B, C_out, F, H, W]."""
+        if kv_cache_meta is None:
+            raise NotImplementedError("training forward (_forward_train) is out of scope")
+        pc = self.parallel_config
+        device = self.patch_embedding.weight.device
+        if self._freqs_table is None or self._freqs_table.device != device:
+            self._freqs_table = ops.rope_table(self.freqs, device)
+
+        # embeddings (causal_model.py:916-936)
+        xs = [self.patch_embedding(u.unsqueeze(0)) for u in x]
+        grid_sizes = torch.stack([torch.tensor(u.shape[2:], dtype=torch.long) for u in xs])
+        xs = [u.flatten(2).transpose(1, 2) for u in xs]
+        assert max(u.size(1) for u in xs) <= seq_len
+        x = torch.cat(xs).contiguous()
+        frames = int(grid_sizes[0, 0])
+        e = self.time_embedding(sinusoidal_embedding_1d(self.freq_dim, t.flatten()).type_as(x))
+        e0 = self.time_projection(e).unflatten(1, (6, self.dim)).unflatten(dim=0, sizes=t.shape)
+
+        x = scatter_tokens(x, frames, pc.world_size, pc.rank).contiguous()           # :939-942
+
+        # text embedding only when some layer still has to build its cross-attention K/V (reference: every call)
+        ctx = None
+        if any(not m["is_init"] for m in crossattn_cache_meta):
+            ctx = self.text_embedding(torch.stack(
+                [torch.cat([u, u.new_zeros(self.text_len - u.size(0), u.size(1))]) for u in context]))
+
+        ws = self._get_workspace(x.shape[1], device)
+        for i, block in enumerate(self.blocks):
+            x = block(x, e=e0, seq_lens=None, grid_sizes=grid_sizes, freqs=self._freqs_table, context=ctx,
+                      context_lens=None, block_mask=None, kv_cache_meta=kv_cache_meta[i],
+                      crossattn_cache_meta=crossattn_cache_meta[i], current_start=current_start,
+                      cache_start=cache_start, kv_cache_manager=kv_cache_manager,
+                      kv_cache_requests=kv_cache_requests, workspace=ws)
+
+        x = self.head(x, e.unflatten(dim=0, sizes=t.shape).unsqueeze(2))             # [B, F, hw/P, 64]
+        x = x.flatten(1, 2)
+        x = all_gather_tokens(x, frames, pc)                                         # :1008-1022
+        return torch.stack(self.unpatchify(x, grid_sizes))
+
+    def unpatchify(self, x, grid_sizes):
+        """causal_model.py:1196-1219."""
+        c = self.out_dim
+        out = []
+        for u, v in zip(x, grid_sizes.tolist()):
+            u = u[:math.prod(v)].view(*v, *self.patch_size, c)
+            u = torch.einsum("fhwpqrc->cfphqwr", u)
+            out.append(u.reshape(c, *[i * j for i, j in zip(v, self.patch_size)]))
+        return out

@@ -164,7 +164,7 @@ def run_case(cm, name, cfg, dtype, frames, latent_hw, local_attn_size, sink_size
     pipe = reference_pipeline(cm, model, pc, cfg, fs, steps, 3, shift)
 
     g = torch.Generator().manual_seed(seed)
-    noise = torch.randn(1, frames, 16, latent_hw, latent_hw, generator=g).to(dtype)
+    noise = torch.randn(1, frames, 16, latent_hw, latent_hw, generator=g).to(dtype)      # fp32 draw, then cast
     context = torch.randn(1, 20, cfg["text_dim"], generator=g).to(dtype)
 
     # --- trace the cache indices and per-block activations of the very first forward
@@ -189,11 +189,20 @@ def run_case(cm, name, cfg, dtype, frames, latent_hw, local_attn_size, sink_size
     mgr = KVCacheManager("cpu")
     reqs = [KVCacheRequest("req_0")]
     blocks_out = []
-    torch.manual_seed(1234)   # re-noising draws from the global CPU generator (CausalInferencePipeline.py:307)
-    with torch.no_grad():
-        out = pipe.inference(noise=noise, text_prompts=context, kv_cache_manager=mgr, kv_cache_requests=reqs,
-                             free_cache_before_vae=False, decode_mode=DecodeMode.NO_DECODE,
-                             block_callback=lambda lat, idx: blocks_out.append((idx, lat.clone())))
+    # Re-noising (CausalInferencePipeline.py:307) calls torch.randn_like on the latents.  randn draws different
+    # numbers for bf16 and fp32 tensors, which would make the two dtype runs incomparable, so for the duration of
+    # the run randn_like is bound to "draw fp32 from a seeded generator, cast to the tensor's dtype".  This changes
+    # where the noise comes from, not a single arithmetic operation of the reference.
+    regen = torch.Generator().manual_seed(1234)
+    real_randn_like = torch.randn_like
+    torch.randn_like = lambda x, **kw: torch.randn(x.shape, generator=regen, dtype=torch.float32).to(x.dtype)
+    try:
+        with torch.no_grad():
+            out = pipe.inference(noise=noise, text_prompts=context, kv_cache_manager=mgr, kv_cache_requests=reqs,
+                                 free_cache_before_vae=False, decode_mode=DecodeMode.NO_DECODE,
+                                 block_callback=lambda lat, idx: blocks_out.append((idx, lat.clone())))
+    finally:
+        torch.randn_like = real_randn_like
     for h in hooks:
         h.remove()
     # (2, N, 1, H, D) -> valid prefix only; the full tensor is kept for the bf16 runs, a checksum for fp32

@@ -1,0 +1,122 @@
+"""End-to-end parity of the native path against the reference's own outputs (tests/golden, produced by running
+/root/reference on CPU) and against the oracle, through the reference-shaped Python surface.
+
+Tolerance statement.  The path is bf16.  KV indices: bit-exact.  Latents:
+  (a) relL2(ours_bf16, ref_fp32) <= 1.5 x relL2(ref_bf16, ref_fp32)   [the reference's own bf16-vs-fp32 gap], and
+  (b) relL2(ours_bf16, ref_bf16) <= 5e-3 over the whole multi-block pipeline (measured 2.4e-3 .. 2.8e-3: the same
+      distance two FlashAttention-2 runs with different key order sit apart; per-op parity at <= 1e-3 is in
+      tests/test_gpu_kernels.py).
+"""
+import types
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from inferix_b200.kvcache_manager import KVCacheManager, KVCacheRequest     # noqa: E402
+from inferix_b200.pipeline import CausalInferencePipeline, DecodeMode        # noqa: E402
+from inferix_b200.synthetic import synth_state_dict                          # noqa: E402
+from inferix_b200.wan_model import CausalWanModel                            # noqa: E402
+from inferix_b200.wrapper import WanDiffusionWrapper                         # noqa: E402
+from oracle import wan_oracle as wo                                          # noqa: E402
+
+DEV = "cuda"
+
+
+def rel_l2(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def build(cfg_d, local_attn_size, sink_size, steps, shift):
+    model = CausalWanModel(**cfg_d, local_attn_size=local_attn_size, sink_size=sink_size)
+    model.load_state_dict(synth_state_dict(cfg_d, seed=0))
+    model = model.to(torch.bfloat16).to(DEV)
+    gen = WanDiffusionWrapper(model=model, timestep_shift=shift)
+    args = types.SimpleNamespace(denoising_step_list=steps, warp_denoising_step=True, num_frame_per_block=3,
+                                 context_noise=0)
+    return CausalInferencePipeline(args, DEV, generator=gen)
+
+
+def run_ours(gold):
+    pipe = build(gold["cfg"], gold["local_attn_size"], gold["sink_size"], gold["steps"], gold["shift"])
+    cpu_gen = torch.Generator().manual_seed(gold["renoise_seed"])   # same draws as oracle/make_golden.py
+    pipe.renoise_fn = lambda x: torch.randn(x.shape, generator=cpu_gen, dtype=torch.float32).to(x.dtype).to(x.device)
+    mgr, reqs = KVCacheManager(DEV), [KVCacheRequest("req_0")]
+    trace, blocks = [], []
+    blk0 = pipe.generator.model.blocks[0]
+    hook = blk0.register_forward_hook(lambda m, i, o: trace.append(pipe.kv_cache_meta[0]["_ifx_plan"]))
+    out = pipe.inference(noise=gold["noise"].to(torch.bfloat16).to(DEV), text_prompts=gold["context"].to(torch.bfloat16).to(DEV),
+                         kv_cache_manager=mgr, kv_cache_requests=reqs, free_cache_before_vae=False,
+                         decode_mode=DecodeMode.NO_DECODE, block_callback=lambda lat, i: blocks.append(i))
+    hook.remove()
+    return pipe, mgr, reqs, out, trace, blocks
+
+
+@pytest.mark.parametrize("case", ["sf_tiny_1block", "sf_tiny_evict"])
+def test_pipeline_matches_reference(case, golden_dir):
+    g16 = torch.load(golden_dir / f"{case}_bf16.pt", weights_only=False)
+    g32 = torch.load(golden_dir / f"{case}_fp32.pt", weights_only=False)
+    pipe, mgr, reqs, out, trace, blocks = run_ours(g16)
+    # --- indices: bit-exact against the reference's (global_end, local_end) after every forward
+    assert [(g, l) for (_, l, g, _) in trace] == g16["index_trace"]
+    assert blocks == g16["callback_blocks"]
+    meta = pipe.kv_cache_meta[0]
+    assert (int(meta["global_end_index"]), int(meta["local_end_index"])) == g16["index_trace"][-1]
+    # --- latents
+    ref_gap = rel_l2(g16["latents"], g32["latents"])
+    ours_vs_fp32 = rel_l2(out, g32["latents"])
+    ours_vs_bf16 = rel_l2(out, g16["latents"])
+    print(f"{case}: ref bf16-vs-fp32 {ref_gap:.3e}; ours-vs-fp32 {ours_vs_fp32:.3e}; ours-vs-ref-bf16 {ours_vs_bf16:.3e}")
+    assert ours_vs_fp32 <= 1.5 * ref_gap
+    assert ours_vs_bf16 <= 5e-3
+    # --- last layer's cache in the reference's logical order
+    last = pipe.generator.model.blocks[-1].kv_cache_manager
+    kv = last.get_kv_cache(mgr, reqs[0])                        # (2, N, H, D)
+    le = g16["index_trace"][-1][1]
+    ref_kv = g16["last_layer_cache"][:, :, 0]                   # (2, le, H, D)
+    # K/V are bf16 re-roundings of activations that already carry the ~3e-3 bf16-path noise, in a 2-layer net
+    # with an un-trained (xavier) second layer that amplifies it: measured 6e-3 .. 8e-3, bounded at 1.5e-2.
+    kv_err = rel_l2(kv[:, :le], ref_kv)
+    print(f"{case}: last-layer cache rel-L2 vs reference {kv_err:.3e}")
+    assert kv_err <= 1.5e-2
+
+
+def test_pipeline_window_not_multiple_of_block(golden_dir):
+    g16 = torch.load(golden_dir / "sf_tiny_evict7_bf16.pt", weights_only=False)
+    _, _, _, out, trace, _ = run_ours(g16)
+    assert [(g, l) for (_, l, g, _) in trace] == g16["index_trace"]
+    assert rel_l2(out, g16["latents"]) <= 5e-3
+
+
+def test_block_forward_matches_oracle():
+    """One DiT block (the ifx_wan_block_forward call) against oracle.block_forward on the same inputs."""
+    from inferix_b200.synthetic import TINY
+    from inferix_b200 import ops
+    cfg = wo.WanConfig(**TINY, local_attn_size=6, sink_size=0)
+    sd = {k: v.bfloat16() for k, v in synth_state_dict(TINY, seed=0).items()}
+    model = CausalWanModel(**TINY, local_attn_size=6, sink_size=0)
+    model.load_state_dict(synth_state_dict(TINY, seed=0))
+    model = model.to(torch.bfloat16).to(DEV)
+    g = torch.Generator().manual_seed(3)
+    frames, fs, C = 3, 64, TINY["dim"]
+    x = torch.randn(1, frames * fs, C, generator=g).bfloat16()
+    e0 = (torch.randn(1, frames, 6, C, generator=g) * 0.3).bfloat16()
+    ctx = (torch.randn(1, 512, C, generator=g) * 0.5).bfloat16()
+    grid = (frames, 8, 8)
+    caches, cross = wo.new_cache(cfg, 6 * fs, 1, torch.bfloat16), [dict(is_init=False) for _ in range(2)]
+    mgr, req = KVCacheManager(DEV), KVCacheRequest("r")
+    blk = model.blocks[1]
+    blk.kv_cache_manager.allocate_kv_cache(mgr, req, 6 * fs, torch.bfloat16, page_tokens=fs)
+    blk.kv_cache_manager.allocate_crossattn_cache(mgr, req, 512, torch.bfloat16)
+    meta = {"global_end_index": torch.zeros(1, dtype=torch.long, device=DEV),
+            "local_end_index": torch.zeros(1, dtype=torch.long, device=DEV)}
+    cmeta = {"is_init": False}
+    table = ops.rope_table(model.freqs, DEV)
+    for step, start in enumerate([0, 0, 3 * fs, 6 * fs]):     # repeat, advance, evict
+        ref = wo.block_forward(sd, 1, cfg, x, e0, grid, wo.rope_freqs(128), ctx, caches[1], cross[1], start)
+        out = blk(x.clone().to(DEV), e0.to(DEV), None, torch.tensor([grid]), table, ctx.to(DEV), None, None, meta, cmeta,
+                  current_start=start, kv_cache_manager=mgr, kv_cache_requests=[req])
+        assert rel_l2(out, ref) <= 5e-3, f"step {step}"
+        assert (int(meta["global_end_index"]), int(meta["local_end_index"])) == (caches[1].global_end, caches[1].local_end)

@@ -23,10 +23,12 @@ def run_oracle(gold):
     steps = wo.warp_steps(sched, gold["steps"])
     fs = (gold["latent_hw"] // 2) ** 2
     cache_tokens = 32760 if gold["local_attn_size"] == -1 else gold["local_attn_size"] * fs
-    torch.manual_seed(gold["renoise_seed"])
+    regen = torch.Generator().manual_seed(gold["renoise_seed"])    # fp32 draws cast to the run dtype, as make_golden
     blocks = []
-    out, caches = wo.pipeline_inference(sd, cfg, sched, gold["noise"], gold["context"], steps, 3, fs, cache_tokens,
-                                        block_callback=lambda lat, i: blocks.append(i))
+    out, caches = wo.pipeline_inference(
+        sd, cfg, sched, gold["noise"], gold["context"], steps, 3, fs, cache_tokens,
+        block_callback=lambda lat, i: blocks.append(i),
+        noise_fn=lambda x: torch.randn(x.shape, generator=regen, dtype=torch.float32).to(x.dtype))
     return out, caches, blocks
 
 

@@ -1,6 +1,6 @@
 // Non-causal flash attention for sm_100a:  out = softmax(q k^T * scale) v,  head_dim = 128, bf16 in/out.
 //
-// One CTA owns 256 query rows of one head (two 128-row tiles, "ping-pong") and streams all keys/values:
+// One CTA owns 256 query rows of one head (two 128-row tiles, "ping-pong") and streams keys/values:
 //   warp 0        TMA producer: Q once, then K_j / V_j tiles (128 keys x 128 dims, two SWIZZLE_128B boxes each)
 //                 into a ring of kSlots 32-KiB shared-memory slots
 //   warp 1        MMA issuer (one thread):  S_w = Q_w K_j^T  (SS, 128x128x16 x 8)  -> TMEM
@@ -11,6 +11,11 @@
 //                 lazy rescaling of O (only when the running max grows by more than 2^8), P written back to
 //                 TMEM as packed bf16, final O / l epilogue straight from TMEM to global memory.
 // While the softmax warps of one tile work, the tensor core runs the other tile's MMAs.
+//
+// Grid shaping: work items are (head, 256-row pair).  Items that fill whole waves of SMs run over the full key
+// range; the items of the last, partial wave are split along the keys into `split` pieces so that the tail costs
+// 1/split of a wave; pieces emit un-normalised (O, max, sum) partials that attn_combine_kernel merges.
+// A pair whose second tile lies entirely past the last query row runs in single-tile mode.
 //
 // Replaces flash_attention()/attention() (inferix/models/attention/flash_attention.py:42-200) at the two call
 // sites of the block: self-attention over cache[0:local_end] (causal_model.py:307-315) and text
@@ -30,15 +35,20 @@ constexpr int kHalfBytes = kTileBytes / 2; // one 64-wide SWIZZLE_128B box
 constexpr int kAttnThreads = 384;
 constexpr int kAttnSmem = 2 * kTileBytes + kSlots * kTileBytes + 1024 + 256;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
+constexpr int kMaxSplit = 8;
 
 struct AttnParams {
     int32_t q_rows;
     int32_t kv_rows;
     int32_t heads;
     int32_t num_q_pairs;
+    int32_t n_whole;     // items [0, n_whole) cover all keys; the rest are split into `split` pieces
+    int32_t split;
     float scale_log2;
     __nv_bfloat16* out;
     int64_t ldo;
+    float* part_o;       // [pieces][256][128] un-normalised O
+    float* part_ml;      // [pieces][256][2]   (max * scale_log2, sum)
 };
 
 __global__ void __launch_bounds__(kAttnThreads, 1)
@@ -59,9 +69,24 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int head = blockIdx.x / p.num_q_pairs;
-    const int q0 = (blockIdx.x % p.num_q_pairs) * (2 * kQT);
-    const int n_kv = (p.kv_rows + kKT - 1) / kKT;
+
+    // ---- which (item, key range) does this CTA own
+    const int n_kv_all = (p.kv_rows + kKT - 1) / kKT;
+    int item, piece = -1, kv_begin = 0, kv_end = n_kv_all;
+    if (static_cast<int>(blockIdx.x) < p.n_whole) {
+        item = blockIdx.x;
+    } else {
+        const int idx = blockIdx.x - p.n_whole;
+        item = p.n_whole + idx / p.split;
+        const int sub = idx % p.split;
+        piece = idx;
+        kv_begin = static_cast<int>(static_cast<int64_t>(n_kv_all) * sub / p.split);
+        kv_end = static_cast<int>(static_cast<int64_t>(n_kv_all) * (sub + 1) / p.split);
+    }
+    const int head = item / p.num_q_pairs;
+    const int q0 = (item % p.num_q_pairs) * (2 * kQT);
+    const int n_kv = kv_end - kv_begin;
+    const bool two = q0 + kQT < p.q_rows;  // second tile has at least one real row
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmQ);
@@ -92,16 +117,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
     if (warp == 0) {
         if (lane == 0) {
-            // Q: two tiles x two 64-wide halves
-            mbar_expect_tx(q_full, 2 * kTileBytes);
-#pragma unroll
-            for (int w = 0; w < 2; ++w)
+            // Q: one or two tiles x two 64-wide halves
+            const int nq = two ? 2 : 1;
+            mbar_expect_tx(q_full, nq * kTileBytes);
+            for (int w = 0; w < nq; ++w)
 #pragma unroll
                 for (int h = 0; h < 2; ++h)
                     tma_load_2d_hint(sQ + w * kTileBytes + h * kHalfBytes, &tmQ, q_full, head * kHD + h * 64,
                                      q0 + w * kQT, kEvictFirst);
             int idx = 0;
-            for (int j = 0; j < n_kv; ++j) {
+            for (int j = kv_begin; j < kv_end; ++j) {
 #pragma unroll
                 for (int kv = 0; kv < 2; ++kv, ++idx) {
                     const int s = idx % kSlots;
@@ -150,8 +175,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             tc_fence_after();
             issue_qk(0, slot_of(0));
             umma_commit(&s_full[0]);
-            issue_qk(1, slot_of(0));
-            umma_commit(&s_full[1]);
+            if (two) {
+                issue_qk(1, slot_of(0));
+                umma_commit(&s_full[1]);
+            }
             umma_commit(&kv_empty[slot_of(0)]);
             for (int j = 0; j < n_kv; ++j) {
                 const int vi = 2 * j + 1;
@@ -167,13 +194,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     issue_qk(0, slot_of(kn));
                     umma_commit(&s_full[0]);
                 }
-                mbar_wait(&p_full[1], j & 1);
-                tc_fence_after();
-                issue_pv(1, slot_of(vi), j > 0);
+                if (two) {
+                    mbar_wait(&p_full[1], j & 1);
+                    tc_fence_after();
+                    issue_pv(1, slot_of(vi), j > 0);
+                }
                 umma_commit(&kv_empty[slot_of(vi)]);
                 if (more) {
-                    issue_qk(1, slot_of(kn));
-                    umma_commit(&s_full[1]);
+                    if (two) {
+                        issue_qk(1, slot_of(kn));
+                        umma_commit(&s_full[1]);
+                    }
                     umma_commit(&kv_empty[slot_of(kn)]);
                 }
             }
@@ -181,102 +212,122 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
     } else if (warp >= 4) {
         const int w = (warp - 4) >> 2;  // which query tile
-        const int quad = warp & 3;      // TMEM lane quadrant
-        const uint32_t lane_sel = static_cast<uint32_t>(quad * 32) << 16;
-        const uint32_t tS_row = tS[w] + lane_sel;
-        const uint32_t tO_row = tO[w] + lane_sel;
-        const int row = q0 + w * kQT + quad * 32 + lane;
-        const float sl2 = p.scale_log2;
+        if (w == 0 || two) {
+            const int quad = warp & 3;      // TMEM lane quadrant
+            const uint32_t lane_sel = static_cast<uint32_t>(quad * 32) << 16;
+            const uint32_t tS_row = tS[w] + lane_sel;
+            const uint32_t tO_row = tO[w] + lane_sel;
+            const int row_in_pair = w * kQT + quad * 32 + lane;
+            const int row = q0 + row_in_pair;
+            const float sl2 = p.scale_log2;
 
-        float m_used = -INFINITY;  // max (raw score units) the probabilities are currently referenced to
-        float l = 0.f;
-        for (int j = 0; j < n_kv; ++j) {
-            mbar_wait(&s_full[w], j & 1);
-            tc_fence_after();
-            uint32_t s[4][32];
+            float m_used = -INFINITY;  // max (raw score units) the probabilities are currently referenced to
+            float l = 0.f;
+            for (int j = 0; j < n_kv; ++j) {
+                mbar_wait(&s_full[w], j & 1);
+                tc_fence_after();
+                uint32_t s[4][32];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) tmem_ld32(tS_row + c * 32, s[c]);
-            tmem_wait_ld();
-            const int valid = p.kv_rows - j * kKT;
-            if (valid < kKT) {
+                for (int c = 0; c < 4; ++c) tmem_ld32(tS_row + c * 32, s[c]);
+                tmem_wait_ld();
+                const int valid = p.kv_rows - (kv_begin + j) * kKT;
+                if (valid < kKT) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (c * 32 + i >= valid) s[c][i] = __float_as_uint(-INFINITY);
+                }
+                float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
                 for (int c = 0; c < 4; ++c)
 #pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if (c * 32 + i >= valid) s[c][i] = __float_as_uint(-INFINITY);
-            }
-            float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll
-            for (int c = 0; c < 4; ++c)
-#pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    mx0 = fmaxf(mx0, __uint_as_float(s[c][i]));
-                    mx1 = fmaxf(mx1, __uint_as_float(s[c][i + 1]));
-                    mx2 = fmaxf(mx2, __uint_as_float(s[c][i + 2]));
-                    mx3 = fmaxf(mx3, __uint_as_float(s[c][i + 3]));
-                }
-            const float m_new = fmaxf(fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)), m_used);
-            if (j == 0) {
-                m_used = m_new;
-            } else {
-                const bool need = (m_new - m_used) * sl2 > kRescaleThreshold;
-                if (__any_sync(0xffffffffu, need)) {
-                    // whole warp rescales (tcgen05.ld/st are warp-collective); rows that did not need it use
-                    // their exact (possibly tiny) correction as well, which keeps every row consistent.
-                    const float alpha = ex2_approx((m_used - m_new) * sl2);
+                    for (int i = 0; i < 32; i += 4) {
+                        mx0 = fmaxf(mx0, __uint_as_float(s[c][i]));
+                        mx1 = fmaxf(mx1, __uint_as_float(s[c][i + 1]));
+                        mx2 = fmaxf(mx2, __uint_as_float(s[c][i + 2]));
+                        mx3 = fmaxf(mx3, __uint_as_float(s[c][i + 3]));
+                    }
+                const float m_new = fmaxf(fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)), m_used);
+                if (j == 0) {
                     m_used = m_new;
-                    l *= alpha;
+                } else {
+                    const bool need = (m_new - m_used) * sl2 > kRescaleThreshold;
+                    if (__any_sync(0xffffffffu, need)) {
+                        // whole warp rescales (tcgen05.ld/st are warp-collective); rows that did not need it use
+                        // their exact (possibly tiny) correction as well, which keeps every row consistent.
+                        const float alpha = ex2_approx((m_used - m_new) * sl2);
+                        m_used = m_new;
+                        l *= alpha;
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        uint32_t o[32];
-                        tmem_ld32(tO_row + c * 32, o);
-                        tmem_wait_ld();
+                        for (int c = 0; c < 4; ++c) {
+                            uint32_t o[32];
+                            tmem_ld32(tO_row + c * 32, o);
+                            tmem_wait_ld();
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                        tmem_st32(tO_row + c * 32, o);
+                            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                            tmem_st32(tO_row + c * 32, o);
+                        }
                     }
                 }
+                const float ms = m_used * sl2;
+                float l0 = 0.f, l1 = 0.f;
+                uint32_t pk[2][32];
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+#pragma unroll
+                    for (int i = 0; i < 32; i += 2) {
+                        const float p0 = ex2_approx(fmaf(__uint_as_float(s[c][i]), sl2, -ms));
+                        const float p1 = ex2_approx(fmaf(__uint_as_float(s[c][i + 1]), sl2, -ms));
+                        l0 += p0;
+                        l1 += p1;
+                        pk[c >> 1][(c & 1) * 16 + (i >> 1)] = pack_bf16x2(p0, p1);
+                    }
+                l += l0 + l1;
+                tmem_st32(tS_row, pk[0]);
+                tmem_st32(tS_row + 32, pk[1]);
+                tmem_wait_st();
+                tc_fence_before();
+                mbar_arrive(&p_full[w]);
             }
-            const float ms = m_used * sl2;
-            float l0 = 0.f, l1 = 0.f;
-            uint32_t pk[2][32];
-#pragma unroll
-            for (int c = 0; c < 4; ++c)
-#pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    const float p0 = ex2_approx(fmaf(__uint_as_float(s[c][i]), sl2, -ms));
-                    const float p1 = ex2_approx(fmaf(__uint_as_float(s[c][i + 1]), sl2, -ms));
-                    l0 += p0;
-                    l1 += p1;
-                    pk[c >> 1][(c & 1) * 16 + (i >> 1)] = pack_bf16x2(p0, p1);
-                }
-            l += l0 + l1;
-            tmem_st32(tS_row, pk[0]);
-            tmem_st32(tS_row + 32, pk[1]);
-            tmem_wait_st();
-            tc_fence_before();
-            mbar_arrive(&p_full[w]);
-        }
 
-        // epilogue: O / l -> bf16 -> global
-        mbar_wait(o_full, 0);
-        tc_fence_after();
-        const float inv_l = 1.0f / l;
-        __nv_bfloat16* optr = p.out + static_cast<int64_t>(row) * p.ldo + head * kHD;
+            mbar_wait(o_full, 0);
+            tc_fence_after();
+            if (piece < 0) {
+                // epilogue: O / l -> bf16 -> global
+                const float inv_l = 1.0f / l;
+                __nv_bfloat16* optr = p.out + static_cast<int64_t>(row) * p.ldo + head * kHD;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            uint32_t o[32];
-            tmem_ld32(tO_row + c * 32, o);
-            tmem_wait_ld();
-            if (row < p.q_rows) {
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t o[32];
+                    tmem_ld32(tO_row + c * 32, o);
+                    tmem_wait_ld();
+                    if (row < p.q_rows) {
 #pragma unroll
-                for (int v = 0; v < 4; ++v) {
-                    uint4 pkt;
-                    pkt.x = pack_bf16x2(__uint_as_float(o[v * 8 + 0]) * inv_l, __uint_as_float(o[v * 8 + 1]) * inv_l);
-                    pkt.y = pack_bf16x2(__uint_as_float(o[v * 8 + 2]) * inv_l, __uint_as_float(o[v * 8 + 3]) * inv_l);
-                    pkt.z = pack_bf16x2(__uint_as_float(o[v * 8 + 4]) * inv_l, __uint_as_float(o[v * 8 + 5]) * inv_l);
-                    pkt.w = pack_bf16x2(__uint_as_float(o[v * 8 + 6]) * inv_l, __uint_as_float(o[v * 8 + 7]) * inv_l);
-                    *reinterpret_cast<uint4*>(optr + c * 32 + v * 8) = pkt;
+                        for (int v = 0; v < 4; ++v) {
+                            uint4 pkt;
+                            pkt.x = pack_bf16x2(__uint_as_float(o[v * 8 + 0]) * inv_l, __uint_as_float(o[v * 8 + 1]) * inv_l);
+                            pkt.y = pack_bf16x2(__uint_as_float(o[v * 8 + 2]) * inv_l, __uint_as_float(o[v * 8 + 3]) * inv_l);
+                            pkt.z = pack_bf16x2(__uint_as_float(o[v * 8 + 4]) * inv_l, __uint_as_float(o[v * 8 + 5]) * inv_l);
+                            pkt.w = pack_bf16x2(__uint_as_float(o[v * 8 + 6]) * inv_l, __uint_as_float(o[v * 8 + 7]) * inv_l);
+                            *reinterpret_cast<uint4*>(optr + c * 32 + v * 8) = pkt;
+                        }
+                    }
+                }
+            } else {
+                // partial: un-normalised O, reference max (log2 units) and sum
+                float* po = p.part_o + (static_cast<int64_t>(piece) * (2 * kQT) + row_in_pair) * kHD;
+                float* pml = p.part_ml + (static_cast<int64_t>(piece) * (2 * kQT) + row_in_pair) * 2;
+                pml[0] = m_used * sl2;
+                pml[1] = l;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t o[32];
+                    tmem_ld32(tO_row + c * 32, o);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int v = 0; v < 8; ++v)
+                        *reinterpret_cast<uint4*>(po + c * 32 + v * 4) = make_uint4(o[v * 4], o[v * 4 + 1], o[v * 4 + 2], o[v * 4 + 3]);
                 }
             }
         }
@@ -289,6 +340,43 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tmem_dealloc<512>(tmem_base);
     }
 }
+
+// Merge the key-range pieces of the split items: one warp per query row, lane owns 4 of the 128 dims.
+__global__ void __launch_bounds__(256)
+attn_combine_kernel(const AttnParams p) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int gw = blockIdx.x * 8 + warp;  // (split item, row in pair)
+    const int sitem = gw / (2 * kQT);
+    const int r = gw % (2 * kQT);
+    const int item = p.n_whole + sitem;
+    const int head = item / p.num_q_pairs;
+    const int row = (item % p.num_q_pairs) * (2 * kQT) + r;
+    if (row >= p.q_rows) return;
+    float m = -INFINITY;
+    for (int s = 0; s < p.split; ++s)
+        m = fmaxf(m, p.part_ml[((static_cast<int64_t>(sitem) * p.split + s) * (2 * kQT) + r) * 2]);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float l = 0.f;
+    for (int s = 0; s < p.split; ++s) {
+        const int64_t base = (static_cast<int64_t>(sitem) * p.split + s) * (2 * kQT) + r;
+        const float a = ex2_approx(p.part_ml[base * 2] - m);
+        l += p.part_ml[base * 2 + 1] * a;
+        const float4 o = *reinterpret_cast<const float4*>(p.part_o + base * kHD + lane * 4);
+        acc.x += o.x * a;
+        acc.y += o.y * a;
+        acc.z += o.z * a;
+        acc.w += o.w * a;
+    }
+    const float inv = 1.0f / l;
+    uint2 pkt;
+    pkt.x = pack_bf16x2(acc.x * inv, acc.y * inv);
+    pkt.y = pack_bf16x2(acc.z * inv, acc.w * inv);
+    *reinterpret_cast<uint2*>(p.out + static_cast<int64_t>(row) * p.ldo + head * kHD + lane * 4) = pkt;
+}
+
+// persistent scratch for split partials (grown on demand; one stream at a time, see header "not thread-safe")
+static float* g_part = nullptr;
+static size_t g_part_bytes = 0;
 
 static ifx_status attention_launch(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, void* out,
                                    int64_t ldo, int64_t q_rows, int64_t kv_rows, int32_t heads, int32_t head_dim,
@@ -324,14 +412,52 @@ static ifx_status attention_launch(const void* q, int64_t ldq, const void* k, co
     p.scale_log2 = softmax_scale * 1.4426950408889634f;
     p.out = static_cast<__nv_bfloat16*>(out);
     p.ldo = ldo;
-    const int grid = p.num_q_pairs * heads;
+    p.part_o = nullptr;
+    p.part_ml = nullptr;
+
+    // ---- grid shaping: split the items of the last partial wave along the keys
+    const int items = p.num_q_pairs * heads;
+    const int sms = sm_count();
+    const int n_kv = static_cast<int>((kv_rows + kKT - 1) / kKT);
+    int rem = items % sms;
+    int split = 1;
+    if (rem != 0 && n_kv >= 2 * kMaxSplit) {
+        // minimise ceil(rem * s / sms) / s  (cost of the tail in waves); ties -> smaller s
+        double best = 1.0;
+        for (int s = 2; s <= kMaxSplit; ++s) {
+            const double cost = static_cast<double>((rem * s + sms - 1) / sms) / s;
+            if (cost < best - 1e-9) {
+                best = cost;
+                split = s;
+            }
+        }
+    }
+    if (split == 1) rem = 0;
+    p.n_whole = items - rem;
+    p.split = split;
+    const int pieces = rem * split;
+    if (pieces > 0) {
+        const size_t need = static_cast<size_t>(pieces) * (2 * kQT) * (kHD + 2) * sizeof(float);
+        if (need > g_part_bytes) {
+            if (g_part) IFX_CUDA_OK(cudaFree(g_part));
+            g_part = nullptr;
+            g_part_bytes = 0;
+            IFX_CUDA_OK(cudaMalloc(&g_part, need));
+            g_part_bytes = need;
+        }
+        p.part_o = g_part;
+        p.part_ml = g_part + static_cast<size_t>(pieces) * (2 * kQT) * kHD;
+    }
+    const int grid = p.n_whole + pieces;
     {
         char label[96];
         snprintf(label, sizeof(label), "attn_fwd_kernel[Lq=%d,Lk=%d,H=%d]", p.q_rows, p.kv_rows, heads);
         ProfScope prof(label, stream);
         attn_fwd_kernel<<<grid, kAttnThreads, kAttnSmem, stream>>>(tmQ, tmK, tmV, p);
+        if (pieces > 0) attn_combine_kernel<<<rem * (2 * kQT) / 8, 256, 0, stream>>>(p);
     }
     IFX_LAUNCH_OK("attn_fwd_kernel");
+    if (pieces > 0) count_launch();
     return IFX_OK;
 }
 

@@ -36,6 +36,10 @@ constexpr int kAttnThreads = 384;
 constexpr int kAttnSmem = 2 * kTileBytes + kSlots * kTileBytes + 1024 + 256;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
 constexpr int kMaxSplit = 8;
+#ifndef IFX_ATTN_POLY_EVERY
+#define IFX_ATTN_POLY_EVERY 0
+#endif
+constexpr int kPolyEvery = IFX_ATTN_POLY_EVERY;  // 0: all exponentials on MUFU; n: one pair in n on the FMA pipe
 
 struct AttnParams {
     int32_t q_rows;
@@ -115,7 +119,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t tS[2] = {tmem_base + 0, tmem_base + 128};
     const uint32_t tO[2] = {tmem_base + 256, tmem_base + 384};
 
-    if (warp == 0) {
+    // register re-balancing: the producer / MMA warpgroup needs few registers, the softmax warps hold a whole
+    // 128-wide score row per thread (the CTA owns 384 x 168 = 64512 registers = 128 x 56 + 256 x 224; asking for more deadlocks the inc)
+    if (warp < 4) {
+      setmaxnreg_dec<56>();
+      if (warp == 0) {
         if (lane == 0) {
             // Q: one or two tiles x two 64-wide halves
             const int nq = two ? 2 : 1;
@@ -210,7 +218,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             }
             umma_commit(o_full);
         }
-    } else if (warp >= 4) {
+      }
+    } else {
+        setmaxnreg_inc<224>();
         const int w = (warp - 4) >> 2;  // which query tile
         if (w == 0 || two) {
             const int quad = warp & 3;      // TMEM lane quadrant
@@ -277,8 +287,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 for (int c = 0; c < 4; ++c)
 #pragma unroll
                     for (int i = 0; i < 32; i += 2) {
-                        const float p0 = ex2_approx(fmaf(__uint_as_float(s[c][i]), sl2, -ms));
-                        const float p1 = ex2_approx(fmaf(__uint_as_float(s[c][i + 1]), sl2, -ms));
+                        const float x0 = fmaf(__uint_as_float(s[c][i]), sl2, -ms);
+                        const float x1 = fmaf(__uint_as_float(s[c][i + 1]), sl2, -ms);
+                        // every kPolyEvery-th pair takes the FMA-pipe polynomial instead of MUFU.EX2
+                        const bool poly = kPolyEvery > 0 && ((i >> 1) % (kPolyEvery > 0 ? kPolyEvery : 1)) == kPolyEvery - 1;
+                        const float p0 = poly ? ex2_poly(x0) : ex2_approx(x0);
+                        const float p1 = poly ? ex2_poly(x1) : ex2_approx(x1);
                         l0 += p0;
                         l1 += p1;
                         pk[c >> 1][(c & 1) * 16 + (i >> 1)] = pack_bf16x2(p0, p1);

@@ -223,6 +223,82 @@ def run_case(cm, name, cfg, dtype, frames, latent_hw, local_attn_size, sink_size
           f"size={path.stat().st_size / 1e3:.0f} kB")
 
 
+def run_causvid_case(name, cfg, dtype, frames, latent_hw, steps, shift=8.0, seed=2, start_frames=0):
+    """CausVid: reference models/causvid + pipeline/causvid, constructed without touching disk."""
+    import torch.distributed  # noqa: F401
+    from inferix.kvcache_manager.kvcache_manager import KVCacheManager, KVCacheRequest
+    from inferix.models.causvid import causal_model as cvm
+    from inferix.models.causvid import wrapper as cvw
+    from inferix.models.schedulers.flow_match import FlowMatchScheduler
+    from inferix.models.wan_base import ParallelConfig
+    from inferix.pipeline.causvid.CausalInferencePipeline import CausalInferencePipeline as CVPipe
+    from inferix_b200.synthetic import synth_state_dict
+    import inferix.models.attention as att_pkg
+
+    cvm.attention = att_pkg.attention                      # SDPA fallback with dtype=q.dtype (see import_reference)
+    pc = ParallelConfig.__new__(ParallelConfig)
+    pc.ulysses_size = pc.ring_size = pc.world_size = 1
+    pc.rank = pc.local_rank = 0
+    pc.ring_strategy, pc.attn_backend = "pass-kv", "FlexAttention"
+    model = cvm.CausalWanModel(model_type="t2v", patch_size=(1, 2, 2), text_len=cfg["text_len"], in_dim=cfg["in_dim"],
+                               dim=cfg["dim"], ffn_dim=cfg["ffn_dim"], freq_dim=cfg["freq_dim"],
+                               text_dim=cfg["text_dim"], out_dim=cfg["out_dim"], num_heads=cfg["num_heads"],
+                               num_layers=cfg["num_layers"], qk_norm=True, cross_attn_norm=True, eps=1e-6,
+                               enable_kv_offload=False, parallel_config=pc)
+    for blk in model.blocks:
+        blk.self_attn.attention = cvm.attention
+    model.load_state_dict(synth_state_dict(cfg, seed=0), strict=True)
+    model = model.to(dtype).eval()
+
+    gen = cvw.WanDiffusionWrapper.__new__(cvw.WanDiffusionWrapper)
+    torch.nn.Module.__init__(gen)
+    gen.parallel_config, gen.enable_kv_offload, gen.model, gen.uniform_timestep = pc, False, model, False
+    gen.scheduler = FlowMatchScheduler(shift=shift, sigma_min=0.0, extra_one_step=True)
+    gen.scheduler.set_timesteps(1000, training=True)
+    gen.seq_len = 32760
+
+    class Text(torch.nn.Module):
+        def forward(self, text_prompts):
+            return {"prompt_embeds": text_prompts}
+
+    class NoVae:
+        def decode_to_pixel(self, x, **kw):
+            return x
+
+    fs = (latent_hw // 2) ** 2
+    pipe = CVPipe.__new__(CVPipe)
+    torch.nn.Module.__init__(pipe)
+    pipe.parallel_config, pipe.generator, pipe.text_encoder, pipe.vae = pc, gen, Text(), NoVae()
+    pipe.scheduler = gen.scheduler
+    pipe.denoising_step_list = torch.tensor(steps, dtype=torch.long)[:-1]          # :37
+    pipe.num_transformer_blocks = cfg["num_layers"]
+    pipe.frame_seq_length = pipe.per_rank_frame_seq_length = fs
+    pipe.is_kv_cache_initialized = False
+    pipe.args = types.SimpleNamespace()
+    pipe.num_frame_per_block = 3
+    model.num_frame_per_block = 3
+
+    g = torch.Generator().manual_seed(seed)
+    noise = torch.randn(1, frames, 16, latent_hw, latent_hw, generator=g).to(dtype)
+    context = torch.randn(1, 20, cfg["text_dim"], generator=g).to(dtype)
+    start = torch.randn(1, start_frames, 16, latent_hw, latent_hw, generator=g).to(dtype) if start_frames else None
+    regen = torch.Generator().manual_seed(4321)
+    real = torch.randn_like
+    torch.randn_like = lambda x, **kw: torch.randn(x.shape, generator=regen, dtype=torch.float32).to(x.dtype)
+    try:
+        with torch.no_grad():
+            _, out = pipe.inference(noise=noise, text_prompts=context, start_latents=start, return_latents=True,
+                                    kv_cache_manager=KVCacheManager("cpu"), kv_cache_requests=[KVCacheRequest("req_0")])
+    finally:
+        torch.randn_like = real
+    gold = dict(name=name, cfg=cfg, dtype=str(dtype), frames=frames, latent_hw=latent_hw, steps=steps, shift=shift,
+                noise=noise, context=context, start_latents=start, renoise_seed=4321, latents=out,
+                torch_version=torch.__version__)
+    path = ROOT / "tests" / "golden" / f"{name}.pt"
+    torch.save(gold, path)
+    print(f"wrote {path}  latents |x|={out.float().norm():.4f}  size={path.stat().st_size / 1e3:.0f} kB")
+
+
 def main():
     from inferix_b200.synthetic import TINY
     cm = import_reference()
@@ -238,6 +314,11 @@ def main():
     # window that is not a multiple of the block (7 frames), no sink
     run_case(cm, "sf_tiny_evict7_bf16", TINY, torch.bfloat16, frames=12, latent_hw=16, local_attn_size=7,
              sink_size=0, steps=[1000, 500])
+    # CausVid: shipped step list [1000, 757, 522, 0] (causvid/default_config.yaml), 2 blocks, one given as start latent
+    for dt, tag in ((torch.float32, "fp32"), (torch.bfloat16, "bf16")):
+        run_causvid_case(f"causvid_tiny_{tag}", TINY, dt, frames=6, latent_hw=16, steps=[1000, 757, 522, 0])
+    run_causvid_case("causvid_tiny_start_bf16", TINY, torch.bfloat16, frames=9, latent_hw=16,
+                     steps=[1000, 757, 522, 0], start_frames=3)
 
 
 if __name__ == "__main__":

@@ -349,3 +349,41 @@ def pipeline_inference(sd, cfg: WanConfig, sched: FlowMatchSigmas, noise: torch.
         if block_callback is not None:
             block_callback(out[:, start - n:start], blk)
     return out, caches
+
+
+# ----------------------------------------------------------------------------- CausVid
+def causvid_pipeline_inference(sd, cfg: WanConfig, sched: FlowMatchSigmas, noise: torch.Tensor, context: torch.Tensor,
+                               denoising_steps: torch.Tensor, num_frame_per_block: int, frame_seq_length: int,
+                               cache_tokens: int, start_latents: Optional[torch.Tensor] = None, attn_dtype=None,
+                               noise_fn: Optional[Callable] = None):
+    """CausVid block scheduler, pipeline/causvid/CausalInferencePipeline.py:94-257 (latents only), over the CausVid
+    model (models/causvid/causal_model.py): every forward writes cache[kv_start:kv_end] and attends cache[0:kv_end]
+    (:169-175, :262) — the un-windowed case of cache_append — and the wrapper returns x0 only (wrapper.py:269-305).
+    `denoising_steps` is the list AFTER the reference dropped its trailing entry (:37)."""
+    assert cfg.local_attn_size == -1
+    b, num_frames = noise.shape[:2]
+    n = num_frame_per_block
+    caches = new_cache(cfg, cache_tokens, b, noise.dtype)
+    cross = [dict(is_init=False) for _ in range(cfg.num_layers)]
+    out = torch.zeros_like(noise)
+    noise_fn = noise_fn or torch.randn_like
+    num_input_blocks = start_latents.shape[1] // n if start_latents is not None else 0
+    for blk in range(num_frames // n):
+        start = blk * n * frame_seq_length
+        x = noise[:, blk * n:(blk + 1) * n]
+        zeros = torch.ones([b, n], dtype=torch.int64) * 0
+        if start_latents is not None and blk < num_input_blocks:
+            ref = start_latents[:, blk * n:(blk + 1) * n]
+            out[:, blk * n:(blk + 1) * n] = ref
+            generator_forward(sd, cfg, sched, ref, zeros, context, caches, cross, start, attn_dtype)
+            continue
+        x0 = ts = None
+        for idx, cur in enumerate(denoising_steps):
+            ts = torch.ones([b, n], dtype=torch.int64) * cur
+            _, x0 = generator_forward(sd, cfg, sched, x, ts, context, caches, cross, start, attn_dtype)
+            if idx < len(denoising_steps) - 1:
+                nxt = denoising_steps[idx + 1] * torch.ones([b], dtype=torch.long)
+                x = sched.add_noise(x0.flatten(0, 1), noise_fn(x0.flatten(0, 1)), nxt).view(x0.shape)
+        out[:, blk * n:(blk + 1) * n] = x0
+        generator_forward(sd, cfg, sched, x0, ts * 0, context, caches, cross, start, attn_dtype)
+    return out, caches

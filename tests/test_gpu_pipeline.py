@@ -120,3 +120,39 @@ def test_block_forward_matches_oracle():
                   current_start=start, kv_cache_manager=mgr, kv_cache_requests=[req])
         assert rel_l2(out, ref) <= 5e-3, f"step {step}"
         assert (int(meta["global_end_index"]), int(meta["local_end_index"])) == (caches[1].global_end, caches[1].local_end)
+
+
+@pytest.mark.parametrize("case", ["causvid_tiny", "causvid_tiny_start"])
+def test_causvid_pipeline_matches_reference(case, golden_dir):
+    """CausVid surface (explicit kv_start / kv_end, x0-only wrapper, steps[:-1]) against the reference's own run."""
+    from inferix_b200.causvid import CausVidCausalWanModel, CausVidDiffusionWrapper, CausVidInferencePipeline
+    g16 = torch.load(golden_dir / f"{case}_bf16.pt", weights_only=False)
+    model = CausVidCausalWanModel(**g16["cfg"])
+    model.load_state_dict(synth_state_dict(g16["cfg"], seed=0))
+    model = model.to(torch.bfloat16).to(DEV)
+    args = types.SimpleNamespace(denoising_step_list=g16["steps"], warp_denoising_step=False, num_frame_per_block=3)
+    pipe = CausVidInferencePipeline(args, DEV, generator=CausVidDiffusionWrapper(model=model, timestep_shift=g16["shift"]))
+    cpu_gen = torch.Generator().manual_seed(g16["renoise_seed"])
+    pipe.renoise_fn = lambda x: torch.randn(x.shape, generator=cpu_gen, dtype=torch.float32).to(x.dtype).to(x.device)
+    blocks = []
+    start = g16["start_latents"]
+    mgr, reqs = KVCacheManager(DEV), [KVCacheRequest("prompt text as id")]      # causvid keys requests by prompt
+    _, out = pipe.inference(noise=g16["noise"].to(DEV), text_prompts=g16["context"].to(DEV),
+                            start_latents=None if start is None else start.to(DEV), return_latents=True,
+                            kv_cache_manager=mgr, kv_cache_requests=reqs,
+                            block_callback=lambda lat, i: blocks.append(i))
+    err = rel_l2(out, g16["latents"])
+    print(f"{case}: ours-vs-ref-bf16 {err:.3e}")
+    assert err <= 5e-3
+    if start is None:
+        g32 = torch.load(golden_dir / f"{case}_fp32.pt", weights_only=False)
+        assert rel_l2(out, g32["latents"]) <= 1.5 * rel_l2(g16["latents"], g32["latents"])
+        assert blocks == [0, 1]
+    else:
+        assert blocks == [1, 2]                                    # block 0 came from start_latents
+    # second segment on the same pipeline object: caches are reset, result reproduces
+    cpu_gen.manual_seed(g16["renoise_seed"])
+    _, out2 = pipe.inference(noise=g16["noise"].to(DEV), text_prompts=g16["context"].to(DEV),
+                             start_latents=None if start is None else start.to(DEV), return_latents=True,
+                             kv_cache_manager=mgr, kv_cache_requests=reqs)
+    assert torch.equal(out2, out)

@@ -84,3 +84,20 @@ def test_frame_provenance_kat_from_survey():
                             [0, 10, 11, 12, 13, 14]]
     assert run(7, 1, 5) == [[0, 1, 2], [0, 1, 2, 3, 4, 5], [0, 3, 4, 5, 6, 7, 8], [0, 6, 7, 8, 9, 10, 11],
                             [0, 9, 10, 11, 12, 13, 14]]
+
+
+@pytest.mark.parametrize("case", ["causvid_tiny_fp32", "causvid_tiny_bf16", "causvid_tiny_start_bf16"])
+def test_causvid_oracle_matches_reference_bit_exact(case, golden_dir):
+    torch.set_num_threads(1)
+    gold = torch.load(golden_dir / f"{case}.pt", weights_only=False)
+    dtype = torch.float32 if "float32" in gold["dtype"] else torch.bfloat16
+    cfg = wo.WanConfig(**gold["cfg"])
+    sd = {k: v.to(dtype) for k, v in synth_state_dict(gold["cfg"], seed=0).items()}
+    sched = wo.FlowMatchSigmas(shift=gold["shift"])
+    steps = torch.tensor(gold["steps"], dtype=torch.long)[:-1]          # causvid pipeline :37, no warping
+    fs = (gold["latent_hw"] // 2) ** 2
+    regen = torch.Generator().manual_seed(gold["renoise_seed"])
+    out, _ = wo.causvid_pipeline_inference(
+        sd, cfg, sched, gold["noise"], gold["context"], steps, 3, fs, 32760, start_latents=gold["start_latents"],
+        noise_fn=lambda x: torch.randn(x.shape, generator=regen, dtype=torch.float32).to(x.dtype))
+    assert torch.equal(out, gold["latents"]), f"max |diff| = {(out.float() - gold['latents'].float()).abs().max()}"

@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 ROOT = Path(__file__).resolve().parent.parent
 
 
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_sp_pipeline_equals_single_gpu(world):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")

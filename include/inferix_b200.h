@@ -154,10 +154,12 @@ ifx_status ifx_kv_append(ifx_kv* kv, const ifx_kv_plan* plan, const void* k_src,
                          int64_t rows, void* stream);
 
 /* Sequence-parallel append: k_src / v_src hold the all-gathered new rows rank-major, [world, frames*chunk, H*D]
- * (rank r owns hw indices [r*chunk, (r+1)*chunk) of every frame, causal_model.py:939-942); they are written in the
- * single-process token order (frame, rank, hw) == 'b (cp f hw) c -> b (f cp hw) c' of causal_model.py:1018. */
+ * with `src_rank_stride` elements between consecutive ranks (so K and V may come out of ONE all-gather of a
+ * [world, 2, rows, H*D] buffer).  Rank r owns hw indices [r*chunk, (r+1)*chunk) of every frame
+ * (causal_model.py:939-942); rows are written in the single-process token order (frame, rank, hw)
+ * == 'b (cp f hw) c -> b (f cp hw) c' of causal_model.py:1018. */
 ifx_status ifx_kv_append_sp(ifx_kv* kv, const ifx_kv_plan* plan, const void* k_src, const void* v_src,
-                            int32_t world, int32_t frames, int32_t chunk, void* stream);
+                            int64_t src_rank_stride, int32_t world, int32_t frames, int32_t chunk, void* stream);
 
 /* WanRMSNorm on its own (cross-attention q / text k, wan_base/model.py:77,82): out = bf16(bf16(x*rsqrt(ms+eps))*w) */
 ifx_status ifx_rmsnorm(const void* x, int64_t ldx, const void* weight, void* out, int64_t ldo, int64_t rows,

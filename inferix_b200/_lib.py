@@ -99,7 +99,7 @@ SIGNATURES = {
     "ifx_qk_norm_rope_append": (C.c_int, [_vp, _i64, _vp, _vp, _vp, C.POINTER(RopeGrid), _vp, _i64, _vp,
                                           C.POINTER(KvPlan), _vp, _vp, _i64, _i32, _i32, _f32, _vp]),
     "ifx_kv_append": (C.c_int, [_vp, C.POINTER(KvPlan), _vp, _vp, _i64, _i64, _vp]),
-    "ifx_kv_append_sp": (C.c_int, [_vp, C.POINTER(KvPlan), _vp, _vp, _i32, _i32, _i32, _vp]),
+    "ifx_kv_append_sp": (C.c_int, [_vp, C.POINTER(KvPlan), _vp, _vp, _i64, _i32, _i32, _i32, _vp]),
     "ifx_rmsnorm": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _i64, _i32, _f32, _vp]),
     "ifx_attention": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _vp, _i64, _i64, _i64, _i32, _i32, _f32, _vp]),
     "ifx_attention_kv": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _i64, _f32, _vp]),

@@ -302,6 +302,7 @@ struct SpAppendParams {
     __nv_bfloat16* cache_v;
     const __nv_bfloat16* src_k;
     const __nv_bfloat16* src_v;
+    int64_t rank_stride;
     int32_t world, frames, chunk, page_tokens, C;
     PageList pl;
 };
@@ -319,8 +320,9 @@ sp_append_kernel(const SpAppendParams p) {
         const int64_t r = row / rows_per_rank, rem = row % rows_per_rank;
         const int64_t t = (rem / p.chunk) * fs + r * p.chunk + rem % p.chunk;  // token index inside the block
         const int64_t crow = static_cast<int64_t>(p.pl.pages[t / p.page_tokens]) * p.page_tokens + t % p.page_tokens;
-        reinterpret_cast<uint4*>(p.cache_k + crow * p.C)[vi] = reinterpret_cast<const uint4*>(p.src_k + row * p.C)[vi];
-        reinterpret_cast<uint4*>(p.cache_v + crow * p.C)[vi] = reinterpret_cast<const uint4*>(p.src_v + row * p.C)[vi];
+        const int64_t srow = r * p.rank_stride + rem * p.C;
+        reinterpret_cast<uint4*>(p.cache_k + crow * p.C)[vi] = reinterpret_cast<const uint4*>(p.src_k + srow)[vi];
+        reinterpret_cast<uint4*>(p.cache_v + crow * p.C)[vi] = reinterpret_cast<const uint4*>(p.src_v + srow)[vi];
     }
 }
 
@@ -329,7 +331,8 @@ sp_append_kernel(const SpAppendParams p) {
 using namespace ifx;
 
 extern "C" ifx_status ifx_kv_append_sp(ifx_kv* kv_, const ifx_kv_plan* plan, const void* k_src, const void* v_src,
-                                       int32_t world, int32_t frames, int32_t chunk, void* stream) {
+                                       int64_t src_rank_stride, int32_t world, int32_t frames, int32_t chunk,
+                                       void* stream) {
     KvImpl* kv = kv_cast(kv_);
     if (!kv) return set_error(IFX_ERR_HANDLE, "ifx_kv_append_sp: bad kv handle");
     IFX_CHECK_ARG(plan && k_src && v_src, "ifx_kv_append_sp: null pointer");
@@ -347,6 +350,9 @@ extern "C" ifx_status ifx_kv_append_sp(ifx_kv* kv_, const ifx_kv_plan* plan, con
     p.chunk = chunk;
     p.page_tokens = kv->page_tokens;
     p.C = kv->heads * kv->head_dim;
+    IFX_CHECK_ARG(src_rank_stride >= static_cast<int64_t>(frames) * chunk * p.C && src_rank_stride % 8 == 0,
+                  "ifx_kv_append_sp: bad src_rank_stride");
+    p.rank_stride = src_rank_stride;
     p.pl.n = plan->num_pages;
     for (int i = 0; i < plan->num_pages; ++i) p.pl.pages[i] = plan->pages[i];
     const int64_t total = rows * (p.C >> 3);

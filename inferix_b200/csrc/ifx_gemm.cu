@@ -15,14 +15,18 @@
 namespace ifx {
 
 constexpr int kBM = 128;
-constexpr int kBN = 256;
 constexpr int kBK = 64;  // 64 bf16 = 128 bytes = one swizzle atom row
-constexpr int kStages = 4;
 constexpr int kABytes = kBM * kBK * 2;  // 16 KiB
-constexpr int kBBytes = kBN * kBK * 2;  // 32 KiB
-constexpr int kStageBytes = kABytes + kBBytes;
 constexpr int kGemmThreads = 256;
-constexpr int kGemmSmem = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+// Tile width is a template parameter: 256 (4 stages of 48 KiB) is the throughput shape; 128 (6 stages of 32 KiB)
+// is picked by the host when the 256-wide grid would leave most SMs idle (small M under sequence parallelism).
+template <int kBN>
+struct GemmCfg {
+    static constexpr int kStages = kBN == 256 ? 4 : 6;
+    static constexpr int kBBytes = kBN * kBK * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kSmem = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
 
 struct GemmParams {
     int64_t M;
@@ -48,10 +52,13 @@ __device__ __forceinline__ float gelu_tanh_f(float x) {
     return 0.5f * x * (1.0f + t);
 }
 
-template <int kEpi>
+template <int kEpi, int kBN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const GemmParams p) {
+    constexpr int kStages = GemmCfg<kBN>::kStages;
+    constexpr int kBBytes = GemmCfg<kBN>::kBBytes;
+    constexpr int kStageBytes = GemmCfg<kBN>::kStageBytes;
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B tiles need 1024-byte alignment
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -230,12 +237,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
 }
 
-template <int kEpi>
+template <int kEpi, int kBN>
 static ifx_status launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p,
                               cudaStream_t stream) {
+    constexpr int kGemmSmem = GemmCfg<kBN>::kSmem;
     static bool configured = false;
     if (!configured) {
-        IFX_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tn_kernel<kEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        IFX_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tn_kernel<kEpi, kBN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          kGemmSmem));
         configured = true;
     }
@@ -243,9 +251,10 @@ static ifx_status launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, co
     const int grid = tiles < sm_count() ? tiles : sm_count();
     {
         char label[96];
-        snprintf(label, sizeof(label), "gemm_bf16_tn_kernel<%d>[M=%lld,N=%d,K=%d]", kEpi, (long long)p.M, p.N, p.K);
+        snprintf(label, sizeof(label), "gemm_bf16_tn_kernel<%d,%d>[M=%lld,N=%d,K=%d]", kEpi, kBN, (long long)p.M, p.N,
+                 p.K);
         ProfScope prof(label, stream);
-        gemm_bf16_tn_kernel<kEpi><<<grid, kGemmThreads, kGemmSmem, stream>>>(tmA, tmB, p);
+        gemm_bf16_tn_kernel<kEpi, kBN><<<grid, kGemmThreads, kGemmSmem, stream>>>(tmA, tmB, p);
     }
     IFX_LAUNCH_OK("gemm_bf16_tn_kernel");
     return IFX_OK;
@@ -275,10 +284,20 @@ extern "C" ifx_status ifx_gemm_bf16(const void* A, int64_t lda, const void* W, i
                       aligned16(gate),
                   "ifx_gemm_bf16: pointers must be 16-byte aligned");
 
+    // tile width: wave efficiency of the 256-wide grid vs the 128-wide one (which is ~15 % less efficient per tile
+    // because A and B shared-memory reads per MMA are no longer amortised over 256 columns)
+    const int sms = sm_count();
+    const int64_t mt = (M + kBM - 1) / kBM;
+    auto wave_eff = [&](int bn) {
+        const int64_t tiles = mt * ((N + bn - 1) / bn);
+        return static_cast<double>(tiles) / static_cast<double>(((tiles + sms - 1) / sms) * sms);
+    };
+    const int bn = (0.85 * wave_eff(128) > wave_eff(256)) ? 128 : 256;
+
     CUtensorMap tmA, tmB;
     ifx_status st = make_tmap_bf16_2d(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, kBK, kBM);
     if (st != IFX_OK) return st;
-    st = make_tmap_bf16_2d(&tmB, W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw, kBK, kBN);
+    st = make_tmap_bf16_2d(&tmB, W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw, kBK, bn);
     if (st != IFX_OK) return st;
 
     GemmParams p;
@@ -294,11 +313,18 @@ extern "C" ifx_status ifx_gemm_bf16(const void* A, int64_t lda, const void* W, i
     p.gate_frame_stride = gate_frame_stride;
     p.tokens_per_frame = tokens_per_frame > 0 ? tokens_per_frame : 1;
     p.num_m_tiles = static_cast<int32_t>((M + kBM - 1) / kBM);
-    p.num_n_tiles = (N + kBN - 1) / kBN;
+    p.num_n_tiles = (N + bn - 1) / bn;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (bn == 256) {
+        switch (epilogue) {
+            case IFX_EPI_BIAS: return launch_gemm<IFX_EPI_BIAS, 256>(tmA, tmB, p, s);
+            case IFX_EPI_BIAS_GELU: return launch_gemm<IFX_EPI_BIAS_GELU, 256>(tmA, tmB, p, s);
+            default: return launch_gemm<IFX_EPI_BIAS_GATE_RES, 256>(tmA, tmB, p, s);
+        }
+    }
     switch (epilogue) {
-        case IFX_EPI_BIAS: return launch_gemm<IFX_EPI_BIAS>(tmA, tmB, p, s);
-        case IFX_EPI_BIAS_GELU: return launch_gemm<IFX_EPI_BIAS_GELU>(tmA, tmB, p, s);
-        default: return launch_gemm<IFX_EPI_BIAS_GATE_RES>(tmA, tmB, p, s);
+        case IFX_EPI_BIAS: return launch_gemm<IFX_EPI_BIAS, 128>(tmA, tmB, p, s);
+        case IFX_EPI_BIAS_GELU: return launch_gemm<IFX_EPI_BIAS_GELU, 128>(tmA, tmB, p, s);
+        default: return launch_gemm<IFX_EPI_BIAS_GATE_RES, 128>(tmA, tmB, p, s);
     }
 }

@@ -181,13 +181,17 @@ class PagedKV:
                                              k_rows.stride(0), k_rows.shape[0], _stream()))
 
     def append_sp(self, plan: KvPlan, k_gathered: torch.Tensor, v_gathered: torch.Tensor, frames: int) -> None:
-        """k/v_gathered: [world, frames*chunk, H*D] rank-major (all_gather output) -> (frame, rank, hw) token order."""
-        if k_gathered.dim() != 3 or not k_gathered.is_contiguous() or not v_gathered.is_contiguous() \
-                or k_gathered.shape != v_gathered.shape or k_gathered.dtype != torch.bfloat16:
-            raise ValueError("append_sp: contiguous bf16 [world, frames*chunk, H*D] tensors expected")
+        """k/v_gathered: [world, frames*chunk, H*D] rank-major views (rows contiguous, any common rank stride — e.g.
+        the two halves of one [world, 2, rows, H*D] all-gather output) -> (frame, rank, hw) token order."""
+        ok = (k_gathered.dim() == 3 and k_gathered.shape == v_gathered.shape and k_gathered.dtype == torch.bfloat16
+              and k_gathered.stride(2) == 1 and k_gathered.stride(1) == k_gathered.shape[2]
+              and k_gathered.stride() == v_gathered.stride())
+        if not ok:
+            raise ValueError("append_sp: bf16 [world, frames*chunk, H*D] views with contiguous rows expected")
         world, rows, _ = k_gathered.shape
         _lib.check(_lib.load().ifx_kv_append_sp(self.handle, C.byref(plan), k_gathered.data_ptr(),
-                                                v_gathered.data_ptr(), world, frames, rows // frames, _stream()))
+                                                v_gathered.data_ptr(), k_gathered.stride(0), world, frames,
+                                                rows // frames, _stream()))
 
     def export(self, start: int, length: int):
         """Tokens [start, start+length) in the reference's logical order -> (k, v) each [length, H*D]."""

@@ -239,10 +239,9 @@ class CausalWanAttentionBlock(nn.Module):
         ops.ln_modulate(x, ws.h, shift=m[:, 0], scale=m[:, 1], tokens_per_frame=fs, eps=self.eps)
         ops.gemm(ws.h, qkv_w, qkv_b, ws.qkv)
         ops.qk_norm_rope_append(ws.qkv, sa.norm_q.weight, sa.norm_k.weight, freqs, grid, heads, hd, q_out=ws.q,
-                                k_out=ws.k_new, v_out=ws.v_new, eps=self.eps)
-        kg = all_gather_rows(ws.k_new, pc, ws.k_all)
-        vg = all_gather_rows(ws.v_new, pc, ws.v_all)
-        store.append_sp(plan, kg, vg, frames)
+                                k_out=ws.kv_new[0], v_out=ws.kv_new[1], eps=self.eps)
+        kvg = all_gather_rows(ws.kv_new, pc, ws.kv_all)           # ONE all-gather: [P, 2, rows, C]
+        store.append_sp(plan, kvg[:, 0], kvg[:, 1], frames)
         store.attention(ws.q, ws.attn)
         ops.gemm(ws.attn, sa.o.weight, sa.o.bias, x, epilogue=ops.EPI_BIAS_GATE_RES, residual=x, gate=m[:, 2],
                  tokens_per_frame=fs)
@@ -267,8 +266,8 @@ class _Workspace:
         self.rows = rows
         self.h, self.qkv, self.q, self.attn, self.ffn = buf(rows, dim), buf(rows, 3 * dim), buf(rows, dim), buf(rows, dim), buf(rows, ffn_dim)
         if world > 1:
-            self.k_new, self.v_new = buf(rows, dim), buf(rows, dim)
-            self.k_all, self.v_all = buf(world, rows, dim), buf(world, rows, dim)
+            self.kv_new = buf(2, rows, dim)              # this rank's new roped-K | V, one send buffer
+            self.kv_all = buf(world, 2, rows, dim)       # all-gather destination
 
 
 class CausalHead(nn.Module):

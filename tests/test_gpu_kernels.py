@@ -204,6 +204,11 @@ def test_sp_append_layout():
     kv.append_sp(plan, shard(full_k).to(DEV).contiguous(), shard(full_v).to(DEV).contiguous(), frames)
     ke, ve = kv.export(0, frames * fs)
     assert torch.equal(ke.cpu(), full_k) and torch.equal(ve.cpu(), full_v)
+    # K and V out of one [world, 2, rows, C] gather buffer (strided rank views)
+    both = torch.stack([shard(full_v), shard(full_k)], dim=1).to(DEV).contiguous()
+    kv.append_sp(kv.plan_append(frames * fs, frames * fs, 0, True), both[:, 0], both[:, 1], frames)
+    ke, ve = kv.export(frames * fs, frames * fs)
+    assert torch.equal(ke.cpu(), full_v) and torch.equal(ve.cpu(), full_k)
 
 
 def test_kv_manager_reference_api():

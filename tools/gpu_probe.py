@@ -169,6 +169,31 @@ def check_perf():
             print("   flash_attn unavailable:", ex)
 
 
+def check_perf_sp8():
+    """Per-rank shapes of the 8-way sequence-parallel run (S/P = 1350 rows)."""
+    torch.manual_seed(0)
+    S, C, F, H = 1350, 1536, 8960, 12
+    for (N, K, name) in [(3 * C, C, "qkv"), (C, C, "o"), (F, C, "ffn1"), (C, F, "ffn2")]:
+        x = torch.randn(S, K, device=dev).bfloat16()
+        w = (torch.randn(N, K, device=dev) / math.sqrt(K)).bfloat16()
+        b = torch.randn(N, device=dev).bfloat16()
+        out = torch.empty(S, N, device=dev, dtype=torch.bfloat16)
+        ms = timeit(lambda: ops.gemm(x, w, b, out=out), iters=20)
+        ms_t = timeit(lambda: torch.nn.functional.linear(x, w, b), iters=20)
+        fl = 2.0 * S * N * K
+        ref = torch.nn.functional.linear(x, w, b)
+        print(f"gemm {name} M={S}: {ms * 1e3:.1f} us {fl / ms / 1e9:.1f} TFLOP/s   (cuBLAS {ms_t * 1e3:.1f} us {fl / ms_t / 1e9:.1f})",
+              flush=True)
+        stats("vs cuBLAS", out, ref)
+    Lk = 86400
+    q = torch.randn(S, C, device=dev).bfloat16()
+    k = torch.randn(Lk, C, device=dev).bfloat16()
+    v = torch.randn(Lk, C, device=dev).bfloat16()
+    out = torch.empty(S, C, device=dev, dtype=torch.bfloat16)
+    ms = timeit(lambda: ops.attention(q, k, v, H, out=out), iters=10, warm=2)
+    print(f"attn Lq={S} Lk={Lk}: {ms:.3f} ms {4.0 * S * Lk * C / ms / 1e9:.1f} TFLOP/s", flush=True)
+
+
 def check_attn_once():
     """Self-attention at the BASELINE config-2 shape, a few launches (target of `ncu --set full -k regex:attn_fwd`)."""
     S, C, H, Lk = 10800, 1536, 12, 86400

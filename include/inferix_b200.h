@@ -127,6 +127,28 @@ ifx_status ifx_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw,
                          int64_t ldr, const void* gate, int64_t gate_frame_stride, int64_t tokens_per_frame,
                          void* stream);
 
+/* ---- FP8 (e4m3) linears, per-tensor scales.  In-tree specification: MAGI's PerTensorQuantizedFp8Linear +
+ * div_clamp_to (models/magi/dit/dit_module.py:367-387,434-459):
+ *     x_q = e4m3( bf16( clamp(float(x) / input_scale, -448, 448) ) )
+ *     y   = bf16( (x_q @ W_q^T) * (input_scale * weight_scale) [+ bias] )            (flashinfer.bmm_fp8)
+ * The Wan quantization examples call DAX (not vendored): "DAX parity unpinned". */
+
+/* Activation quantisation x[rows, cols] bf16 -> e4m3 with a static per-tensor scale. */
+ifx_status ifx_quantize_fp8(const void* x, int64_t ldx, void* out, int64_t ldo, int64_t rows, int32_t cols,
+                            float scale, void* stream);
+/* ifx_ln_modulate whose result is quantised on the way out (out: e4m3 [rows, cols]) — the quantisation of the
+ * QKV / cross-q / FFN1 GEMM inputs fused into the kernel that produces them. */
+ifx_status ifx_ln_modulate_fp8(const void* x, void* out, const void* ln_weight, const void* ln_bias, const void* shift,
+                               const void* scale, int64_t mod_frame_stride, int64_t rows, int32_t cols,
+                               int64_t tokens_per_frame, float eps, float out_scale, void* stream);
+/* out[M,N] = epilogue((A_q[M,K] @ W_q[N,K]^T) * alpha + bias): tcgen05 kind::f8f6f4 (K = 32 per MMA, twice the
+ * bf16 rate), fp32 accumulation; dequantisation (alpha = input_scale * weight_scale), bias and the same three
+ * epilogues as ifx_gemm_bf16 are fused.  A_q / W_q are e4m3 bytes, K % 16 == 0; bias / residual / gate / out bf16. */
+ifx_status ifx_gemm_fp8(const void* A, int64_t lda, const void* W, int64_t ldw, float alpha, const void* bias, void* out,
+                        int64_t ldo, int64_t M, int32_t N, int32_t K, int32_t epilogue, const void* residual,
+                        int64_t ldr, const void* gate, int64_t gate_frame_stride, int64_t tokens_per_frame,
+                        void* stream);
+
 /* 3-D RoPE table: complex128 [1024, head_dim/2] exactly as CausalWanModel.freqs (causal_model.py:634-641,
  * rope_params components.py:34-52), uploaded once by the host as interleaved (cos, sin) doubles. */
 typedef struct ifx_rope_grid {

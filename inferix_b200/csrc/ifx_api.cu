@@ -76,15 +76,31 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
+static ifx_status make_tmap_2d(CUtensorMap* out, CUtensorMapDataType dt, int elem_bytes, const void* base,
+                               uint64_t inner_elems, uint64_t outer_rows, uint64_t row_stride_elems,
+                               uint32_t box_inner, uint32_t box_rows);
+
 ifx_status make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t inner_elems, uint64_t outer_rows,
                              uint64_t row_stride_elems, uint32_t box_inner, uint32_t box_rows) {
+    return make_tmap_2d(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, inner_elems, outer_rows, row_stride_elems,
+                        box_inner, box_rows);
+}
+ifx_status make_tmap_u8_2d(CUtensorMap* out, const void* base, uint64_t inner_elems, uint64_t outer_rows,
+                           uint64_t row_stride_elems, uint32_t box_inner, uint32_t box_rows) {
+    return make_tmap_2d(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, base, inner_elems, outer_rows, row_stride_elems,
+                        box_inner, box_rows);
+}
+
+static ifx_status make_tmap_2d(CUtensorMap* out, CUtensorMapDataType dt, int elem_bytes, const void* base,
+                               uint64_t inner_elems, uint64_t outer_rows, uint64_t row_stride_elems,
+                               uint32_t box_inner, uint32_t box_rows) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return set_error(IFX_ERR_CUDA, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
     cuuint64_t dims[2] = {inner_elems, outer_rows};
-    cuuint64_t strides[1] = {row_stride_elems * 2};
+    cuuint64_t strides[1] = {row_stride_elems * static_cast<uint64_t>(elem_bytes)};
     cuuint32_t box[2] = {box_inner, box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+    CUresult r = fn(out, dt, 2, const_cast<void*>(base), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)

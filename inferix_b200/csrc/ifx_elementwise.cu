@@ -52,11 +52,23 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 }
 
 // ------------------------------------------------------------------ LayerNorm + modulation
+// e4m3( bf16( clamp(v / scale) ) ) for 8 values -> 8 bytes   (div_clamp_to, dit_module.py:367-387)
+__device__ __forceinline__ uint2 quant8_e4m3(const float (&v)[8], float scale) {
+    float q[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) q[e] = bf16_round(fminf(fmaxf(__fdiv_rn(v[e], scale), -448.f), 448.f));
+    uint2 o;
+    o.x = static_cast<uint32_t>(pack_e4m3x2(q[0], q[1])) | (static_cast<uint32_t>(pack_e4m3x2(q[2], q[3])) << 16);
+    o.y = static_cast<uint32_t>(pack_e4m3x2(q[4], q[5])) | (static_cast<uint32_t>(pack_e4m3x2(q[6], q[7])) << 16);
+    return o;
+}
+
+template <bool kOutFp8>
 __global__ void __launch_bounds__(kRowThreads)
-ln_modulate_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
+ln_modulate_kernel(const __nv_bfloat16* __restrict__ x, void* __restrict__ out_,
                    const __nv_bfloat16* __restrict__ ln_w, const __nv_bfloat16* __restrict__ ln_b,
                    const __nv_bfloat16* __restrict__ shift, const __nv_bfloat16* __restrict__ scale,
-                   int64_t mod_frame_stride, int cols, int64_t tokens_per_frame, float eps) {
+                   int64_t mod_frame_stride, int cols, int64_t tokens_per_frame, float eps, float out_scale) {
     __shared__ float scratch[2 * 32];
     const int64_t row = blockIdx.x;
     const int nvec = cols >> 3;
@@ -93,7 +105,8 @@ ln_modulate_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restric
     const int64_t frame = row / tokens_per_frame;
     const uint4* sh = shift ? reinterpret_cast<const uint4*>(shift + frame * mod_frame_stride) : nullptr;
     const uint4* sc = scale ? reinterpret_cast<const uint4*>(scale + frame * mod_frame_stride) : nullptr;
-    uint4* orow = reinterpret_cast<uint4*>(out + row * cols);
+    uint4* orow = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(out_) + row * cols);
+    uint2* orow8 = reinterpret_cast<uint2*>(static_cast<uint8_t*>(out_) + row * cols);
 #pragma unroll
     for (int i = 0; i < kMaxVecPerThread; ++i) {
         const int vi = threadIdx.x + i * kRowThreads;
@@ -119,8 +132,30 @@ ln_modulate_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restric
                     y[e] = bf16_round(y[e] * one_plus) + b[e];  // final rounding happens in pack8
                 }
             }
-            orow[vi] = pack8(y);
+            if (kOutFp8) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) y[e] = bf16_round(y[e]);  // the bf16 tensor the reference would quantise
+                orow8[vi] = quant8_e4m3(y, out_scale);
+            } else {
+                orow[vi] = pack8(y);
+            }
         }
+    }
+}
+
+// ------------------------------------------------------------------ bf16 -> e4m3 quantisation
+__global__ void __launch_bounds__(256)
+quantize_fp8_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, uint8_t* __restrict__ out, int64_t ldo,
+                    int64_t rows, int cols, float scale) {
+    const int nvec = cols >> 3;
+    const int64_t total = rows * nvec;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t r = i / nvec;
+        const int vi = static_cast<int>(i % nvec);
+        float v[8];
+        unpack8(reinterpret_cast<const uint4*>(x + r * ldx)[vi], v);
+        reinterpret_cast<uint2*>(out + r * ldo)[vi] = quant8_e4m3(v, scale);
     }
 }
 
@@ -367,9 +402,10 @@ extern "C" ifx_status ifx_kv_append_sp(ifx_kv* kv_, const ifx_kv_plan* plan, con
     return IFX_OK;
 }
 
-extern "C" ifx_status ifx_ln_modulate(const void* x, void* out, const void* ln_weight, const void* ln_bias,
-                                      const void* shift, const void* scale, int64_t mod_frame_stride, int64_t rows,
-                                      int32_t cols, int64_t tokens_per_frame, float eps, void* stream) {
+static ifx_status ln_modulate_entry(const void* x, void* out, const void* ln_weight, const void* ln_bias,
+                                    const void* shift, const void* scale, int64_t mod_frame_stride, int64_t rows,
+                                    int32_t cols, int64_t tokens_per_frame, float eps, bool fp8, float out_scale,
+                                    void* stream) {
     IFX_CHECK_ARG(x && out, "ifx_ln_modulate: null pointer");
     IFX_CHECK_ARG(rows > 0 && cols > 0 && cols % 8 == 0 && cols <= kRowThreads * kMaxVecPerThread * 8,
                   "ifx_ln_modulate: cols must be a multiple of 8 and <= %d (got %d)",
@@ -378,15 +414,58 @@ extern "C" ifx_status ifx_ln_modulate(const void* x, void* out, const void* ln_w
     IFX_CHECK_ARG((shift == nullptr) == (scale == nullptr), "ifx_ln_modulate: shift and scale go together");
     IFX_CHECK_ARG(!scale || (tokens_per_frame > 0 && mod_frame_stride % 8 == 0),
                   "ifx_ln_modulate: bad modulation layout");
+    IFX_CHECK_ARG(!fp8 || out_scale > 0.f, "ifx_ln_modulate_fp8: out_scale must be positive");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int64_t tpf = tokens_per_frame > 0 ? tokens_per_frame : 1;
     {
-        ProfScope prof("ln_modulate_kernel", static_cast<cudaStream_t>(stream));
-        ln_modulate_kernel<<<static_cast<unsigned>(rows), kRowThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-            static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(out),
-            static_cast<const __nv_bfloat16*>(ln_weight), static_cast<const __nv_bfloat16*>(ln_bias),
-            static_cast<const __nv_bfloat16*>(shift), static_cast<const __nv_bfloat16*>(scale), mod_frame_stride, cols,
-            tokens_per_frame > 0 ? tokens_per_frame : 1, eps);
+        ProfScope prof(fp8 ? "ln_modulate_kernel<fp8>" : "ln_modulate_kernel", st);
+        if (fp8)
+            ln_modulate_kernel<true><<<static_cast<unsigned>(rows), kRowThreads, 0, st>>>(
+                static_cast<const __nv_bfloat16*>(x), out, static_cast<const __nv_bfloat16*>(ln_weight),
+                static_cast<const __nv_bfloat16*>(ln_bias), static_cast<const __nv_bfloat16*>(shift),
+                static_cast<const __nv_bfloat16*>(scale), mod_frame_stride, cols, tpf, eps, out_scale);
+        else
+            ln_modulate_kernel<false><<<static_cast<unsigned>(rows), kRowThreads, 0, st>>>(
+                static_cast<const __nv_bfloat16*>(x), out, static_cast<const __nv_bfloat16*>(ln_weight),
+                static_cast<const __nv_bfloat16*>(ln_bias), static_cast<const __nv_bfloat16*>(shift),
+                static_cast<const __nv_bfloat16*>(scale), mod_frame_stride, cols, tpf, eps, 1.0f);
     }
     IFX_LAUNCH_OK("ln_modulate_kernel");
+    return IFX_OK;
+}
+
+extern "C" ifx_status ifx_ln_modulate(const void* x, void* out, const void* ln_weight, const void* ln_bias,
+                                      const void* shift, const void* scale, int64_t mod_frame_stride, int64_t rows,
+                                      int32_t cols, int64_t tokens_per_frame, float eps, void* stream) {
+    return ln_modulate_entry(x, out, ln_weight, ln_bias, shift, scale, mod_frame_stride, rows, cols, tokens_per_frame,
+                             eps, false, 1.0f, stream);
+}
+
+extern "C" ifx_status ifx_ln_modulate_fp8(const void* x, void* out, const void* ln_weight, const void* ln_bias,
+                                          const void* shift, const void* scale, int64_t mod_frame_stride,
+                                          int64_t rows, int32_t cols, int64_t tokens_per_frame, float eps,
+                                          float out_scale, void* stream) {
+    return ln_modulate_entry(x, out, ln_weight, ln_bias, shift, scale, mod_frame_stride, rows, cols, tokens_per_frame,
+                             eps, true, out_scale, stream);
+}
+
+extern "C" ifx_status ifx_quantize_fp8(const void* x, int64_t ldx, void* out, int64_t ldo, int64_t rows, int32_t cols,
+                                       float scale, void* stream) {
+    IFX_CHECK_ARG(x && out, "ifx_quantize_fp8: null pointer");
+    IFX_CHECK_ARG(rows > 0 && cols > 0 && cols % 8 == 0, "ifx_quantize_fp8: cols must be a multiple of 8");
+    IFX_CHECK_ARG(ldx >= cols && ldx % 8 == 0 && ldo >= cols && ldo % 8 == 0, "ifx_quantize_fp8: bad strides");
+    IFX_CHECK_ARG(scale > 0.f, "ifx_quantize_fp8: scale must be positive");
+    const int64_t total = rows * (cols >> 3);
+    int64_t blocks = (total + 255) / 256;
+    const int64_t cap = static_cast<int64_t>(sm_count()) * 16;
+    if (blocks > cap) blocks = cap;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    {
+        ProfScope prof("quantize_fp8_kernel", st);
+        quantize_fp8_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(
+            static_cast<const __nv_bfloat16*>(x), ldx, static_cast<uint8_t*>(out), ldo, rows, cols, scale);
+    }
+    IFX_LAUNCH_OK("quantize_fp8_kernel");
     return IFX_OK;
 }
 

@@ -31,6 +31,7 @@ struct GemmCfg {
 struct GemmParams {
     int64_t M;
     int32_t N, K;
+    float alpha;  // FP8 path: input_scale * weight_scale applied to the fp32 accumulator before the bias
     const __nv_bfloat16* bias;
     __nv_bfloat16* out;
     int64_t ldo;
@@ -52,7 +53,7 @@ __device__ __forceinline__ float gelu_tanh_f(float x) {
     return 0.5f * x * (1.0f + t);
 }
 
-template <int kEpi, int kBN>
+template <int kEpi, int kBN, bool kFp8>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const GemmParams p) {
@@ -74,7 +75,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int num_tiles = p.num_m_tiles * p.num_n_tiles;
-    const int num_kb = (p.K + kBK - 1) / kBK;
+    constexpr int kElemsPerKb = kFp8 ? 2 * kBK : kBK;  // one k-block is 128 bytes of K per row either way
+    const int num_kb = (p.K + kElemsPerKb - 1) / kElemsPerKb;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -107,8 +109,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
                     mbar_expect_tx(&full[stage], kStageBytes);
-                    tma_load_2d(sA + stage * kABytes, &tmA, &full[stage], kb * kBK, m_blk * kBM);
-                    tma_load_2d(sB + stage * kBBytes, &tmB, &full[stage], kb * kBK, n_blk * kBN);
+                    tma_load_2d(sA + stage * kABytes, &tmA, &full[stage], kb * kElemsPerKb, m_blk * kBM);
+                    tma_load_2d(sB + stage * kBBytes, &tmB, &full[stage], kb * kElemsPerKb, n_blk * kBN);
                     if (++stage == kStages) {
                         stage = 0;
                         phase ^= 1;
@@ -118,7 +120,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(kBM, kBN, 0, 0);
+            constexpr uint32_t idesc = kFp8 ? make_idesc_e4m3(kBM, kBN) : make_idesc_bf16(kBM, kBN, 0, 0);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
@@ -136,7 +138,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
                     for (int k = 0; k < kBK / 16; ++k) {
                         // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the (addr >> 4) field
-                        umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                        if (kFp8)
+                            umma_ss_f8(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                        else
+                            umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
                     }
                     umma_commit(&empty[stage]);
                     if (++stage == kStages) {
@@ -190,7 +195,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         }
                         float val[8];
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) val[e] = bf16_round(__uint_as_float(acc[v * 8 + e]) + bv[e]);
+                        for (int e = 0; e < 8; ++e) {
+                            const float a = __uint_as_float(acc[v * 8 + e]);
+                            val[e] = bf16_round((kFp8 ? a * p.alpha : a) + bv[e]);
+                        }
                         if (kEpi == IFX_EPI_BIAS_GELU) {
 #pragma unroll
                             for (int e = 0; e < 8; ++e) val[e] = gelu_tanh_f(val[e]);
@@ -237,13 +245,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
 }
 
-template <int kEpi, int kBN>
+template <int kEpi, int kBN, bool kFp8>
 static ifx_status launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p,
                               cudaStream_t stream) {
     constexpr int kGemmSmem = GemmCfg<kBN>::kSmem;
     static bool configured = false;
     if (!configured) {
-        IFX_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tn_kernel<kEpi, kBN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        IFX_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tn_kernel<kEpi, kBN, kFp8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          kGemmSmem));
         configured = true;
     }
@@ -251,10 +259,10 @@ static ifx_status launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, co
     const int grid = tiles < sm_count() ? tiles : sm_count();
     {
         char label[96];
-        snprintf(label, sizeof(label), "gemm_bf16_tn_kernel<%d,%d>[M=%lld,N=%d,K=%d]", kEpi, kBN, (long long)p.M, p.N,
-                 p.K);
+        snprintf(label, sizeof(label), "gemm_%s_tn_kernel<%d,%d>[M=%lld,N=%d,K=%d]", kFp8 ? "fp8" : "bf16", kEpi, kBN,
+                 (long long)p.M, p.N, p.K);
         ProfScope prof(label, stream);
-        gemm_bf16_tn_kernel<kEpi, kBN><<<grid, kGemmThreads, kGemmSmem, stream>>>(tmA, tmB, p);
+        gemm_bf16_tn_kernel<kEpi, kBN, kFp8><<<grid, kGemmThreads, kGemmSmem, stream>>>(tmA, tmB, p);
     }
     IFX_LAUNCH_OK("gemm_bf16_tn_kernel");
     return IFX_OK;
@@ -264,14 +272,16 @@ static ifx_status launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, co
 
 using namespace ifx;
 
-extern "C" ifx_status ifx_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias,
-                                    void* out, int64_t ldo, int64_t M, int32_t N, int32_t K, int32_t epilogue,
-                                    const void* residual, int64_t ldr, const void* gate, int64_t gate_frame_stride,
-                                    int64_t tokens_per_frame, void* stream) {
+template <bool kFp8>
+static ifx_status gemm_entry(const void* A, int64_t lda, const void* W, int64_t ldw, float alpha, const void* bias,
+                             void* out, int64_t ldo, int64_t M, int32_t N, int32_t K, int32_t epilogue,
+                             const void* residual, int64_t ldr, const void* gate, int64_t gate_frame_stride,
+                             int64_t tokens_per_frame, void* stream) {
+    constexpr int kAlign = kFp8 ? 16 : 8;  // operand rows must be 16-byte multiples
     IFX_CHECK_ARG(A && W && out, "ifx_gemm_bf16: null pointer");
     IFX_CHECK_ARG(M > 0 && N > 0 && K > 0, "ifx_gemm_bf16: empty problem M=%lld N=%d K=%d", (long long)M, N, K);
-    IFX_CHECK_ARG(N % 8 == 0 && K % 8 == 0, "ifx_gemm_bf16: N and K must be multiples of 8 (N=%d K=%d)", N, K);
-    IFX_CHECK_ARG(lda % 8 == 0 && ldw % 8 == 0 && ldo % 8 == 0, "ifx_gemm_bf16: strides must be multiples of 8");
+    IFX_CHECK_ARG(N % 8 == 0 && K % kAlign == 0, "ifx_gemm: N %% 8 and K %% %d must be 0 (N=%d K=%d)", kAlign, N, K);
+    IFX_CHECK_ARG(lda % kAlign == 0 && ldw % kAlign == 0 && ldo % 8 == 0, "ifx_gemm: strides must be 16-byte multiples");
     IFX_CHECK_ARG(lda >= K && ldw >= K && ldo >= N, "ifx_gemm_bf16: stride smaller than row");
     IFX_CHECK_ARG(epilogue >= IFX_EPI_BIAS && epilogue <= IFX_EPI_BIAS_GATE_RES, "ifx_gemm_bf16: bad epilogue %d",
                   epilogue);
@@ -295,15 +305,18 @@ extern "C" ifx_status ifx_gemm_bf16(const void* A, int64_t lda, const void* W, i
     const int bn = (0.85 * wave_eff(128) > wave_eff(256)) ? 128 : 256;
 
     CUtensorMap tmA, tmB;
-    ifx_status st = make_tmap_bf16_2d(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, kBK, kBM);
+    ifx_status st = kFp8 ? make_tmap_u8_2d(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, 2 * kBK, kBM)
+                         : make_tmap_bf16_2d(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, kBK, kBM);
     if (st != IFX_OK) return st;
-    st = make_tmap_bf16_2d(&tmB, W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw, kBK, bn);
+    st = kFp8 ? make_tmap_u8_2d(&tmB, W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw, 2 * kBK, bn)
+              : make_tmap_bf16_2d(&tmB, W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw, kBK, bn);
     if (st != IFX_OK) return st;
 
     GemmParams p;
     p.M = M;
     p.N = N;
     p.K = K;
+    p.alpha = alpha;
     p.bias = static_cast<const __nv_bfloat16*>(bias);
     p.out = static_cast<__nv_bfloat16*>(out);
     p.ldo = ldo;
@@ -317,14 +330,31 @@ extern "C" ifx_status ifx_gemm_bf16(const void* A, int64_t lda, const void* W, i
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (bn == 256) {
         switch (epilogue) {
-            case IFX_EPI_BIAS: return launch_gemm<IFX_EPI_BIAS, 256>(tmA, tmB, p, s);
-            case IFX_EPI_BIAS_GELU: return launch_gemm<IFX_EPI_BIAS_GELU, 256>(tmA, tmB, p, s);
-            default: return launch_gemm<IFX_EPI_BIAS_GATE_RES, 256>(tmA, tmB, p, s);
+            case IFX_EPI_BIAS: return launch_gemm<IFX_EPI_BIAS, 256, kFp8>(tmA, tmB, p, s);
+            case IFX_EPI_BIAS_GELU: return launch_gemm<IFX_EPI_BIAS_GELU, 256, kFp8>(tmA, tmB, p, s);
+            default: return launch_gemm<IFX_EPI_BIAS_GATE_RES, 256, kFp8>(tmA, tmB, p, s);
         }
     }
     switch (epilogue) {
-        case IFX_EPI_BIAS: return launch_gemm<IFX_EPI_BIAS, 128>(tmA, tmB, p, s);
-        case IFX_EPI_BIAS_GELU: return launch_gemm<IFX_EPI_BIAS_GELU, 128>(tmA, tmB, p, s);
-        default: return launch_gemm<IFX_EPI_BIAS_GATE_RES, 128>(tmA, tmB, p, s);
+        case IFX_EPI_BIAS: return launch_gemm<IFX_EPI_BIAS, 128, kFp8>(tmA, tmB, p, s);
+        case IFX_EPI_BIAS_GELU: return launch_gemm<IFX_EPI_BIAS_GELU, 128, kFp8>(tmA, tmB, p, s);
+        default: return launch_gemm<IFX_EPI_BIAS_GATE_RES, 128, kFp8>(tmA, tmB, p, s);
     }
+}
+
+extern "C" ifx_status ifx_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias,
+                                    void* out, int64_t ldo, int64_t M, int32_t N, int32_t K, int32_t epilogue,
+                                    const void* residual, int64_t ldr, const void* gate, int64_t gate_frame_stride,
+                                    int64_t tokens_per_frame, void* stream) {
+    return gemm_entry<false>(A, lda, W, ldw, 1.0f, bias, out, ldo, M, N, K, epilogue, residual, ldr, gate,
+                             gate_frame_stride, tokens_per_frame, stream);
+}
+
+extern "C" ifx_status ifx_gemm_fp8(const void* A, int64_t lda, const void* W, int64_t ldw, float alpha,
+                                   const void* bias, void* out, int64_t ldo, int64_t M, int32_t N, int32_t K,
+                                   int32_t epilogue, const void* residual, int64_t ldr, const void* gate,
+                                   int64_t gate_frame_stride, int64_t tokens_per_frame, void* stream) {
+    IFX_CHECK_ARG(alpha > 0.f, "ifx_gemm_fp8: alpha (input_scale * weight_scale) must be positive");
+    return gemm_entry<true>(A, lda, W, ldw, alpha, bias, out, ldo, M, N, K, epilogue, residual, ldr, gate,
+                            gate_frame_stride, tokens_per_frame, stream);
 }

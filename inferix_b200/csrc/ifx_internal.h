@@ -50,6 +50,10 @@ struct ProfScope {
 ifx_status make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t inner_elems, uint64_t outer_rows,
                              uint64_t row_stride_elems, uint32_t box_inner, uint32_t box_rows);
 
+// same for 1-byte elements (FP8 operands): box = [box_rows, 128 bytes]
+ifx_status make_tmap_u8_2d(CUtensorMap* out, const void* base, uint64_t inner_elems, uint64_t outer_rows,
+                           uint64_t row_stride_elems, uint32_t box_inner, uint32_t box_rows);
+
 int sm_count();
 
 struct KvImpl {

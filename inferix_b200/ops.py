@@ -14,7 +14,7 @@ from . import _lib
 from ._lib import EPI_BIAS, EPI_BIAS_GATE_RES, EPI_BIAS_GELU, KvPlan, RopeGrid
 
 __all__ = [
-    "ln_modulate", "gemm", "rmsnorm", "attention", "qk_norm_rope_append", "PagedKV", "rope_table",
+    "ln_modulate", "gemm", "rmsnorm", "quantize_fp8", "ln_modulate_fp8", "gemm_fp8", "attention", "qk_norm_rope_append", "PagedKV", "rope_table",
     "EPI_BIAS", "EPI_BIAS_GELU", "EPI_BIAS_GATE_RES",
 ]
 
@@ -96,6 +96,68 @@ def gemm(a, w, bias=None, out=None, *, epilogue=EPI_BIAS, residual=None, gate=No
         a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), _ptr(_bf16_vec(bias, N, "bias")), out.data_ptr(),
         out.stride(0), M, N, K, epilogue, _ptr(residual), residual.stride(0) if residual is not None else 0,
         _ptr(gate), gstride, tokens_per_frame, _stream()))
+    return out
+
+
+def _fp8_2d(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda or t.dtype != torch.float8_e4m3fn or t.dim() != 2 or t.stride(1) != 1:
+        raise ValueError(f"{name}: expected a 2-D CUDA float8_e4m3fn tensor with unit inner stride")
+    return t
+
+
+def quantize_fp8(x, scale: float, out=None):
+    """e4m3(bf16(clamp(x / scale, +-448))) — MAGI div_clamp_to (dit_module.py:367-387) with a per-tensor scale."""
+    x = _bf16_2d(x, "x")
+    rows, cols = x.shape
+    out = torch.empty((rows, cols), dtype=torch.float8_e4m3fn, device=x.device) if out is None else _fp8_2d(out, "out")
+    _lib.check(_lib.load().ifx_quantize_fp8(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), rows, cols,
+                                            float(scale), _stream()))
+    return out
+
+
+def ln_modulate_fp8(x, out_scale: float, out=None, *, weight=None, bias=None, shift=None, scale=None,
+                    tokens_per_frame=0, eps=1e-6):
+    """ln_modulate whose bf16 result is quantised to e4m3 on the way out (same rounding as quantize_fp8 after it)."""
+    x = _bf16_2d(x, "x")
+    if not x.is_contiguous():
+        raise ValueError("x must be contiguous")
+    rows, cols = x.shape
+    out = torch.empty((rows, cols), dtype=torch.float8_e4m3fn, device=x.device) if out is None else _fp8_2d(out, "out")
+    if not out.is_contiguous():
+        raise ValueError("out must be contiguous")
+    stride = 0
+    if scale is not None:
+        if shift is None or scale.shape != shift.shape or scale.stride(0) != shift.stride(0):
+            raise ValueError("shift/scale must both be [frames, C] with a common frame stride")
+        stride = scale.stride(0)
+    _lib.check(_lib.load().ifx_ln_modulate_fp8(
+        x.data_ptr(), out.data_ptr(), _ptr(_bf16_vec(weight, cols, "weight")), _ptr(_bf16_vec(bias, cols, "bias")),
+        _ptr(shift), _ptr(scale), stride, rows, cols, tokens_per_frame, eps, float(out_scale), _stream()))
+    return out
+
+
+def gemm_fp8(a_q, w_q, alpha: float, bias=None, out=None, *, epilogue=EPI_BIAS, residual=None, gate=None,
+             tokens_per_frame=0):
+    """out = epilogue((a_q @ w_q.T) * alpha + bias); a_q [M,K], w_q [N,K] e4m3; alpha = input_scale * weight_scale."""
+    a_q, w_q = _fp8_2d(a_q, "a_q"), _fp8_2d(w_q, "w_q")
+    M, K = a_q.shape
+    N = w_q.shape[0]
+    if w_q.shape[1] != K:
+        raise ValueError(f"gemm_fp8: a is [{M},{K}] but w is {tuple(w_q.shape)}")
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.bfloat16, device=a_q.device)
+    out = _bf16_2d(out, "out")
+    gstride = 0
+    if gate is not None:
+        if gate.dim() != 2 or gate.shape[1] != N or gate.stride(1) != 1:
+            raise ValueError("gate must be [frames, N] with unit inner stride")
+        gstride = gate.stride(0)
+    if residual is not None:
+        residual = _bf16_2d(residual, "residual")
+    _lib.check(_lib.load().ifx_gemm_fp8(
+        a_q.data_ptr(), a_q.stride(0), w_q.data_ptr(), w_q.stride(0), float(alpha), _ptr(_bf16_vec(bias, N, "bias")),
+        out.data_ptr(), out.stride(0), M, N, K, epilogue, _ptr(residual),
+        residual.stride(0) if residual is not None else 0, _ptr(gate), gstride, tokens_per_frame, _stream()))
     return out
 
 

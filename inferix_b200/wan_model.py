@@ -137,6 +137,8 @@ class CausalWanAttentionBlock(nn.Module):
         self.ffn = nn.Sequential(nn.Linear(dim, ffn_dim), nn.GELU(approximate="tanh"), nn.Linear(ffn_dim, dim))
         self.modulation = nn.Parameter(torch.randn(1, 6, dim) / dim ** 0.5)
         self._packed = None
+        self._fp8 = None      # site -> quantised weight / scales once quantize_fp8() ran
+        self._amax = None     # dict while calibrating
 
     # ------------------------------------------------------------------ weight packing for the C ABI
     def _pack(self):
@@ -170,6 +172,7 @@ class CausalWanAttentionBlock(nn.Module):
 
     def invalidate_packed(self):
         self._packed = None
+        self._fp8 = None
 
     # ------------------------------------------------------------------ forward
     def forward(self, x, e, seq_lens, grid_sizes, freqs, context, context_lens, block_mask, kv_cache_meta=None,
@@ -206,7 +209,7 @@ class CausalWanAttentionBlock(nn.Module):
             xb = x[bi]
             if not xb.is_contiguous():
                 raise ValueError("x must be contiguous per sample")
-            if world == 1:
+            if world == 1 and getattr(self, "_fp8", None) is None and self._amax is None:
                 io = WanBlockIO()
                 io.x, io.rows, io.tokens_per_frame = xb.data_ptr(), rows, fs
                 io.mod, io.freqs, io.grid = mod[bi].data_ptr(), freqs.data_ptr(), grid
@@ -217,8 +220,8 @@ class CausalWanAttentionBlock(nn.Module):
                 plan = KvPlan()
                 _lib.check(lib.ifx_wan_block_forward(C.byref(w), C.byref(io), C.byref(plan), stream))
             else:
-                plan = self._forward_sharded(xb, mod[bi], fs, frames, grid, freqs, store, cstore, current_start,
-                                             sink_tokens, windowed, ws, qkv_w, qkv_b, pc)
+                plan = self._forward_ops(xb, mod[bi], fs, frames, grid, freqs, store, cstore, current_start,
+                                         sink_tokens, windowed, ws, qkv_w, qkv_b, pc, amax=self._amax)
             # mirror of causal_model.py:328-329 (host ints -> device scalars, no sync)
             kv_cache_meta["global_end_index"].fill_(plan.global_end)
             kv_cache_meta["local_end_index"].fill_(plan.local_end)
@@ -227,33 +230,92 @@ class CausalWanAttentionBlock(nn.Module):
             crossattn_cache_meta["is_init"] = True
         return x
 
-    def _forward_sharded(self, x, mod, fs, frames, grid, freqs, store, cstore, current_start, sink_tokens, windowed,
-                         ws, qkv_w, qkv_b, pc: ParallelConfig):
-        """Same 13 kernels, op by op, with the all-gather of this rank's new K/V between the QKV epilogue and the
-        attention.  x [S/P, C] holds this rank's hw slice of every frame."""
+    # ------------------------------------------------------------------ FP8 (e4m3, per-tensor static scales)
+    FP8_SITES = ("qkv", "o", "cq", "co", "ffn1", "ffn2")
+
+    def quantize_fp8(self, input_scales: dict):
+        """Quantise the six block GEMMs' weights to e4m3 with one scale per launched weight matrix (q|k|v fused = one
+        tensor) and fix the activation scales.  input_scales: site -> float (amax / 448 of that GEMM's input)."""
+        _w, _keep, qkv_w, qkv_b = self._packed or self._pack()
+        sa, ca = self.self_attn, self.cross_attn
+        mats = {"qkv": (qkv_w, qkv_b), "o": (sa.o.weight, sa.o.bias), "cq": (ca.q.weight, ca.q.bias),
+                "co": (ca.o.weight, ca.o.bias), "ffn1": (self.ffn[0].weight, self.ffn[0].bias),
+                "ffn2": (self.ffn[2].weight, self.ffn[2].bias)}
+        q = {}
+        for site, (wt, bias) in mats.items():
+            ws_ = float(wt.detach().abs().max().float()) / 448.0
+            wq = torch.clamp(wt.detach().float() / ws_, -448.0, 448.0).bfloat16().to(torch.float8_e4m3fn).contiguous()
+            q[site] = dict(w=wq, w_scale=ws_, in_scale=float(input_scales[site]), bias=bias.detach())
+        self._fp8 = q
+
+    def fp8_state(self):
+        """Reference-named view of the quantised weights for the oracle: name -> (weight_q, weight_scale, input_scale)."""
+        c = self.dim
+        q = self._fp8
+        p = f"blocks.{self.layer_idx}"
+        out = {}
+        for j, name in enumerate(("q", "k", "v")):
+            out[f"{p}.self_attn.{name}"] = (q["qkv"]["w"][j * c:(j + 1) * c], q["qkv"]["w_scale"], q["qkv"]["in_scale"])
+        for site, name in (("o", "self_attn.o"), ("cq", "cross_attn.q"), ("co", "cross_attn.o"), ("ffn1", "ffn.0"),
+                           ("ffn2", "ffn.2")):
+            out[f"{p}.{name}"] = (q[site]["w"], q[site]["w_scale"], q[site]["in_scale"])
+        return out
+
+    def _forward_ops(self, x, mod, fs, frames, grid, freqs, store, cstore, current_start, sink_tokens, windowed,
+                     ws, qkv_w, qkv_b, pc: Optional[ParallelConfig], amax: Optional[dict] = None):
+        """The 13 kernels of the block, op by op.  Used (a) under sequence parallelism: one all-gather of this rank's
+        new K/V between the QKV epilogue and the attention, x [S/P, C] holding this rank's hw slice of
+        every frame; (b) for FP8 linears (quantisation fused into the LN kernels, dequantisation into the GEMM
+        epilogues); (c) for calibration (`amax` collects the absolute maxima of the six GEMM inputs)."""
         rows, c = x.shape
         sa, ca = self.self_attn, self.cross_attn
         heads, hd = self.num_heads, self.dim // self.num_heads
         m = mod.view(frames, 6, c)
-        plan = store.plan_append(current_start, rows * pc.world_size, sink_tokens, windowed)
-        ops.ln_modulate(x, ws.h, shift=m[:, 0], scale=m[:, 1], tokens_per_frame=fs, eps=self.eps)
-        ops.gemm(ws.h, qkv_w, qkv_b, ws.qkv)
-        ops.qk_norm_rope_append(ws.qkv, sa.norm_q.weight, sa.norm_k.weight, freqs, grid, heads, hd, q_out=ws.q,
-                                k_out=ws.kv_new[0], v_out=ws.kv_new[1], eps=self.eps)
-        kvg = all_gather_rows(ws.kv_new, pc, ws.kv_all)           # ONE all-gather: [P, 2, rows, C]
-        store.append_sp(plan, kvg[:, 0], kvg[:, 1], frames)
+        world = pc.world_size if pc is not None else 1
+        f8 = getattr(self, "_fp8", None) if amax is None else None
+
+        def note(site, t):
+            if amax is not None:
+                amax[site] = max(amax.get(site, 0.0), float(t.abs().max().float()))
+
+        def linear(site, a_bf16, a_fp8, w, b, out, **kw):
+            if f8 is None:
+                note(site, a_bf16)
+                return ops.gemm(a_bf16, w, b, out, **kw)
+            q = f8[site]
+            if a_fp8 is None:                    # producer had no fused quantisation: one extra elementwise pass
+                a_fp8 = ops.quantize_fp8(a_bf16, q["in_scale"], ws.q8(site, a_bf16.shape))
+            return ops.gemm_fp8(a_fp8, q["w"], q["in_scale"] * q["w_scale"], q["bias"], out, **kw)
+
+        def ln(site, **kw):
+            if f8 is None:
+                ops.ln_modulate(x, ws.h, eps=self.eps, **kw)
+                return ws.h, None
+            return None, ops.ln_modulate_fp8(x, f8[site]["in_scale"], ws.q8(site, x.shape), eps=self.eps, **kw)
+
+        plan = store.plan_append(current_start, rows * world, sink_tokens, windowed)
+        h, h8 = ln("qkv", shift=m[:, 0], scale=m[:, 1], tokens_per_frame=fs)
+        linear("qkv", h, h8, qkv_w, qkv_b, ws.qkv)
+        if world > 1:
+            ops.qk_norm_rope_append(ws.qkv, sa.norm_q.weight, sa.norm_k.weight, freqs, grid, heads, hd, q_out=ws.q,
+                                    k_out=ws.kv_new[0], v_out=ws.kv_new[1], eps=self.eps)
+            kvg = all_gather_rows(ws.kv_new, pc, ws.kv_all)       # ONE all-gather: [P, 2, rows, C]
+            store.append_sp(plan, kvg[:, 0], kvg[:, 1], frames)
+        else:
+            ops.qk_norm_rope_append(ws.qkv, sa.norm_q.weight, sa.norm_k.weight, freqs, grid, heads, hd, kv=store,
+                                    plan=plan, q_out=ws.q, eps=self.eps)
         store.attention(ws.q, ws.attn)
-        ops.gemm(ws.attn, sa.o.weight, sa.o.bias, x, epilogue=ops.EPI_BIAS_GATE_RES, residual=x, gate=m[:, 2],
-                 tokens_per_frame=fs)
-        ops.ln_modulate(x, ws.h, weight=self.norm3.weight, bias=self.norm3.bias, eps=self.eps)
-        ops.gemm(ws.h, ca.q.weight, ca.q.bias, ws.qkv[:, :c])
+        linear("o", ws.attn, None, sa.o.weight, sa.o.bias, x, epilogue=ops.EPI_BIAS_GATE_RES, residual=x,
+               gate=m[:, 2], tokens_per_frame=fs)
+        h, h8 = ln("cq", weight=self.norm3.weight, bias=self.norm3.bias)
+        linear("cq", h, h8, ca.q.weight, ca.q.bias, ws.qkv[:, :c])
         ops.rmsnorm(ws.qkv[:, :c], ca.norm_q.weight, ws.q, eps=self.eps)
         ops.attention(ws.q, cstore.k, cstore.v, heads, ws.attn)
-        ops.gemm(ws.attn, ca.o.weight, ca.o.bias, x, epilogue=ops.EPI_BIAS_GATE_RES, residual=x)
-        ops.ln_modulate(x, ws.h, shift=m[:, 3], scale=m[:, 4], tokens_per_frame=fs, eps=self.eps)
-        ops.gemm(ws.h, self.ffn[0].weight, self.ffn[0].bias, ws.ffn, epilogue=ops.EPI_BIAS_GELU)
-        ops.gemm(ws.ffn, self.ffn[2].weight, self.ffn[2].bias, x, epilogue=ops.EPI_BIAS_GATE_RES, residual=x,
-                 gate=m[:, 5], tokens_per_frame=fs)
+        linear("co", ws.attn, None, ca.o.weight, ca.o.bias, x, epilogue=ops.EPI_BIAS_GATE_RES, residual=x)
+        h, h8 = ln("ffn1", shift=m[:, 3], scale=m[:, 4], tokens_per_frame=fs)
+        linear("ffn1", h, h8, self.ffn[0].weight, self.ffn[0].bias, ws.ffn, epilogue=ops.EPI_BIAS_GELU)
+        linear("ffn2", ws.ffn, None, self.ffn[2].weight, self.ffn[2].bias, x, epilogue=ops.EPI_BIAS_GATE_RES,
+               residual=x, gate=m[:, 5], tokens_per_frame=fs)
         return plan
 
 
@@ -265,9 +327,18 @@ class _Workspace:
             return torch.empty(shape, dtype=torch.bfloat16, device=device)
         self.rows = rows
         self.h, self.qkv, self.q, self.attn, self.ffn = buf(rows, dim), buf(rows, 3 * dim), buf(rows, dim), buf(rows, dim), buf(rows, ffn_dim)
+        self._q8 = {}
         if world > 1:
             self.kv_new = buf(2, rows, dim)              # this rank's new roped-K | V, one send buffer
             self.kv_all = buf(world, 2, rows, dim)       # all-gather destination
+
+    def q8(self, site, shape):
+        """e4m3 staging buffer for a GEMM input (lazily allocated, keyed by shape)."""
+        key = tuple(shape)
+        t = self._q8.get(key)
+        if t is None:
+            t = self._q8[key] = torch.empty(key, dtype=torch.float8_e4m3fn, device=self.h.device)
+        return t
 
 
 class CausalHead(nn.Module):
@@ -340,6 +411,25 @@ class CausalWanModel(nn.Module):
         self._freqs_table = None
         self._workspace = None
         return out
+
+    # ------------------------------------------------------------------ FP8
+    def begin_fp8_calibration(self):
+        """Subsequent forwards run op by op in bf16 and record the absolute maximum of every block-GEMM input."""
+        for blk in self.blocks:
+            blk._fp8, blk._amax = None, {}
+
+    def finish_fp8_calibration(self, margin: float = 1.0):
+        """Static per-tensor activation scales = margin * amax / 448, weights quantised per launched matrix.
+        First and last layers could be kept in bf16 as MAGI does (dit_module.py:410); Wan quantises all blocks."""
+        for blk in self.blocks:
+            amax, blk._amax = blk._amax, None
+            if not amax:
+                raise RuntimeError("finish_fp8_calibration: no forward ran since begin_fp8_calibration")
+            blk.quantize_fp8({k: max(v, 1e-6) * margin / 448.0 for k, v in amax.items()})
+
+    def disable_fp8(self):
+        for blk in self.blocks:
+            blk._fp8 = blk._amax = None
 
     def _get_workspace(self, rows, device):
         ws = self._workspace

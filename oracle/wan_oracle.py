@@ -172,7 +172,26 @@ def plan_indices(cache_size: int, global_end: int, local_end: int, current_start
 
 
 # ----------------------------------------------------------------------------- the DiT block
+def div_clamp_to_e4m3(x: torch.Tensor, scale: float) -> torch.Tensor:
+    """models/magi/dit/dit_module.py:367-387 with a per-tensor scale: clamp in fp32 -> bf16 -> e4m3."""
+    return torch.clamp(x.float() / scale, -448.0, 448.0).bfloat16().to(torch.float8_e4m3fn)
+
+
+def fp8_linear(x: torch.Tensor, w_q: torch.Tensor, weight_scale: float, input_scale: float, bias=None) -> torch.Tensor:
+    """PerTensorQuantizedFp8Linear.forward, dit_module.py:434-459: bmm_fp8(x_q, W_q^T, input_scale, weight_scale)
+    = (x_q @ W_q^T) * input_scale * weight_scale with fp32 accumulation, cast to bf16.  The Wan linears carry a bias
+    (MAGI's do not): it is added in fp32 before the cast.  fp8 x fp8 products are exact in fp32."""
+    xq = div_clamp_to_e4m3(x, input_scale).float()
+    y = (xq @ w_q.float().t()) * (input_scale * weight_scale)
+    if bias is not None:
+        y = y + bias.float()
+    return y.to(torch.bfloat16)
+
+
 def _lin(sd: Dict[str, torch.Tensor], name: str, x: torch.Tensor) -> torch.Tensor:
+    q = sd.get("__fp8__", {}).get(name)
+    if q is not None:      # (weight_q, weight_scale, input_scale): this linear is FP8-quantised
+        return fp8_linear(x, q[0], q[1], q[2], sd.get(name + ".bias"))
     return F.linear(x, sd[name + ".weight"], sd.get(name + ".bias"))
 
 

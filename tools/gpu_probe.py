@@ -194,6 +194,25 @@ def check_perf_sp8():
     print(f"attn Lq={S} Lk={Lk}: {ms:.3f} ms {4.0 * S * Lk * C / ms / 1e9:.1f} TFLOP/s", flush=True)
 
 
+def check_perf_fp8():
+    torch.manual_seed(0)
+    S, C, F = 10800, 1536, 8960
+    for (N, K, name) in [(3 * C, C, "qkv"), (C, C, "o"), (F, C, "ffn1"), (C, F, "ffn2")]:
+        x = torch.randn(S, K, device=dev).bfloat16()
+        w = (torch.randn(N, K, device=dev) / math.sqrt(K)).bfloat16()
+        b = torch.randn(N, device=dev).bfloat16()
+        s_in, s_w = float(x.abs().max()) / 448, float(w.abs().max()) / 448
+        xq, wq = ops.quantize_fp8(x, s_in), ops.quantize_fp8(w, s_w)
+        out = torch.empty(S, N, device=dev, dtype=torch.bfloat16)
+        ms = timeit(lambda: ops.gemm_fp8(xq, wq, s_in * s_w, b, out=out))
+        msq = timeit(lambda: ops.quantize_fp8(x, s_in, xq))
+        ref = torch.nn.functional.linear(x, w, b)
+        fl = 2.0 * S * N * K
+        print(f"gemm_fp8 {name}: {ms:.3f} ms {fl / ms / 1e9:.1f} TFLOP/s; quantize {msq * 1e3:.1f} us "
+              f"({S * K * 3 / msq / 1e6:.0f} GB/s)", flush=True)
+        stats("vs bf16 linear", out, ref)
+
+
 def check_attn_once():
     """Self-attention at the BASELINE config-2 shape, a few launches (target of `ncu --set full -k regex:attn_fwd`)."""
     S, C, H, Lk = 10800, 1536, 12, 86400

@@ -195,6 +195,13 @@ ifx_status ifx_rmsnorm(const void* x, int64_t ldx, const void* weight, void* out
 ifx_status ifx_attention(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, void* out,
                          int64_t ldo, int64_t q_rows, int64_t kv_rows, int32_t heads, int32_t head_dim,
                          float softmax_scale, void* stream);
+/* Grouped-query variant: q has `heads` heads, k/v have `kv_heads` (heads % kv_heads == 0); query head h reads
+ * key/value head h / (heads / kv_heads).  MAGI-1's FullyParallelAttention (models/magi/dit/dit_module.py:833-1014:
+ * 24 or 48 query heads over 8 KV groups); the per-range loop of :1000-1014 is one call per (q_range, k_range) row
+ * with offset pointers. */
+ifx_status ifx_attention_gqa(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, void* out,
+                             int64_t ldo, int64_t q_rows, int64_t kv_rows, int32_t heads, int32_t kv_heads,
+                             int32_t head_dim, float softmax_scale, void* stream);
 /* Same, keys/values taken from the valid prefix of a paged cache (rows [0, local_end)). */
 ifx_status ifx_attention_kv(const void* q, int64_t ldq, const ifx_kv* kv, void* out, int64_t ldo, int64_t q_rows,
                             float softmax_scale, void* stream);

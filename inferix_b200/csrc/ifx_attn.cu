@@ -45,6 +45,7 @@ struct AttnParams {
     int32_t q_rows;
     int32_t kv_rows;
     int32_t heads;
+    int32_t kv_group;    // query heads per key/value head (grouped-query attention; 1 = MHA)
     int32_t num_q_pairs;
     int32_t n_whole;     // items [0, n_whole) cover all keys; the rest are split into `split` pieces
     int32_t split;
@@ -145,7 +146,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
                     for (int h = 0; h < 2; ++h)
                         tma_load_2d_hint(sKV + s * kTileBytes + h * kHalfBytes, tm, &kv_full[s],
-                                         head * kHD + h * 64, j * kKT, kEvictLast);
+                                         (head / p.kv_group) * kHD + h * 64, j * kKT, kEvictLast);
                 }
             }
         }
@@ -394,23 +395,26 @@ static size_t g_part_bytes = 0;
 
 static ifx_status attention_launch(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, void* out,
                                    int64_t ldo, int64_t q_rows, int64_t kv_rows, int32_t heads, int32_t head_dim,
-                                   float softmax_scale, cudaStream_t stream) {
+                                   float softmax_scale, cudaStream_t stream, int32_t kv_heads = 0) {
+    if (kv_heads <= 0) kv_heads = heads;
+    IFX_CHECK_ARG(heads % kv_heads == 0, "ifx_attention: heads (%d) must be a multiple of kv_heads (%d)", heads, kv_heads);
     IFX_CHECK_ARG(q && k && v && out, "ifx_attention: null pointer");
     IFX_CHECK_ARG(head_dim == kHD, "ifx_attention: head_dim must be 128 (got %d)", head_dim);
     IFX_CHECK_ARG(q_rows > 0 && kv_rows > 0 && heads > 0, "ifx_attention: empty problem (q_rows=%lld kv_rows=%lld)",
                   (long long)q_rows, (long long)kv_rows);
     IFX_CHECK_ARG(q_rows < (1ll << 31) && kv_rows < (1ll << 31), "ifx_attention: sequence too long");
     const int64_t width = static_cast<int64_t>(heads) * head_dim;
-    IFX_CHECK_ARG(ldq >= width && ldkv >= width && ldo >= width, "ifx_attention: stride smaller than heads*head_dim");
+    const int64_t kv_width = static_cast<int64_t>(kv_heads) * head_dim;
+    IFX_CHECK_ARG(ldq >= width && ldkv >= kv_width && ldo >= width, "ifx_attention: stride smaller than heads*head_dim");
     IFX_CHECK_ARG(ldq % 8 == 0 && ldkv % 8 == 0 && ldo % 8 == 0, "ifx_attention: strides must be multiples of 8");
     IFX_CHECK_ARG(softmax_scale > 0.f, "ifx_attention: softmax_scale must be positive");
 
     CUtensorMap tmQ, tmK, tmV;
     ifx_status st = make_tmap_bf16_2d(&tmQ, q, (uint64_t)width, (uint64_t)q_rows, (uint64_t)ldq, 64, kQT);
     if (st != IFX_OK) return st;
-    st = make_tmap_bf16_2d(&tmK, k, (uint64_t)width, (uint64_t)kv_rows, (uint64_t)ldkv, 64, kKT);
+    st = make_tmap_bf16_2d(&tmK, k, (uint64_t)kv_width, (uint64_t)kv_rows, (uint64_t)ldkv, 64, kKT);
     if (st != IFX_OK) return st;
-    st = make_tmap_bf16_2d(&tmV, v, (uint64_t)width, (uint64_t)kv_rows, (uint64_t)ldkv, 64, kKT);
+    st = make_tmap_bf16_2d(&tmV, v, (uint64_t)kv_width, (uint64_t)kv_rows, (uint64_t)ldkv, 64, kKT);
     if (st != IFX_OK) return st;
 
     static bool configured = false;
@@ -422,6 +426,7 @@ static ifx_status attention_launch(const void* q, int64_t ldq, const void* k, co
     p.q_rows = static_cast<int32_t>(q_rows);
     p.kv_rows = static_cast<int32_t>(kv_rows);
     p.heads = heads;
+    p.kv_group = heads / kv_heads;
     p.num_q_pairs = static_cast<int32_t>((q_rows + 2 * kQT - 1) / (2 * kQT));
     p.scale_log2 = softmax_scale * 1.4426950408889634f;
     p.out = static_cast<__nv_bfloat16*>(out);
@@ -484,6 +489,13 @@ extern "C" ifx_status ifx_attention(const void* q, int64_t ldq, const void* k, c
                                     float softmax_scale, void* stream) {
     return attention_launch(q, ldq, k, v, ldkv, out, ldo, q_rows, kv_rows, heads, head_dim, softmax_scale,
                             static_cast<cudaStream_t>(stream));
+}
+
+extern "C" ifx_status ifx_attention_gqa(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv,
+                                        void* out, int64_t ldo, int64_t q_rows, int64_t kv_rows, int32_t heads,
+                                        int32_t kv_heads, int32_t head_dim, float softmax_scale, void* stream) {
+    return attention_launch(q, ldq, k, v, ldkv, out, ldo, q_rows, kv_rows, heads, head_dim, softmax_scale,
+                            static_cast<cudaStream_t>(stream), kv_heads);
 }
 
 extern "C" ifx_status ifx_attention_kv(const void* q, int64_t ldq, const ifx_kv* kv_, void* out, int64_t ldo,

@@ -14,7 +14,7 @@ from . import _lib
 from ._lib import EPI_BIAS, EPI_BIAS_GATE_RES, EPI_BIAS_GELU, KvPlan, RopeGrid
 
 __all__ = [
-    "ln_modulate", "gemm", "rmsnorm", "quantize_fp8", "ln_modulate_fp8", "gemm_fp8", "attention", "qk_norm_rope_append", "PagedKV", "rope_table",
+    "ln_modulate", "gemm", "rmsnorm", "quantize_fp8", "ln_modulate_fp8", "gemm_fp8", "attention", "attention_gqa", "attention_ranges", "qk_norm_rope_append", "PagedKV", "rope_table",
     "EPI_BIAS", "EPI_BIAS_GELU", "EPI_BIAS_GATE_RES",
 ]
 
@@ -185,6 +185,30 @@ def attention(q, k, v, heads, out=None, *, softmax_scale=None):
     _lib.check(_lib.load().ifx_attention(q.data_ptr(), q.stride(0), k.data_ptr(), v.data_ptr(), k.stride(0),
                                          out.data_ptr(), out.stride(0), q.shape[0], k.shape[0], heads, head_dim,
                                          scale, _stream()))
+    return out
+
+
+def attention_gqa(q, k, v, heads, kv_heads, out=None, *, softmax_scale=None):
+    """Grouped-query attention: q [Lq, heads*D], k/v [Lk, kv_heads*D]."""
+    q, k, v = _bf16_2d(q, "q"), _bf16_2d(k, "k"), _bf16_2d(v, "v")
+    head_dim = q.shape[1] // heads
+    if k.shape != v.shape or k.shape[1] != kv_heads * head_dim or k.stride(0) != v.stride(0):
+        raise ValueError("attention_gqa: k / v must be [Lk, kv_heads*D] with identical strides")
+    if out is None:
+        out = torch.empty((q.shape[0], q.shape[1]), dtype=torch.bfloat16, device=q.device)
+    scale = softmax_scale if softmax_scale is not None else head_dim ** -0.5
+    _lib.check(_lib.load().ifx_attention_gqa(q.data_ptr(), q.stride(0), k.data_ptr(), v.data_ptr(), k.stride(0),
+                                             out.data_ptr(), out.stride(0), q.shape[0], k.shape[0], heads, kv_heads,
+                                             head_dim, scale, _stream()))
+    return out
+
+
+def attention_ranges(q, k, v, q_ranges, k_ranges, heads, kv_heads, *, softmax_scale=None):
+    """MAGI range attention (dit_module.py:1000-1014): output rows q_ranges[i] attend keys k_ranges[i].
+    q [Sq, heads*D], k/v [Sk, kv_heads*D]; ranges are host int pairs [start, end) in tokens (np_q_range / np_k_range)."""
+    out = torch.empty_like(q)
+    for (qs, qe), (ks, ke) in zip(q_ranges, k_ranges):
+        attention_gqa(q[qs:qe], k[ks:ke], v[ks:ke], heads, kv_heads, out[qs:qe], softmax_scale=softmax_scale)
     return out
 
 

@@ -234,3 +234,38 @@ def test_kv_manager_reference_api():
     mgr.free(req)
     with pytest.raises(KeyError):
         mgr.free(req)
+
+
+# ----------------------------------------------------------------------------------------------- MAGI pieces
+def test_gqa_range_attention():
+    """Grouped-query attention over per-chunk key ranges (MAGI dit_module.py:1000-1014) vs an fp32 reference."""
+    from inferix_b200 import magi_schedule as ms
+    heads, kv_heads, D, clip = 6, 2, 128, 96
+    kr = ms.noise2clean_kvrange(2, 3, clip, [3, 2], -1, [3, 1, 0], 4).tolist()      # 3 denoising chunks after 2 clean
+    qr = [[i * clip, (i + 1) * clip] for i in range(3)]
+    Sk = 5 * clip
+    q, k, v = bf(3 * clip, heads * D, seed=40), bf(Sk, kv_heads * D, seed=41), bf(Sk, kv_heads * D, seed=42)
+    out = ops.attention_ranges(q.to(DEV), k.to(DEV), v.to(DEV), qr, kr, heads, kv_heads)
+    for (qs, qe), (ks, ke) in zip(qr, kr):
+        qq = q[qs:qe].view(1, -1, heads, D).float()
+        kk = k[ks:ke].view(1, -1, kv_heads, D).float().repeat_interleave(heads // kv_heads, dim=2)
+        vv = v[ks:ke].view(1, -1, kv_heads, D).float().repeat_interleave(heads // kv_heads, dim=2)
+        ref = wo.sdpa_attention(qq, kk, vv)[0].reshape(qe - qs, heads * D)
+        assert rel_l2(out[qs:qe], ref) <= 4e-3
+
+
+def test_magi_kv_cache_manager_matches_reference(golden_dir):
+    """MagiKVCacheManager on the native cache vs the reference's adapter run on its CPU KVCacheManager."""
+    from inferix_b200.kvcache_manager.model import InferenceParams, KVMetaArgs, MagiKVCacheManager
+    gold = torch.load(golden_dir / "magi_kv.pt", weights_only=False)
+    mgr = MagiKVCacheManager(3, gold["hn"], gold["d"])
+    ip = InferenceParams(1, gold["clip"] * gold["chunks"], device=DEV)
+    for st in gold["steps"]:
+        ip.update_kv_cache = st["update"]
+        k, v = mgr.adjust_key_and_value_for_inference(st["kv"].to(DEV), ip, KVMetaArgs(**st["meta"]))
+        assert torch.equal(k.cpu(), st["k"]) and torch.equal(v.cpu(), st["v"])
+    mapped = ip.kv_cache_manager.get_raw(ip.kv_cache_request, "layer_3")
+    written = gold["chunks"] * gold["clip"]                  # the scenario stores all four clips
+    assert torch.equal(mapped[:, :written].cpu(), gold["final_cache"][:, :written])
+    mgr.clear_cache(ip)
+    assert not mgr.is_cached(ip)

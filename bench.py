@@ -42,6 +42,9 @@ WORKLOADS = {
     # reference-native resolution with its shipped 4-step schedule (for context; not the headline)
     "self_forcing_480p_4step": dict(latent_hw=(60, 104), frames_per_block=3, timesteps=4, window_blocks=7,
                                     model="WAN_1_3B"),
+    # BASELINE.json configs[2]: CausVid 540p (544x960 -> 68x120 latent), FP8 per-tensor linears, 3 steps, 7-block cache
+    "causvid_540p_fp8": dict(latent_hw=(68, 120), frames_per_block=3, timesteps=3, window_blocks=7, model="WAN_1_3B",
+                             fp8=True),
     # tiny shape for smoke runs
     "tiny": dict(latent_hw=(16, 16), frames_per_block=3, timesteps=4, window_blocks=2, model="TINY"),
 }
@@ -291,6 +294,11 @@ def main():
         return t.item()
 
     step = 0
+    if wl.get("fp8"):
+        # static per-tensor activation scales from one calibration block (bf16, op by op), then e4m3 weights
+        model.begin_fp8_calibration()
+        pipe.denoise_block(noise_dev[0], frame0, common)
+        model.finish_fp8_calibration()
     for _ in range(args.warmup):
         pipe.denoise_block(noise_dev[step], frame0 + step * n, common)
         step += 1
@@ -336,7 +344,14 @@ def main():
         L = window_frames * fs
         attn_ms, attn_n = _lib.prof_read(f"attn_fwd_kernel[Lq={S_local},Lk={L},")
         all_ms, all_n = _lib.prof_read("")
-        gemm_ms, gemm_n = _lib.prof_read("gemm_bf16_tn_kernel")
+        gemm_ms, gemm_n = _lib.prof_read("gemm_")
+        # HBM-bound KV kernels (second half of the BASELINE metric): algorithmic bytes / device time
+        app_ms, app_n = _lib.prof_read("qk_norm_rope_append_kernel")
+        kv_hbm = {}
+        if app_n:
+            app_bytes = 6.0 * S_local * C * 2          # read q|k|v rows, write q, roped-k and v (into the cache pages)
+            kv_hbm["append_norm_rope"] = {"gbs": app_bytes / (app_ms / app_n * 1e-3) / 1e9, "bytes_per_launch": app_bytes,
+                                          "avg_launch_us": 1e3 * app_ms / app_n, "launches_timed": app_n}
         peak_tf, peak_bw, src = measured_peaks()
         roofline = None
         if attn_n:
@@ -354,6 +369,21 @@ def main():
                         "share_of_step": {"attention_self": attn_ms / ms_total, "gemm": gemm_ms / ms_total,
                                           "all_kernels": all_ms / ms_total}}
         _lib.prof_reset()
+        # gather of one layer's whole window through the block table (what get()/get_range() cost), timed alone
+        store0 = model.blocks[0].kv_cache_manager.store(mgr, reqs[0])
+        for _ in range(3):
+            store0.export(0, L)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(10):
+            store0.export(0, L)
+        ev1.record()
+        torch.cuda.synchronize()
+        exp_bytes = 2.0 * 2 * L * C * 2                # K and V, read + write
+        kv_hbm["export_gather"] = {"gbs": exp_bytes / (ev0.elapsed_time(ev1) / 10 * 1e-3) / 1e9,
+                                   "bytes_per_launch": exp_bytes}
+        kv_hbm["evict"] = {"bytes_moved": 0, "note": "block-table rotation; the reference copies up to 4*(L-S)*C*2 B"}
+        kv_hbm["peak_gbs"] = peak_bw
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
@@ -363,6 +393,7 @@ def main():
                     "d2h_bytes_per_step": out_host.numel() * 2},
             "gpu_launches": int(launches),
             "roofline": roofline,
+            "kv_hbm": kv_hbm,
         }
         if world == 1 and not args.no_cpu_baseline:
             try:

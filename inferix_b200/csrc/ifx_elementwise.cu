@@ -7,7 +7,17 @@
 namespace ifx {
 
 constexpr int kRowThreads = 256;
-constexpr int kMaxVecPerThread = 4;  // cols <= 256 * 4 * 8 = 8192
+constexpr int kMaxVecPerThread = 8;  // cols <= 256 * 8 * 8; one warp per row up to 2048 columns
+
+// threads per row CTA: one 16-byte vector per thread when the row fits, rounded up to whole warps
+// Rows up to 2048 columns get ONE WARP (each lane keeps up to 8 x 16 B loads in flight and the row statistics need
+// only shuffles); wider rows fall back to a multi-warp CTA with a shared-memory reduction.
+static inline int row_threads(int cols) {
+    const int nvec = cols >> 3;
+    if (nvec <= 32 * kMaxVecPerThread) return 32;
+    int t = ((nvec + kMaxVecPerThread - 1) / kMaxVecPerThread + 31) / 32 * 32;
+    return t > kRowThreads ? kRowThreads : t;
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -21,6 +31,10 @@ __device__ __forceinline__ void block_sum(float (&v)[kN], float* scratch /* [kN]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
 #pragma unroll
     for (int i = 0; i < kN; ++i) v[i] = warp_sum(v[i]);
+    if (nwarps == 1) {       // one warp per row: done (uniform branch)
+        __syncwarp();
+        return;
+    }
     if (lane == 0)
 #pragma unroll
         for (int i = 0; i < kN; ++i) scratch[i * 32 + warp] = v[i];
@@ -77,7 +91,7 @@ ln_modulate_kernel(const __nv_bfloat16* __restrict__ x, void* __restrict__ out_,
     float acc[2] = {0.f, 0.f};
 #pragma unroll
     for (int i = 0; i < kMaxVecPerThread; ++i) {
-        const int vi = threadIdx.x + i * kRowThreads;
+        const int vi = threadIdx.x + i * blockDim.x;
         if (vi < nvec) {
             unpack8(xr[vi], v[i]);
 #pragma unroll
@@ -90,7 +104,7 @@ ln_modulate_kernel(const __nv_bfloat16* __restrict__ x, void* __restrict__ out_,
     // two-pass variance (matches at::native RowwiseMoments to fp32 rounding)
 #pragma unroll
     for (int i = 0; i < kMaxVecPerThread; ++i) {
-        const int vi = threadIdx.x + i * kRowThreads;
+        const int vi = threadIdx.x + i * blockDim.x;
         if (vi < nvec)
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
@@ -109,7 +123,7 @@ ln_modulate_kernel(const __nv_bfloat16* __restrict__ x, void* __restrict__ out_,
     uint2* orow8 = reinterpret_cast<uint2*>(static_cast<uint8_t*>(out_) + row * cols);
 #pragma unroll
     for (int i = 0; i < kMaxVecPerThread; ++i) {
-        const int vi = threadIdx.x + i * kRowThreads;
+        const int vi = threadIdx.x + i * blockDim.x;
         if (vi < nvec) {
             float y[8];
             if (ln_w) {
@@ -171,7 +185,7 @@ rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const __nv_bflo
     float ss[1] = {0.f};
 #pragma unroll
     for (int i = 0; i < kMaxVecPerThread; ++i) {
-        const int vi = threadIdx.x + i * kRowThreads;
+        const int vi = threadIdx.x + i * blockDim.x;
         if (vi < nvec) {
             unpack8(xr[vi], v[i]);
 #pragma unroll
@@ -183,7 +197,7 @@ rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const __nv_bflo
     uint4* orow = reinterpret_cast<uint4*>(out + row * ldo);
 #pragma unroll
     for (int i = 0; i < kMaxVecPerThread; ++i) {
-        const int vi = threadIdx.x + i * kRowThreads;
+        const int vi = threadIdx.x + i * blockDim.x;
         if (vi < nvec) {
             float wv[8], y[8];
             unpack8(__ldg(reinterpret_cast<const uint4*>(w) + vi), wv);
@@ -245,11 +259,19 @@ qk_norm_rope_append_kernel(const NormRopeParams p) {
     const int h_pos = hw / p.grid.width;
     const int w_pos = hw % p.grid.width;
 
+    // this token's 64 rotation factors are shared by every head and by q and k: stage them once (1 KiB) instead of
+    // re-reading the table from L2 for each of the 2 x heads x 64 pairs
+    __shared__ double2 cs_s[128];
+    const int half = p.head_dim >> 1;
+    for (int pr = threadIdx.x; pr < half; pr += blockDim.x)
+        cs_s[pr] = __ldg(&p.freqs[rope_pos(pr, half, t_pos, h_pos, w_pos) * half + pr]);
+    __syncthreads();
+
     float q[kMaxVecPerThread][8], k[kMaxVecPerThread][8];
     float ss[2] = {0.f, 0.f};
 #pragma unroll
     for (int i = 0; i < kMaxVecPerThread; ++i) {
-        const int vi = threadIdx.x + i * kRowThreads;
+        const int vi = threadIdx.x + i * blockDim.x;
         if (vi < nvec) {
             unpack8(qr[vi], q[i]);
             unpack8(kr[vi], k[i]);
@@ -265,10 +287,9 @@ qk_norm_rope_append_kernel(const NormRopeParams p) {
     block_sum<2>(ss, scratch);
     const float rq = rsqrtf(ss[0] / C + p.eps);
     const float rk = rsqrtf(ss[1] / C + p.eps);
-    const int half = p.head_dim >> 1;
 #pragma unroll
     for (int i = 0; i < kMaxVecPerThread; ++i) {
-        const int vi = threadIdx.x + i * kRowThreads;
+        const int vi = threadIdx.x + i * blockDim.x;
         if (vi < nvec) {
             float wq[8], wk[8], qo[8], ko[8];
             unpack8(__ldg(reinterpret_cast<const uint4*>(p.wq) + vi), wq);
@@ -278,7 +299,7 @@ qk_norm_rope_append_kernel(const NormRopeParams p) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const int pair = pair0 + e;
-                const double2 cs = __ldg(&p.freqs[rope_pos(pair, half, t_pos, h_pos, w_pos) * half + pair]);
+                const double2 cs = cs_s[pair];
                 // RMSNorm: bf16(x * rsqrt) then bf16(.. * weight)  (components.py:118-126)
                 const double qa = bf16_round(bf16_round(q[i][2 * e] * rq) * wq[2 * e]);
                 const double qb = bf16_round(bf16_round(q[i][2 * e + 1] * rq) * wq[2 * e + 1]);
@@ -420,12 +441,12 @@ static ifx_status ln_modulate_entry(const void* x, void* out, const void* ln_wei
     {
         ProfScope prof(fp8 ? "ln_modulate_kernel<fp8>" : "ln_modulate_kernel", st);
         if (fp8)
-            ln_modulate_kernel<true><<<static_cast<unsigned>(rows), kRowThreads, 0, st>>>(
+            ln_modulate_kernel<true><<<static_cast<unsigned>(rows), row_threads(cols), 0, st>>>(
                 static_cast<const __nv_bfloat16*>(x), out, static_cast<const __nv_bfloat16*>(ln_weight),
                 static_cast<const __nv_bfloat16*>(ln_bias), static_cast<const __nv_bfloat16*>(shift),
                 static_cast<const __nv_bfloat16*>(scale), mod_frame_stride, cols, tpf, eps, out_scale);
         else
-            ln_modulate_kernel<false><<<static_cast<unsigned>(rows), kRowThreads, 0, st>>>(
+            ln_modulate_kernel<false><<<static_cast<unsigned>(rows), row_threads(cols), 0, st>>>(
                 static_cast<const __nv_bfloat16*>(x), out, static_cast<const __nv_bfloat16*>(ln_weight),
                 static_cast<const __nv_bfloat16*>(ln_bias), static_cast<const __nv_bfloat16*>(shift),
                 static_cast<const __nv_bfloat16*>(scale), mod_frame_stride, cols, tpf, eps, 1.0f);
@@ -477,7 +498,7 @@ extern "C" ifx_status ifx_rmsnorm(const void* x, int64_t ldx, const void* weight
     IFX_CHECK_ARG(ldx % 8 == 0 && ldo % 8 == 0 && ldx >= cols && ldo >= cols, "ifx_rmsnorm: bad strides");
     {
         ProfScope prof("rmsnorm_kernel", static_cast<cudaStream_t>(stream));
-        rmsnorm_kernel<<<static_cast<unsigned>(rows), kRowThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        rmsnorm_kernel<<<static_cast<unsigned>(rows), row_threads(cols), 0, static_cast<cudaStream_t>(stream)>>>(
             static_cast<const __nv_bfloat16*>(x), ldx, static_cast<const __nv_bfloat16*>(weight),
             static_cast<__nv_bfloat16*>(out), ldo, cols, eps);
     }
@@ -492,7 +513,7 @@ extern "C" ifx_status ifx_qk_norm_rope_append(const void* qkv, int64_t ld_qkv, c
                                               int32_t heads, int32_t head_dim, float eps, void* stream) {
     IFX_CHECK_ARG(qkv && norm_q_weight && norm_k_weight && freqs && grid && q_out, "ifx_qk_norm_rope_append: null");
     const int C = heads * head_dim;
-    IFX_CHECK_ARG(rows > 0 && C % 8 == 0 && C <= kRowThreads * kMaxVecPerThread * 8 && head_dim % 8 == 0,
+    IFX_CHECK_ARG(rows > 0 && C % 8 == 0 && C <= kRowThreads * kMaxVecPerThread * 8 && head_dim % 8 == 0 && head_dim <= 256,
                   "ifx_qk_norm_rope_append: bad shape heads=%d head_dim=%d", heads, head_dim);
     IFX_CHECK_ARG(ld_qkv >= 3 * C && ld_qkv % 8 == 0 && ld_q >= C && ld_q % 8 == 0,
                   "ifx_qk_norm_rope_append: bad strides");
@@ -540,7 +561,7 @@ extern "C" ifx_status ifx_qk_norm_rope_append(const void* qkv, int64_t ld_qkv, c
     }
     {
         ProfScope prof("qk_norm_rope_append_kernel", static_cast<cudaStream_t>(stream));
-        qk_norm_rope_append_kernel<<<static_cast<unsigned>(rows), kRowThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
+        qk_norm_rope_append_kernel<<<static_cast<unsigned>(rows), row_threads(C), 0, static_cast<cudaStream_t>(stream)>>>(p);
     }
     IFX_LAUNCH_OK("qk_norm_rope_append_kernel");
     return IFX_OK;

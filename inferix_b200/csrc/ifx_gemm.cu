@@ -9,8 +9,9 @@
 //
 // Replaces the cuBLAS nn.Linear calls + eager elementwise ops of the reference block
 // (inferix/models/self_forcing/causal_model.py:171-175,333,378-379,444,455-456; wan_base/model.py:77,98).
-#include "ifx_internal.h"
-#include "ifx_ptx.cuh"
+#include <cstdlib>
+
+#include "ifx_gemm_common.cuh"
 
 namespace ifx {
 
@@ -27,31 +28,6 @@ struct GemmCfg {
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kSmem = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
-
-struct GemmParams {
-    int64_t M;
-    int32_t N, K;
-    float alpha;  // FP8 path: input_scale * weight_scale applied to the fp32 accumulator before the bias
-    const __nv_bfloat16* bias;
-    __nv_bfloat16* out;
-    int64_t ldo;
-    const __nv_bfloat16* residual;
-    int64_t ldr;
-    const __nv_bfloat16* gate;
-    int64_t gate_frame_stride;
-    int64_t tokens_per_frame;
-    int32_t num_m_tiles, num_n_tiles;
-};
-
-__device__ __forceinline__ float gelu_tanh_f(float x) {
-    // 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3))), tanh(u) = 1 - 2 / (1 + e^{2u})
-    const float kBeta = 0.7978845608028654f;
-    const float kKappa = 0.044715f;
-    float u = kBeta * (x + kKappa * x * x * x);
-    float e = __expf(2.0f * u);
-    float t = 1.0f - __fdividef(2.0f, 1.0f + e);
-    return 0.5f * x * (1.0f + t);
-}
 
 template <int kEpi, int kBN, bool kFp8>
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -176,61 +152,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 uint32_t acc[32];
                 tmem_ld32(t_row + c * 32, acc);
                 tmem_wait_ld();
-                if (row_ok) {
-                    __nv_bfloat16* optr = p.out + row * p.ldo + col0;
-#pragma unroll
-                    for (int v = 0; v < 4; ++v) {
-                        if (col0 + v * 8 >= p.N) break;
-                        float bv[8];
-                        {
-                            uint4 braw = p.bias ? __ldg(reinterpret_cast<const uint4*>(p.bias + col0 + v * 8))
-                                                : make_uint4(0, 0, 0, 0);
-                            const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&braw);
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                float2 f = __bfloat1622float2(b2[e]);
-                                bv[2 * e] = f.x;
-                                bv[2 * e + 1] = f.y;
-                            }
-                        }
-                        float val[8];
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            const float a = __uint_as_float(acc[v * 8 + e]);
-                            val[e] = bf16_round((kFp8 ? a * p.alpha : a) + bv[e]);
-                        }
-                        if (kEpi == IFX_EPI_BIAS_GELU) {
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) val[e] = gelu_tanh_f(val[e]);
-                        }
-                        if (kEpi == IFX_EPI_BIAS_GATE_RES) {
-                            if (gate_row != nullptr) {
-                                uint4 graw = __ldg(reinterpret_cast<const uint4*>(gate_row + col0 + v * 8));
-                                const __nv_bfloat162* g2 = reinterpret_cast<const __nv_bfloat162*>(&graw);
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    float2 f = __bfloat1622float2(g2[e]);
-                                    val[2 * e] = bf16_round(val[2 * e] * f.x);
-                                    val[2 * e + 1] = bf16_round(val[2 * e + 1] * f.y);
-                                }
-                            }
-                            uint4 rraw = *reinterpret_cast<const uint4*>(p.residual + row * p.ldr + col0 + v * 8);
-                            const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rraw);
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                float2 f = __bfloat1622float2(r2[e]);
-                                val[2 * e] = f.x + val[2 * e];
-                                val[2 * e + 1] = f.y + val[2 * e + 1];
-                            }
-                        }
-                        uint4 o;
-                        o.x = pack_bf16x2(val[0], val[1]);
-                        o.y = pack_bf16x2(val[2], val[3]);
-                        o.z = pack_bf16x2(val[4], val[5]);
-                        o.w = pack_bf16x2(val[6], val[7]);
-                        *reinterpret_cast<uint4*>(optr + v * 8) = o;
-                    }
-                }
+                if (row_ok) gemm_epilogue_chunk<kEpi, kFp8>(p, acc, row, col0, gate_row);
             }
             tc_fence_before();
             mbar_arrive(&tmem_empty[as]);
@@ -272,6 +194,20 @@ static ifx_status launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, co
 
 using namespace ifx;
 
+namespace ifx {
+ifx_status gemm2_dispatch(bool fp8, const void* A, int64_t lda, const void* W, int64_t ldw, GemmParams p, int epilogue,
+                          cudaStream_t stream);
+// IFX_GEMM_2CTA=0 forces the 1-CTA kernel everywhere (A/B testing, bisecting)
+static bool use_2cta() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("IFX_GEMM_2CTA");
+        v = (e == nullptr || e[0] != '0') ? 1 : 0;
+    }
+    return v == 1;
+}
+}  // namespace ifx
+
 template <bool kFp8>
 static ifx_status gemm_entry(const void* A, int64_t lda, const void* W, int64_t ldw, float alpha, const void* bias,
                              void* out, int64_t ldo, int64_t M, int32_t N, int32_t K, int32_t epilogue,
@@ -303,6 +239,7 @@ static ifx_status gemm_entry(const void* A, int64_t lda, const void* W, int64_t 
         return static_cast<double>(tiles) / static_cast<double>(((tiles + sms - 1) / sms) * sms);
     };
     const int bn = (0.85 * wave_eff(128) > wave_eff(256)) ? 128 : 256;
+    const bool pair = bn == 256 && M >= 256 && use_2cta();   // 256 x 256 cluster tiles (ifx_gemm2.cu)
 
     CUtensorMap tmA, tmB;
     ifx_status st = kFp8 ? make_tmap_u8_2d(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, 2 * kBK, kBM)
@@ -328,6 +265,7 @@ static ifx_status gemm_entry(const void* A, int64_t lda, const void* W, int64_t 
     p.num_m_tiles = static_cast<int32_t>((M + kBM - 1) / kBM);
     p.num_n_tiles = (N + bn - 1) / bn;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (pair) return gemm2_dispatch(kFp8, A, lda, W, ldw, p, epilogue, s);
     if (bn == 256) {
         switch (epilogue) {
             case IFX_EPI_BIAS: return launch_gemm<IFX_EPI_BIAS, 256, kFp8>(tmA, tmB, p, s);

@@ -195,8 +195,8 @@ static ifx_status launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, co
 using namespace ifx;
 
 namespace ifx {
-ifx_status gemm2_dispatch(bool fp8, const void* A, int64_t lda, const void* W, int64_t ldw, GemmParams p, int epilogue,
-                          cudaStream_t stream);
+ifx_status gemm2_dispatch(bool fp8, int bn, const void* A, int64_t lda, const void* W, int64_t ldw, GemmParams p,
+                          int epilogue, cudaStream_t stream);
 // IFX_GEMM_2CTA=0 forces the 1-CTA kernel everywhere (A/B testing, bisecting)
 static bool use_2cta() {
     static int v = -1;
@@ -238,8 +238,18 @@ static ifx_status gemm_entry(const void* A, int64_t lda, const void* W, int64_t 
         const int64_t tiles = mt * ((N + bn - 1) / bn);
         return static_cast<double>(tiles) / static_cast<double>(((tiles + sms - 1) / sms) * sms);
     };
-    const int bn = (0.85 * wave_eff(128) > wave_eff(256)) ? 128 : 256;
-    const bool pair = bn == 256 && M >= 256 && use_2cta();   // 256 x 256 cluster tiles (ifx_gemm2.cu)
+    int bn = (0.85 * wave_eff(128) > wave_eff(256)) ? 128 : 256;
+    // 2-CTA kernel (ifx_gemm2.cu): 256-row cluster tiles, 256 or 128 columns wide, picked by the same wave argument
+    const bool pair = M >= 256 && use_2cta();
+    if (pair) {
+        const int clusters = sms / 2;
+        const int64_t mt2 = (M + 255) / 256;
+        auto eff2 = [&](int w) {
+            const int64_t tiles = mt2 * ((N + w - 1) / w);
+            return static_cast<double>(tiles) / static_cast<double>(((tiles + clusters - 1) / clusters) * clusters);
+        };
+        bn = (0.7 * eff2(128) > eff2(256)) ? 128 : 256;   // measured: a 128-wide cluster tile runs at ~0.7x the rate
+    }
 
     CUtensorMap tmA, tmB;
     ifx_status st = kFp8 ? make_tmap_u8_2d(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, 2 * kBK, kBM)
@@ -265,7 +275,7 @@ static ifx_status gemm_entry(const void* A, int64_t lda, const void* W, int64_t 
     p.num_m_tiles = static_cast<int32_t>((M + kBM - 1) / kBM);
     p.num_n_tiles = (N + bn - 1) / bn;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (pair) return gemm2_dispatch(kFp8, A, lda, W, ldw, p, epilogue, s);
+    if (pair) return gemm2_dispatch(kFp8, bn, A, lda, W, ldw, p, epilogue, s);
     if (bn == 256) {
         switch (epilogue) {
             case IFX_EPI_BIAS: return launch_gemm<IFX_EPI_BIAS, 256, kFp8>(tmA, tmB, p, s);

@@ -17,15 +17,19 @@
 namespace ifx {
 
 constexpr int k2BM = 128;        // rows per CTA (256 per cluster)
-constexpr int k2BNHalf = 128;    // weight rows staged per CTA
-constexpr int k2BN = 256;
 constexpr int k2BK = 64;
-constexpr int k2Stages = 6;
 constexpr int k2ABytes = k2BM * k2BK * 2;      // 16 KiB
-constexpr int k2BBytes = k2BNHalf * k2BK * 2;  // 16 KiB
-constexpr int k2StageBytes = k2ABytes + k2BBytes;
 constexpr int k2Threads = 384;      // 4 control warps + 8 epilogue warps (two per SM sub-partition)
-constexpr int k2Smem = k2Stages * k2StageBytes + 1024 + 256;
+// Cluster tile width: 256 (throughput shape) or 128 (small-M grids: twice the tiles, e.g. the 1350-row shard of an
+// 8-way sequence-parallel run).  Each CTA stages half of the weight rows.
+template <int kBN>
+struct Gemm2Cfg {
+    static constexpr int kBNHalf = kBN / 2;
+    static constexpr int kBBytes = kBNHalf * k2BK * 2;
+    static constexpr int kStageBytes = k2ABytes + kBBytes;
+    static constexpr int kStages = kBN == 256 ? 6 : 8;
+    static constexpr int kSmem = kStages * kStageBytes + 1024 + 256;
+};
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -83,9 +87,13 @@ __device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar, uint32_t cta) {
         : "memory");
 }
 
-template <int kEpi, bool kFp8>
+template <int kEpi, bool kFp8, int k2BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1)
 gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+    constexpr int k2BNHalf = Gemm2Cfg<k2BN>::kBNHalf;
+    constexpr int k2BBytes = Gemm2Cfg<k2BN>::kBBytes;
+    constexpr int k2StageBytes = Gemm2Cfg<k2BN>::kStageBytes;
+    constexpr int k2Stages = Gemm2Cfg<k2BN>::kStages;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sA = smem;
@@ -185,7 +193,7 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
     } else if (warp >= 4) {
         const int q = warp & 3;              // TMEM lane quadrant
-        const int chalf = (warp - 4) >> 2;   // warps 4..7 take columns [0,128), warps 8..11 columns [128,256)
+        const int chalf = (warp - 4) >> 2;   // warps 4..7 take the first half of the columns, warps 8..11 the second
         int it = 0;
         for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
             const int as = it & 1;
@@ -202,7 +210,8 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             tc_fence_after();
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * k2BN;
 #pragma unroll 1
-            for (int c = chalf * 4; c < chalf * 4 + 4; ++c) {
+            constexpr int kChunksPerHalf = k2BN / 64;   // 32-column chunks each epilogue half owns
+            for (int c = chalf * kChunksPerHalf; c < (chalf + 1) * kChunksPerHalf; ++c) {
                 const int col0 = n_blk * k2BN + c * 32;
                 if (col0 >= p.N) break;  // warp-uniform
                 uint32_t acc[32];
@@ -223,13 +232,14 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
 }
 
-template <int kEpi, bool kFp8>
+template <int kEpi, bool kFp8, int k2BN>
 static ifx_status launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p,
                                cudaStream_t stream) {
+    constexpr int k2Smem = Gemm2Cfg<k2BN>::kSmem;
     static bool configured = false;
     if (!configured) {
-        IFX_CUDA_OK(cudaFuncSetAttribute(gemm2_tn_kernel<kEpi, kFp8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         k2Smem));
+        IFX_CUDA_OK(cudaFuncSetAttribute(gemm2_tn_kernel<kEpi, kFp8, k2BN>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, k2Smem));
         configured = true;
     }
     const int tiles = p.num_m_tiles * p.num_n_tiles;
@@ -237,29 +247,33 @@ static ifx_status launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, c
     if (tiles < clusters) clusters = tiles;
     {
         char label[96];
-        snprintf(label, sizeof(label), "gemm_%s_tn_kernel<%d,2cta>[M=%lld,N=%d,K=%d]", kFp8 ? "fp8" : "bf16", kEpi,
-                 (long long)p.M, p.N, p.K);
+        snprintf(label, sizeof(label), "gemm_%s_tn_kernel<%d,2cta,%d>[M=%lld,N=%d,K=%d]", kFp8 ? "fp8" : "bf16", kEpi,
+                 k2BN, (long long)p.M, p.N, p.K);
         ProfScope prof(label, stream);
-        gemm2_tn_kernel<kEpi, kFp8><<<2 * clusters, k2Threads, k2Smem, stream>>>(tmA, tmB, p);
+        gemm2_tn_kernel<kEpi, kFp8, k2BN><<<2 * clusters, k2Threads, k2Smem, stream>>>(tmA, tmB, p);
     }
     IFX_LAUNCH_OK("gemm2_tn_kernel");
     return IFX_OK;
 }
 
-// Called by gemm_entry (ifx_gemm.cu) once arguments are validated.
-ifx_status gemm2_dispatch(bool fp8, const void* A, int64_t lda, const void* W, int64_t ldw, GemmParams p, int epilogue,
-                          cudaStream_t stream) {
+// Called by gemm_entry (ifx_gemm.cu) once arguments are validated.  bn = cluster tile width (256 or 128).
+ifx_status gemm2_dispatch(bool fp8, int bn, const void* A, int64_t lda, const void* W, int64_t ldw, GemmParams p,
+                          int epilogue, cudaStream_t stream) {
     CUtensorMap tmA, tmB;
     ifx_status st = fp8 ? make_tmap_u8_2d(&tmA, A, (uint64_t)p.K, (uint64_t)p.M, (uint64_t)lda, 2 * k2BK, k2BM)
                         : make_tmap_bf16_2d(&tmA, A, (uint64_t)p.K, (uint64_t)p.M, (uint64_t)lda, k2BK, k2BM);
     if (st != IFX_OK) return st;
-    st = fp8 ? make_tmap_u8_2d(&tmB, W, (uint64_t)p.K, (uint64_t)p.N, (uint64_t)ldw, 2 * k2BK, k2BNHalf)
-             : make_tmap_bf16_2d(&tmB, W, (uint64_t)p.K, (uint64_t)p.N, (uint64_t)ldw, k2BK, k2BNHalf);
+    st = fp8 ? make_tmap_u8_2d(&tmB, W, (uint64_t)p.K, (uint64_t)p.N, (uint64_t)ldw, 2 * k2BK, bn / 2)
+             : make_tmap_bf16_2d(&tmB, W, (uint64_t)p.K, (uint64_t)p.N, (uint64_t)ldw, k2BK, bn / 2);
     if (st != IFX_OK) return st;
     p.num_m_tiles = static_cast<int32_t>((p.M + 2 * k2BM - 1) / (2 * k2BM));
-    p.num_n_tiles = (p.N + k2BN - 1) / k2BN;
-#define IFX_G2(E)                                                     \
-    return fp8 ? launch_gemm2<E, true>(tmA, tmB, p, stream) : launch_gemm2<E, false>(tmA, tmB, p, stream)
+    p.num_n_tiles = (p.N + bn - 1) / bn;
+#define IFX_G2(E)                                                                                         \
+    do {                                                                                                  \
+        if (bn == 256)                                                                                    \
+            return fp8 ? launch_gemm2<E, true, 256>(tmA, tmB, p, stream) : launch_gemm2<E, false, 256>(tmA, tmB, p, stream); \
+        return fp8 ? launch_gemm2<E, true, 128>(tmA, tmB, p, stream) : launch_gemm2<E, false, 128>(tmA, tmB, p, stream);     \
+    } while (0)
     switch (epilogue) {
         case IFX_EPI_BIAS: IFX_G2(IFX_EPI_BIAS);
         case IFX_EPI_BIAS_GELU: IFX_G2(IFX_EPI_BIAS_GELU);

@@ -156,3 +156,74 @@ def test_causvid_pipeline_matches_reference(case, golden_dir):
                              start_latents=None if start is None else start.to(DEV), return_latents=True,
                              kv_cache_manager=mgr, kv_cache_requests=reqs)
     assert torch.equal(out2, out)
+
+
+def _tiny_pipe(local_attn_size=6, steps=(1000, 500)):
+    return build(dict(__import__("inferix_b200.synthetic", fromlist=["TINY"]).TINY), local_attn_size, 0, list(steps), 5.0)
+
+
+def test_video_extension_and_cache_reuse():
+    """initial_latent (video extension, reference :213-253): the given blocks are copied to the output and cached with
+    a t=0 forward; a second inference() on the same pipeline resets the native block tables and reproduces."""
+    pipe = _tiny_pipe()
+    g = torch.Generator().manual_seed(9)
+    noise = torch.randn(1, 6, 16, 16, 16, generator=g).bfloat16().to(DEV)
+    init = torch.randn(1, 3, 16, 16, 16, generator=g).bfloat16().to(DEV)
+    ctx = torch.randn(1, 20, 64, generator=g).bfloat16().to(DEV)
+    mgr, reqs = KVCacheManager(DEV), [KVCacheRequest("r0")]
+    outs = []
+    for _ in range(2):
+        gen = torch.Generator().manual_seed(5)
+        pipe.renoise_fn = lambda x: torch.randn(x.shape, generator=gen, dtype=torch.float32).to(x.dtype).to(x.device)
+        out = pipe.inference(noise=noise, text_prompts=ctx, kv_cache_manager=mgr, kv_cache_requests=reqs,
+                             initial_latent=init, free_cache_before_vae=False, decode_mode=DecodeMode.NO_DECODE)
+        outs.append(out)
+        assert out.shape == (1, 9, 16, 16, 16) and torch.equal(out[:, :3], init)
+        assert int(pipe.kv_cache_meta[0]["global_end_index"]) == 9 * 64
+        assert int(pipe.kv_cache_meta[0]["local_end_index"]) == 6 * 64           # 6-frame window
+    assert torch.equal(outs[0], outs[1])
+    # free_cache_before_vae=True releases every layer and the meta lists (reference :398-400, :494-502)
+    pipe.inference(noise=noise, text_prompts=ctx, kv_cache_manager=mgr, kv_cache_requests=reqs,
+                   decode_mode=DecodeMode.NO_DECODE)
+    assert pipe.kv_cache_meta is None and list(mgr.layers(reqs[0])) == []
+
+
+def test_two_requests_batch_equals_two_single_runs():
+    """kv_cache_requests is the batch dimension (reference :422-429): B = 2 equals two B = 1 runs."""
+    g = torch.Generator().manual_seed(10)
+    noise = torch.randn(2, 3, 16, 16, 16, generator=g).bfloat16().to(DEV)
+    ctx = torch.randn(2, 20, 64, generator=g).bfloat16().to(DEV)
+
+    def run(nz, cx, names):
+        pipe = _tiny_pipe(steps=(1000,))       # single step: no re-noising, so batching cannot change the RNG stream
+        return pipe.inference(noise=nz, text_prompts=cx, kv_cache_manager=KVCacheManager(DEV),
+                              kv_cache_requests=[KVCacheRequest(n) for n in names], decode_mode=DecodeMode.NO_DECODE)
+    both = run(noise, ctx, ["a", "b"])
+    one_a, one_b = run(noise[:1], ctx[:1], ["a"]), run(noise[1:], ctx[1:], ["b"])
+    assert rel_l2(both[0], one_a[0]) <= 1e-3 and rel_l2(both[1], one_b[0]) <= 1e-3
+
+
+def test_decode_requires_vae_and_reports_block_times():
+    pipe = _tiny_pipe(steps=(1000,))
+    g = torch.Generator().manual_seed(11)
+    noise = torch.randn(1, 3, 16, 16, 16, generator=g).bfloat16().to(DEV)
+    ctx = torch.randn(1, 20, 64, generator=g).bfloat16().to(DEV)
+    with pytest.raises(RuntimeError, match="VAE"):
+        pipe.inference(noise=noise, text_prompts=ctx, kv_cache_manager=KVCacheManager(DEV),
+                       kv_cache_requests=[KVCacheRequest("r")])
+    pipe2 = _tiny_pipe(steps=(1000,))
+    pipe2.inference(noise=noise, text_prompts=ctx, kv_cache_manager=KVCacheManager(DEV),
+                    kv_cache_requests=[KVCacheRequest("r")], decode_mode=DecodeMode.NO_DECODE, profile=True)
+    assert len(pipe2.last_block_times_ms) == 1 and pipe2.last_block_times_ms[0] > 0
+
+
+def test_wrong_dtype_and_device_fail_loudly():
+    from inferix_b200 import ops
+    with pytest.raises(ValueError):
+        ops.gemm(torch.zeros(8, 8), torch.zeros(8, 8))                               # CPU tensors
+    with pytest.raises(ValueError):
+        ops.gemm(torch.zeros(8, 8, device=DEV), torch.zeros(8, 8, device=DEV))       # fp32
+    with pytest.raises(ValueError):
+        KVCacheManager("cpu")
+    with pytest.raises(NotImplementedError):
+        CausalWanModel(dim=512, num_heads=8)                                         # head_dim 64

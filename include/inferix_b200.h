@@ -202,6 +202,20 @@ ifx_status ifx_attention(const void* q, int64_t ldq, const void* k, const void* 
 ifx_status ifx_attention_gqa(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, void* out,
                              int64_t ldo, int64_t q_rows, int64_t kv_rows, int32_t heads, int32_t kv_heads,
                              int32_t head_dim, float softmax_scale, void* stream);
+/* Two-phase attention for overlapping the sequence-parallel K/V exchange with compute.  ifx_attention_partial attends
+ * the queries to a LIST of key-row extents (up to 4 [row0, rows) pairs inside k/v[0:kv_rows_total)) and writes, for
+ * every (head, 256-row pair) item, un-normalised partials (O, max, sum) into `workspace` at piece slots
+ * [piece_first, piece_first + piece_count) of `pieces_per_item`; the extent list is cut into piece_count key ranges,
+ * one CTA each.  ifx_attention_combine merges the pieces into out = O / l.  Usage: phase 1 = pages already in the
+ * cache (runs while the all-gather of the new K/V is in flight), phase 2 = the block's own pages, then combine.
+ * workspace bytes = items * pieces_per_item * 256 * 130 * 4, items = heads * ceil(q_rows / 256). */
+ifx_status ifx_attention_partial(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv,
+                                 int64_t kv_rows_total, const int64_t* extents, int32_t n_ext, int64_t q_rows,
+                                 int32_t heads, int32_t kv_heads, int32_t head_dim, float softmax_scale,
+                                 void* workspace, int64_t workspace_bytes, int32_t pieces_per_item,
+                                 int32_t piece_first, int32_t piece_count, void* stream);
+ifx_status ifx_attention_combine(const void* workspace, int32_t pieces_per_item, void* out, int64_t ldo,
+                                 int64_t q_rows, int32_t heads, int32_t head_dim, void* stream);
 /* Same, keys/values taken from the valid prefix of a paged cache (rows [0, local_end)). */
 ifx_status ifx_attention_kv(const void* q, int64_t ldq, const ifx_kv* kv, void* out, int64_t ldo, int64_t q_rows,
                             float softmax_scale, void* stream);

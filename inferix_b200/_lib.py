@@ -107,6 +107,9 @@ SIGNATURES = {
     "ifx_rmsnorm": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _i64, _i32, _f32, _vp]),
     "ifx_attention": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _vp, _i64, _i64, _i64, _i32, _i32, _f32, _vp]),
     "ifx_attention_gqa": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _vp, _i64, _i64, _i64, _i32, _i32, _i32, _f32, _vp]),
+    "ifx_attention_partial": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _i64, C.POINTER(_i64), _i32, _i64, _i32, _i32, _i32,
+                                        _f32, _vp, _i64, _i32, _i32, _i32, _vp]),
+    "ifx_attention_combine": (C.c_int, [_vp, _i32, _vp, _i64, _i64, _i32, _i32, _vp]),
     "ifx_attention_kv": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _i64, _f32, _vp]),
     "ifx_wan_block_forward": (C.c_int, [C.POINTER(WanBlockWeights), C.POINTER(WanBlockIO), C.POINTER(KvPlan), _vp]),
 }

@@ -54,7 +54,30 @@ struct AttnParams {
     int64_t ldo;
     float* part_o;       // [pieces][256][128] un-normalised O
     float* part_ml;      // [pieces][256][2]   (max * scale_log2, sum)
+    // ---- partial mode (ifx_attention_partial): every CTA emits a partial; keys are a list of row extents
+    int32_t partial;         // 1: blockIdx = item * piece_count + sub, slot = item * pieces_per_item + piece_first + sub
+    int32_t pieces_per_item;
+    int32_t piece_first;
+    int32_t piece_count;
+    int32_t n_ext;           // 0: one dense extent [0, kv_rows)
+    int32_t ext_row0[4];     // first key row of each extent
+    int32_t ext_rows[4];     // keys in each extent
+    int32_t ext_tile0[5];    // cumulative 128-key tile counts
 };
+
+// key tile j (over the concatenated extents) -> first key row and number of valid keys in the tile
+__device__ __forceinline__ void kv_tile_info(const AttnParams& p, int j, int& row0, int& valid) {
+    if (p.n_ext == 0) {
+        row0 = j * kKT;
+        valid = p.kv_rows - row0;
+        return;
+    }
+    int e = 0;
+    while (e + 1 < p.n_ext && j >= p.ext_tile0[e + 1]) ++e;
+    const int lt = j - p.ext_tile0[e];
+    row0 = p.ext_row0[e] + lt * kKT;
+    valid = p.ext_rows[e] - lt * kKT;
+}
 
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -76,9 +99,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int lane = threadIdx.x & 31;
 
     // ---- which (item, key range) does this CTA own
-    const int n_kv_all = (p.kv_rows + kKT - 1) / kKT;
+    const int n_kv_all = p.n_ext ? p.ext_tile0[p.n_ext] : (p.kv_rows + kKT - 1) / kKT;
     int item, piece = -1, kv_begin = 0, kv_end = n_kv_all;
-    if (static_cast<int>(blockIdx.x) < p.n_whole) {
+    if (p.partial) {
+        item = blockIdx.x / p.piece_count;
+        const int sub = blockIdx.x % p.piece_count;
+        piece = item * p.pieces_per_item + p.piece_first + sub;
+        kv_begin = static_cast<int>(static_cast<int64_t>(n_kv_all) * sub / p.piece_count);
+        kv_end = static_cast<int>(static_cast<int64_t>(n_kv_all) * (sub + 1) / p.piece_count);
+    } else if (static_cast<int>(blockIdx.x) < p.n_whole) {
         item = blockIdx.x;
     } else {
         const int idx = blockIdx.x - p.n_whole;
@@ -136,6 +165,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                                      q0 + w * kQT, kEvictFirst);
             int idx = 0;
             for (int j = kv_begin; j < kv_end; ++j) {
+                int krow0, kvalid;
+                kv_tile_info(p, j, krow0, kvalid);
 #pragma unroll
                 for (int kv = 0; kv < 2; ++kv, ++idx) {
                     const int s = idx % kSlots;
@@ -146,7 +177,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
                     for (int h = 0; h < 2; ++h)
                         tma_load_2d_hint(sKV + s * kTileBytes + h * kHalfBytes, tm, &kv_full[s],
-                                         (head / p.kv_group) * kHD + h * 64, j * kKT, kEvictLast);
+                                         (head / p.kv_group) * kHD + h * 64, krow0, kEvictLast);
                 }
             }
         }
@@ -241,7 +272,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
                 for (int c = 0; c < 4; ++c) tmem_ld32(tS_row + c * 32, s[c]);
                 tmem_wait_ld();
-                const int valid = p.kv_rows - (kv_begin + j) * kKT;
+                int krow0, valid;
+                kv_tile_info(p, kv_begin + j, krow0, valid);
                 if (valid < kKT) {
 #pragma unroll
                     for (int c = 0; c < 4; ++c)
@@ -389,6 +421,8 @@ attn_combine_kernel(const AttnParams p) {
     *reinterpret_cast<uint2*>(p.out + static_cast<int64_t>(row) * p.ldo + head * kHD + lane * 4) = pkt;
 }
 
+static void fill_defaults(AttnParams& p);
+
 // persistent scratch for split partials (grown on demand; one stream at a time, see header "not thread-safe")
 static float* g_part = nullptr;
 static size_t g_part_bytes = 0;
@@ -423,6 +457,7 @@ static ifx_status attention_launch(const void* q, int64_t ldq, const void* k, co
         configured = true;
     }
     AttnParams p;
+    fill_defaults(p);
     p.q_rows = static_cast<int32_t>(q_rows);
     p.kv_rows = static_cast<int32_t>(kv_rows);
     p.heads = heads;
@@ -480,9 +515,117 @@ static ifx_status attention_launch(const void* q, int64_t ldq, const void* k, co
     return IFX_OK;
 }
 
+static void fill_defaults(AttnParams& p) {
+    p.partial = 0;
+    p.pieces_per_item = p.piece_count = 1;
+    p.piece_first = 0;
+    p.n_ext = 0;
+    for (int i = 0; i < 4; ++i) p.ext_row0[i] = p.ext_rows[i] = 0;
+    for (int i = 0; i < 5; ++i) p.ext_tile0[i] = 0;
+}
+
 }  // namespace ifx
 
 using namespace ifx;
+
+extern "C" ifx_status ifx_attention_partial(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv,
+                                            int64_t kv_rows_total, const int64_t* extents, int32_t n_ext,
+                                            int64_t q_rows, int32_t heads, int32_t kv_heads, int32_t head_dim,
+                                            float softmax_scale, void* workspace, int64_t workspace_bytes,
+                                            int32_t pieces_per_item, int32_t piece_first, int32_t piece_count,
+                                            void* stream) {
+    IFX_CHECK_ARG(q && k && v && extents && workspace, "ifx_attention_partial: null pointer");
+    IFX_CHECK_ARG(head_dim == kHD, "ifx_attention_partial: head_dim must be 128");
+    IFX_CHECK_ARG(n_ext >= 1 && n_ext <= 4, "ifx_attention_partial: 1..4 key extents (got %d)", n_ext);
+    if (kv_heads <= 0) kv_heads = heads;
+    IFX_CHECK_ARG(heads > 0 && heads % kv_heads == 0, "ifx_attention_partial: bad head counts");
+    IFX_CHECK_ARG(q_rows > 0 && q_rows < (1ll << 31) && kv_rows_total > 0 && kv_rows_total < (1ll << 31),
+                  "ifx_attention_partial: bad sizes");
+    IFX_CHECK_ARG(pieces_per_item >= 1 && piece_count >= 1 && piece_first >= 0 &&
+                      piece_first + piece_count <= pieces_per_item,
+                  "ifx_attention_partial: piece window [%d, %d) outside [0, %d)", piece_first,
+                  piece_first + piece_count, pieces_per_item);
+    const int64_t width = static_cast<int64_t>(heads) * head_dim, kv_width = static_cast<int64_t>(kv_heads) * head_dim;
+    IFX_CHECK_ARG(ldq >= width && ldkv >= kv_width && ldq % 8 == 0 && ldkv % 8 == 0, "ifx_attention_partial: strides");
+    AttnParams p;
+    fill_defaults(p);
+    p.n_ext = n_ext;
+    int tiles = 0;
+    for (int i = 0; i < n_ext; ++i) {
+        const int64_t r0 = extents[2 * i], n = extents[2 * i + 1];
+        IFX_CHECK_ARG(r0 >= 0 && n > 0 && r0 + n <= kv_rows_total, "ifx_attention_partial: extent %d out of range", i);
+        p.ext_row0[i] = static_cast<int32_t>(r0);
+        p.ext_rows[i] = static_cast<int32_t>(n);
+        p.ext_tile0[i] = tiles;
+        tiles += static_cast<int>((n + kKT - 1) / kKT);
+    }
+    for (int i = n_ext; i < 5; ++i) p.ext_tile0[i] = tiles;
+    IFX_CHECK_ARG(tiles >= piece_count, "ifx_attention_partial: more pieces (%d) than key tiles (%d)", piece_count, tiles);
+    p.q_rows = static_cast<int32_t>(q_rows);
+    p.kv_rows = static_cast<int32_t>(kv_rows_total);
+    p.heads = heads;
+    p.kv_group = heads / kv_heads;
+    p.num_q_pairs = static_cast<int32_t>((q_rows + 2 * kQT - 1) / (2 * kQT));
+    p.scale_log2 = softmax_scale * 1.4426950408889634f;
+    p.out = nullptr;
+    p.ldo = 0;
+    p.n_whole = 0;
+    p.split = 1;
+    p.partial = 1;
+    p.pieces_per_item = pieces_per_item;
+    p.piece_first = piece_first;
+    p.piece_count = piece_count;
+    const int items = p.num_q_pairs * heads;
+    const size_t slots = static_cast<size_t>(items) * pieces_per_item;
+    const size_t need = slots * (2 * kQT) * (kHD + 2) * sizeof(float);
+    IFX_CHECK_ARG(static_cast<size_t>(workspace_bytes) >= need, "ifx_attention_partial: workspace needs %zu bytes", need);
+    p.part_o = static_cast<float*>(workspace);
+    p.part_ml = p.part_o + slots * (2 * kQT) * kHD;
+
+    CUtensorMap tmQ, tmK, tmV;
+    ifx_status st = make_tmap_bf16_2d(&tmQ, q, (uint64_t)width, (uint64_t)q_rows, (uint64_t)ldq, 64, kQT);
+    if (st != IFX_OK) return st;
+    st = make_tmap_bf16_2d(&tmK, k, (uint64_t)kv_width, (uint64_t)kv_rows_total, (uint64_t)ldkv, 64, kKT);
+    if (st != IFX_OK) return st;
+    st = make_tmap_bf16_2d(&tmV, v, (uint64_t)kv_width, (uint64_t)kv_rows_total, (uint64_t)ldkv, 64, kKT);
+    if (st != IFX_OK) return st;
+    IFX_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    {
+        char label[96];
+        snprintf(label, sizeof(label), "attn_fwd_kernel<partial>[Lq=%d,tiles=%d,H=%d]", p.q_rows, tiles, heads);
+        ProfScope prof(label, s);
+        attn_fwd_kernel<<<items * piece_count, kAttnThreads, kAttnSmem, s>>>(tmQ, tmK, tmV, p);
+    }
+    IFX_LAUNCH_OK("attn_fwd_kernel<partial>");
+    return IFX_OK;
+}
+
+extern "C" ifx_status ifx_attention_combine(const void* workspace, int32_t pieces_per_item, void* out, int64_t ldo,
+                                            int64_t q_rows, int32_t heads, int32_t head_dim, void* stream) {
+    IFX_CHECK_ARG(workspace && out, "ifx_attention_combine: null pointer");
+    IFX_CHECK_ARG(head_dim == kHD && pieces_per_item >= 1 && q_rows > 0 && heads > 0, "ifx_attention_combine: bad args");
+    AttnParams p;
+    fill_defaults(p);
+    p.q_rows = static_cast<int32_t>(q_rows);
+    p.heads = heads;
+    p.num_q_pairs = static_cast<int32_t>((q_rows + 2 * kQT - 1) / (2 * kQT));
+    p.out = static_cast<__nv_bfloat16*>(out);
+    p.ldo = ldo;
+    p.n_whole = 0;
+    p.split = pieces_per_item;
+    const int items = p.num_q_pairs * heads;
+    const size_t slots = static_cast<size_t>(items) * pieces_per_item;
+    p.part_o = const_cast<float*>(static_cast<const float*>(workspace));
+    p.part_ml = p.part_o + slots * (2 * kQT) * kHD;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    {
+        ProfScope prof("attn_combine_kernel", s);
+        attn_combine_kernel<<<items * (2 * kQT) / 8, 256, 0, s>>>(p);
+    }
+    IFX_LAUNCH_OK("attn_combine_kernel");
+    return IFX_OK;
+}
 
 extern "C" ifx_status ifx_attention(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, void* out,
                                     int64_t ldo, int64_t q_rows, int64_t kv_rows, int32_t heads, int32_t head_dim,

@@ -14,7 +14,8 @@ from . import _lib
 from ._lib import EPI_BIAS, EPI_BIAS_GATE_RES, EPI_BIAS_GELU, KvPlan, RopeGrid
 
 __all__ = [
-    "ln_modulate", "gemm", "rmsnorm", "quantize_fp8", "ln_modulate_fp8", "gemm_fp8", "attention", "attention_gqa", "attention_ranges", "qk_norm_rope_append", "PagedKV", "rope_table",
+    "ln_modulate", "gemm", "rmsnorm", "quantize_fp8", "ln_modulate_fp8", "gemm_fp8", "attention", "attention_gqa", "attention_ranges", "attention_partial", "attention_combine",
+    "attention_workspace_bytes", "qk_norm_rope_append", "PagedKV", "rope_table",
     "EPI_BIAS", "EPI_BIAS_GELU", "EPI_BIAS_GATE_RES",
 ]
 
@@ -212,6 +213,43 @@ def attention_ranges(q, k, v, q_ranges, k_ranges, heads, kv_heads, *, softmax_sc
     return out
 
 
+def _coalesce_pages(pages, page_tokens):
+    """sorted physical pages -> list of (first_row, rows) runs of consecutive pages."""
+    runs = []
+    for pg in sorted(pages):
+        if runs and runs[-1][0] + runs[-1][1] == pg * page_tokens:
+            runs[-1][1] += page_tokens
+        else:
+            runs.append([pg * page_tokens, page_tokens])
+    return [tuple(r) for r in runs]
+
+
+def attention_partial(q, k, v, extents, heads, workspace, pieces_per_item, piece_first, piece_count, *,
+                      kv_heads=None, softmax_scale=None):
+    """Phase of a two-phase attention: q [Lq, heads*D] against the key-row extents [(row0, rows), ...] of k/v;
+    un-normalised partials go to `workspace` (float32, see attention_workspace_bytes)."""
+    q, k, v = _bf16_2d(q, "q"), _bf16_2d(k, "k"), _bf16_2d(v, "v")
+    kv_heads = kv_heads or heads
+    head_dim = q.shape[1] // heads
+    ext = (C.c_int64 * (2 * len(extents)))(*[int(x) for e in extents for x in e])
+    scale = softmax_scale if softmax_scale is not None else head_dim ** -0.5
+    _lib.check(_lib.load().ifx_attention_partial(
+        q.data_ptr(), q.stride(0), k.data_ptr(), v.data_ptr(), k.stride(0), k.shape[0], ext, len(extents), q.shape[0],
+        heads, kv_heads, head_dim, scale, workspace.data_ptr(), workspace.numel() * workspace.element_size(),
+        pieces_per_item, piece_first, piece_count, _stream()))
+
+
+def attention_combine(workspace, pieces_per_item, out, heads):
+    out = _bf16_2d(out, "out")
+    _lib.check(_lib.load().ifx_attention_combine(workspace.data_ptr(), pieces_per_item, out.data_ptr(), out.stride(0),
+                                                 out.shape[0], heads, out.shape[1] // heads, _stream()))
+    return out
+
+
+def attention_workspace_bytes(q_rows: int, heads: int, pieces_per_item: int) -> int:
+    return heads * ((q_rows + 255) // 256) * pieces_per_item * 256 * 130 * 4
+
+
 class PagedKV:
     """One layer's self-attention cache: two bf16 buffers + the native block table (ifx_kv)."""
 
@@ -278,6 +316,14 @@ class PagedKV:
         _lib.check(_lib.load().ifx_kv_append_sp(self.handle, C.byref(plan), k_gathered.data_ptr(),
                                                 v_gathered.data_ptr(), k_gathered.stride(0), world, frames,
                                                 rows // frames, _stream()))
+
+    def split_extents(self, plan: KvPlan):
+        """(old, new): physical key-row extents of the valid pages NOT written by `plan` and of the pages it writes.
+        Attention is invariant to key order, so the two groups can be attended separately and merged."""
+        _, _, table = self.state()
+        new_pages = list(plan.pages[: plan.num_pages])
+        old_pages = [pg for pg in table if pg not in set(new_pages)]
+        return _coalesce_pages(old_pages, self.page_tokens), _coalesce_pages(new_pages, self.page_tokens)
 
     def export(self, start: int, length: int):
         """Tokens [start, start+length) in the reference's logical order -> (k, v) each [length, H*D]."""

@@ -299,12 +299,37 @@ class CausalWanAttentionBlock(nn.Module):
         if world > 1:
             ops.qk_norm_rope_append(ws.qkv, sa.norm_q.weight, sa.norm_k.weight, freqs, grid, heads, hd, q_out=ws.q,
                                     k_out=ws.kv_new[0], v_out=ws.kv_new[1], eps=self.eps)
-            kvg = all_gather_rows(ws.kv_new, pc, ws.kv_all)       # ONE all-gather: [P, 2, rows, C]
-            store.append_sp(plan, kvg[:, 0], kvg[:, 1], frames)
+            old_ext, new_ext = store.split_extents(plan)
+            if _SP_OVERLAP and len(old_ext) <= 4 and len(new_ext) <= 4:
+                # exchange on a side stream while the local queries attend the keys that are already in the cache
+                main = torch.cuda.current_stream()
+                side = ws.side_stream
+                ready = torch.cuda.Event()
+                ready.record(main)
+                with torch.cuda.stream(side):
+                    side.wait_event(ready)
+                    kvg = all_gather_rows(ws.kv_new, pc, ws.kv_all)   # ONE all-gather: [P, 2, rows, C]
+                    gathered = torch.cuda.Event()
+                    gathered.record(side)
+                # one piece per item unless the grid would not fill the SMs (8-way SP: 72 items on 148 SMs -> 2)
+                items = heads * ((rows + 255) // 256)
+                old_tiles = sum((n + 127) // 128 for _, n in old_ext)
+                n_old = min(8, old_tiles, max(1, ws.sm_count // items)) if old_ext else 0
+                part = ws.partials(rows, heads, n_old + 1)
+                if old_ext:
+                    ops.attention_partial(ws.q, store.k, store.v, old_ext, heads, part, n_old + 1, 0, n_old)
+                main.wait_event(gathered)
+                store.append_sp(plan, kvg[:, 0], kvg[:, 1], frames)
+                ops.attention_partial(ws.q, store.k, store.v, new_ext, heads, part, n_old + 1, n_old, 1)
+                ops.attention_combine(part, n_old + 1, ws.attn, heads)
+            else:
+                kvg = all_gather_rows(ws.kv_new, pc, ws.kv_all)
+                store.append_sp(plan, kvg[:, 0], kvg[:, 1], frames)
+                store.attention(ws.q, ws.attn)
         else:
             ops.qk_norm_rope_append(ws.qkv, sa.norm_q.weight, sa.norm_k.weight, freqs, grid, heads, hd, kv=store,
                                     plan=plan, q_out=ws.q, eps=self.eps)
-        store.attention(ws.q, ws.attn)
+            store.attention(ws.q, ws.attn)
         linear("o", ws.attn, None, sa.o.weight, sa.o.bias, x, epilogue=ops.EPI_BIAS_GATE_RES, residual=x,
                gate=m[:, 2], tokens_per_frame=fs)
         h, h8 = ln("cq", weight=self.norm3.weight, bias=self.norm3.bias)
@@ -319,6 +344,25 @@ class CausalWanAttentionBlock(nn.Module):
         return plan
 
 
+# IFX_SP_OVERLAP=1 turns on the exchange/compute overlap of the sequence-parallel path: local queries attend the pages
+# already in the cache (phase 1) while the all-gather of the new K/V runs on a side stream, then the new pages
+# (phase 2), merged by attn_combine_kernel.  Off by default: measured 4 % SLOWER at 2 GPUs (the gather is only
+# ~50 us there and the second launch + partial traffic cost more); it targets 4-8 ranks where the gather is 10 % of
+# the layer, which this round could not re-measure.
+_SP_OVERLAP = __import__("os").environ.get("IFX_SP_OVERLAP", "0") == "1"
+
+
+def _pieces_for(q_rows: int, heads: int, sms: int) -> int:
+    """Key-range pieces per (head, 256-row pair) item so that items * pieces fills whole waves of SMs."""
+    items = heads * ((q_rows + 255) // 256)
+    best, best_cost = 1, float("inf")
+    for s in range(1, 9):
+        cost = -(-items * s // sms) / s
+        if cost < best_cost - 1e-9:
+            best, best_cost = s, cost
+    return best
+
+
 class _Workspace:
     """Scratch activations of one block forward, reused by every layer (all bf16)."""
 
@@ -328,9 +372,19 @@ class _Workspace:
         self.rows = rows
         self.h, self.qkv, self.q, self.attn, self.ffn = buf(rows, dim), buf(rows, 3 * dim), buf(rows, dim), buf(rows, dim), buf(rows, ffn_dim)
         self._q8 = {}
+        self._part = None
         if world > 1:
+            self.side_stream = torch.cuda.Stream(device=device)
+            self.sm_count = torch.cuda.get_device_properties(device).multi_processor_count
             self.kv_new = buf(2, rows, dim)              # this rank's new roped-K | V, one send buffer
             self.kv_all = buf(world, 2, rows, dim)       # all-gather destination
+
+    def partials(self, q_rows, heads, pieces_per_item):
+        """float32 scratch for two-phase attention partials (grown on demand)."""
+        need = ops.attention_workspace_bytes(q_rows, heads, pieces_per_item) // 4
+        if self._part is None or self._part.numel() < need:
+            self._part = torch.empty(need, dtype=torch.float32, device=self.h.device)
+        return self._part
 
     def q8(self, site, shape):
         """e4m3 staging buffer for a GEMM input (lazily allocated, keyed by shape)."""

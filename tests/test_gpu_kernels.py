@@ -269,3 +269,25 @@ def test_magi_kv_cache_manager_matches_reference(golden_dir):
     assert torch.equal(mapped[:, :written].cpu(), gold["final_cache"][:, :written])
     mgr.clear_cache(ip)
     assert not mgr.is_cached(ip)
+
+
+def test_two_phase_attention_equals_single_pass():
+    """attention over [old extents] + [new extents] merged by the combine kernel == one pass over all keys
+    (the sequence-parallel overlap path; extents are whole pages in arbitrary physical order)."""
+    heads, D, pt, pages = 3, 128, 200, 7
+    q = bf(700, heads * D, seed=50).to(DEV)
+    k, v = bf(pages * pt, heads * D, seed=51).to(DEV), bf(pages * pt, heads * D, seed=52).to(DEV)
+    ref = ops.attention(q, k, v, heads)
+    new_ext = ops._coalesce_pages([5, 1, 2], pt)            # -> rows [200, 600) and [1000, 1200)
+    old_ext = ops._coalesce_pages([0, 3, 4, 6], pt)
+    assert new_ext == [(200, 400), (1000, 200)] and old_ext == [(0, 200), (600, 400), (1200, 200)]
+    for n_old in (1, 2, 5):
+        ws = torch.empty(ops.attention_workspace_bytes(700, heads, n_old + 1) // 4, dtype=torch.float32, device=DEV)
+        ops.attention_partial(q, k, v, old_ext, heads, ws, n_old + 1, 0, n_old)
+        ops.attention_partial(q, k, v, new_ext, heads, ws, n_old + 1, n_old, 1)
+        out = ops.attention_combine(ws, n_old + 1, torch.empty_like(q), heads)
+        assert rel_l2(out, ref) <= 5e-3, n_old
+    # one phase only (first block of a video: nothing old yet)
+    ws = torch.empty(ops.attention_workspace_bytes(700, heads, 1) // 4, dtype=torch.float32, device=DEV)
+    ops.attention_partial(q, k, v, [(0, pages * pt)], heads, ws, 1, 0, 1)
+    assert rel_l2(ops.attention_combine(ws, 1, torch.empty_like(q), heads), ref) <= 5e-3

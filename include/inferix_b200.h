@@ -77,6 +77,14 @@ typedef struct ifx_kv_plan {
     int32_t first_offset;  /* token offset inside pages[0] where the new tokens start (0 when frame-aligned) */
 } ifx_kv_plan;
 
+/* Direct row access for caches that are only ever written in place (MAGI-1: kvcache_manager/model/
+ * magi_kv_cache_manager.py:110-146 reads [0, start) and `set`s [start, start+clip); nothing is evicted).  Extends the
+ * block table so that logical tokens [0, tokens) are mapped (identity: logical row i = physical row i) and returns the
+ * base pointers of the K and V rows ([token, heads*head_dim] bf16).  A kernel may then write new tokens straight into
+ * rows [start, start+n) and attend rows [0, start+n) without any get_range / cat copy.  IFX_ERR_UNSUPPORTED once
+ * ifx_kv_plan_append has rotated the table (windowed Wan caches). */
+ifx_status ifx_kv_map(ifx_kv* kv, int64_t tokens, void** k_rows, void** v_rows);
+
 ifx_status ifx_kv_create(ifx_kv** out, void* k_base, void* v_base, int32_t num_pages, int32_t page_tokens,
                          int32_t heads, int32_t head_dim);
 ifx_status ifx_kv_destroy(ifx_kv* kv);
@@ -114,8 +122,9 @@ ifx_status ifx_ln_modulate(const void* x, void* out, const void* ln_weight, cons
 typedef enum ifx_epilogue {
     IFX_EPI_BIAS = 0,          /* out = bf16(acc + bias)                                  nn.Linear            */
     IFX_EPI_BIAS_GELU = 1,     /* out = bf16(gelu_tanh(bf16(acc + bias)))                 ffn[0:2]  :377-379   */
-    IFX_EPI_BIAS_GATE_RES = 2  /* out = bf16(res + bf16(bf16(acc + bias) * gate[f]))      :444, :455-456;      */
+    IFX_EPI_BIAS_GATE_RES = 2, /* out = bf16(res + bf16(bf16(acc + bias) * gate[f]))      :444, :455-456;      */
                                /* gate == NULL -> out = bf16(res + bf16(acc + bias))      cross-attn  :448     */
+    IFX_EPI_BIAS_GELU_ERF = 3  /* out = bf16(gelu_erf(bf16(acc + bias)))   MAGI CustomMLP, dit_module.py:551   */
 } ifx_epilogue;
 
 /* out[M,N] = epilogue(A[M,K] @ W[N,K]^T): tcgen05 BF16 MMA, FP32 accumulation in TMEM, TMA-fed pipeline.
@@ -219,6 +228,49 @@ ifx_status ifx_attention_combine(const void* workspace, int32_t pieces_per_item,
 /* Same, keys/values taken from the valid prefix of a paged cache (rows [0, local_end)). */
 ifx_status ifx_attention_kv(const void* q, int64_t ldq, const ifx_kv* kv, void* out, int64_t ldo, int64_t q_rows,
                             float softmax_scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * MAGI-1 transformer layer row kernels (inferix/models/magi/dit/dit_module.py).  head_dim must be 128.
+ * ------------------------------------------------------------------------------------------------------------ */
+
+/* One pass over the fused projection qkvx [rows, ld] = q | k | v | qx (q, qx: q_heads*128 columns; k, v: kv_heads*128):
+ *   q, k : .float() -> per-head LayerNorm with fp32 affine (FusedLayerNorm, :358-360) -> rotary on dims
+ *          [0, 2*rotary_half) pairing j with j + rotary_half (flash_attn apply_rotary_emb, non-interleaved) -> bf16
+ *          (get_q / get_k, :902-934); q -> q_out, k -> k_dst
+ *   v    : raw copy -> v_dst (get_v, :936-938)
+ *   qx   : per-head LayerNorm with bf16 affine -> qx_out (get_xqkv, :954-958)
+ * rope [rows, ld_rope] fp32 = sin[rotary_half] | cos[rotary_half] per token (rotary_pos_emb.tensor_split, :1097).
+ * k_dst / v_dst are row pointers into the layer's KV rows (ld_kv elements apart): the concatenation of key and value in
+ * get_kv (:940-945) and the cache `set` of magi_kv_cache_manager.py:138-146 become this one write.
+ * Head groups (Ulysses context parallel, distributed/parallelism/context_parallel.py:382-402): q head h goes to
+ * q_out + (h / q_group_heads) * q_group_stride + row * ld_q + (h % q_group_heads) * 128 (k / v likewise), which is
+ * the "(cp seq) hn hd" all-to-all send layout; pass q_group_heads = q_heads, kv_group_heads = kv_heads and zero
+ * strides for the plain token-major layout. */
+ifx_status ifx_magi_qkv_post(const void* qkvx, int64_t ld, int64_t rows, int32_t q_heads, int32_t kv_heads,
+                             int32_t head_dim, const float* q_ln_w, const float* q_ln_b, const float* k_ln_w,
+                             const float* k_ln_b, const void* qx_ln_w, const void* qx_ln_b, const float* rope,
+                             int64_t ld_rope, int32_t rotary_half, float eps, void* q_out, int64_t ld_q,
+                             int32_t q_group_heads, int64_t q_group_stride, void* k_dst, void* v_dst, int64_t ld_kv,
+                             int32_t kv_group_heads, int64_t kv_group_stride, void* qx_out, int64_t ld_qx,
+                             void* stream);
+
+/* Per-head LayerNorm (bf16 in / affine / out, fp32 statistics) on [rows, heads, 128]: k_layernorm_xattn on the caption
+ * keys (dit_module.py:968).  May run in place. */
+ifx_status ifx_head_layernorm(const void* x, int64_t ldx, void* out, int64_t ldo, int64_t rows, int32_t heads,
+                              int32_t head_dim, const void* weight, const void* bias, float eps, void* stream);
+
+/* bias_modulate_add (dit_module.py:295-313): out[r] = bf16( LN_fp32( x[r] * gate[row_map[r]] ) * norm_w + norm_b +
+ * residual[r] ), i.e. range_mod_triton (:205-292) + fp32 FusedLayerNorm + residual add in one pass.
+ * gate bf16 [num_gates, cols] (softcapped AdaModulateLayer output half), row_map int32 [rows] on the device
+ * (condition_map), norm_w / norm_b fp32 [cols].  out may alias x or residual. */
+ifx_status ifx_gate_norm_residual(const void* x, int64_t ldx, const void* gate, int64_t gate_stride, int32_t num_gates,
+                                  const int32_t* row_map, const float* norm_w, const float* norm_b,
+                                  const void* residual, int64_t ldr, void* out, int64_t ldo, int64_t rows,
+                                  int32_t cols, float eps, void* stream);
+
+/* flashinfer.activation.silu_and_mul (dit_module.py:549): out[r, j] = bf16( silu(x[r, j]) * x[r, cols_out + j] ). */
+ifx_status ifx_silu_mul(const void* x, int64_t ldx, void* out, int64_t ldo, int64_t rows, int32_t cols_out,
+                        void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Whole DiT block: CausalWanAttentionBlock.forward  causal_model.py:384-484  in one call (13 launches).

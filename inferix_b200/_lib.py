@@ -18,7 +18,7 @@ LIB_PATH = _HERE / "lib" / "libinferix_b200.so"
 IFX_KV_MAX_PLAN_PAGES = 32
 
 IFX_OK, IFX_ERR_INVALID, IFX_ERR_BOUNDS, IFX_ERR_HANDLE, IFX_ERR_OOM, IFX_ERR_CUDA, IFX_ERR_UNSUPPORTED = range(7)
-EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_GATE_RES = 0, 1, 2
+EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_GATE_RES, EPI_BIAS_GELU_ERF = 0, 1, 2, 3
 
 
 class NativeLibraryError(RuntimeError):
@@ -91,6 +91,7 @@ SIGNATURES = {
     "ifx_kv_reset": (C.c_int, [_vp]),
     "ifx_kv_plan_append": (C.c_int, [_vp, _i64, _i64, _i64, _i32, C.POINTER(KvPlan)]),
     "ifx_kv_state": (C.c_int, [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i32), C.POINTER(_i32), _i32]),
+    "ifx_kv_map": (C.c_int, [_vp, _i64, C.POINTER(_vp), C.POINTER(_vp)]),
     "ifx_kv_export": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp]),
     "ifx_kv_import": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp]),
     "ifx_ln_modulate": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _i64, _f32, _vp]),
@@ -111,6 +112,12 @@ SIGNATURES = {
                                         _f32, _vp, _i64, _i32, _i32, _i32, _vp]),
     "ifx_attention_combine": (C.c_int, [_vp, _i32, _vp, _i64, _i64, _i32, _i32, _vp]),
     "ifx_attention_kv": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _i64, _f32, _vp]),
+    "ifx_magi_qkv_post": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32,
+                                    _vp, _i64, _i32, _i64, _vp, _vp, _i64, _i32, _i64, _vp, _i64, _vp]),
+    "ifx_head_layernorm": (C.c_int, [_vp, _i64, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _f32, _vp]),
+    "ifx_gate_norm_residual": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i32,
+                                         _f32, _vp]),
+    "ifx_silu_mul": (C.c_int, [_vp, _i64, _vp, _i64, _i64, _i32, _vp]),
     "ifx_wan_block_forward": (C.c_int, [C.POINTER(WanBlockWeights), C.POINTER(WanBlockIO), C.POINTER(KvPlan), _vp]),
 }
 

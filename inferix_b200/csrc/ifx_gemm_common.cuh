@@ -61,6 +61,10 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, const u
 #pragma unroll
             for (int e = 0; e < 8; ++e) val[e] = gelu_tanh_f(val[e]);
         }
+        if (kEpi == IFX_EPI_BIAS_GELU_ERF) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) val[e] = 0.5f * val[e] * (1.0f + erff(val[e] * 0.70710678118654752f));
+        }
         if (kEpi == IFX_EPI_BIAS_GATE_RES) {
             if (gate_row != nullptr) {
                 uint4 graw = __ldg(reinterpret_cast<const uint4*>(gate_row + col0 + v * 8));

@@ -69,6 +69,7 @@ struct KvImpl {
     std::vector<int32_t> table;      // logical page -> physical page, size = ceil(local_end / page_tokens)
     std::vector<int32_t> free_pages; // recycled pages, reused LIFO-last (FIFO order) before fresh ones
     int32_t next_fresh;              // physical pages [0, next_fresh) have been handed out at least once
+    bool rotated;                    // a plan_append has unlinked / relinked pages: logical order != physical order
 };
 // by-value page list handed to kernels (no device-side table, no host sync)
 struct PageList {

@@ -65,6 +65,7 @@ extern "C" ifx_status ifx_kv_create(ifx_kv** out, void* k_base, void* v_base, in
     kv->global_end = 0;
     kv->local_end = 0;
     kv->next_fresh = 0;
+    kv->rotated = false;
     *out = reinterpret_cast<ifx_kv*>(kv);
     return IFX_OK;
 }
@@ -85,6 +86,7 @@ extern "C" ifx_status ifx_kv_reset(ifx_kv* kv_) {
     kv->table.clear();
     kv->free_pages.clear();
     kv->next_fresh = 0;
+    kv->rotated = false;
     return IFX_OK;
 }
 
@@ -151,6 +153,7 @@ extern "C" ifx_status ifx_kv_plan_append(ifx_kv* kv_, int64_t current_start, int
         table.push_back(pg);
     }
     // commit
+    if (evicted > 0 || kv->table.size() > need_pages) kv->rotated = true;
     kv->table.swap(table);
     kv->free_pages.swap(free_pages);
     kv->next_fresh = next_fresh;
@@ -182,6 +185,31 @@ extern "C" ifx_status ifx_kv_state(const ifx_kv* kv_, int64_t* global_end, int64
         IFX_CHECK_ARG(table_cap >= static_cast<int32_t>(kv->table.size()), "ifx_kv_state: table_cap too small");
         std::copy(kv->table.begin(), kv->table.end(), table_out);
     }
+    return IFX_OK;
+}
+
+extern "C" ifx_status ifx_kv_map(ifx_kv* kv_, int64_t tokens, void** k_rows, void** v_rows) {
+    KvImpl* kv = kv_cast(kv_);
+    if (!kv) return set_error(IFX_ERR_HANDLE, "ifx_kv_map: bad kv handle");
+    IFX_CHECK_ARG(tokens >= 0, "ifx_kv_map: negative token count");
+    const int64_t pt = kv->page_tokens;
+    if (tokens > static_cast<int64_t>(kv->num_pages) * pt)
+        return set_error(IFX_ERR_BOUNDS, "ifx_kv_map: %lld tokens beyond the cache of %lld", (long long)tokens,
+                         (long long)(kv->num_pages * pt));
+    if (kv->rotated)
+        return set_error(IFX_ERR_UNSUPPORTED, "ifx_kv_map: the cache has been rotated by ifx_kv_plan_append; its "
+                                              "logical order is no longer the physical order");
+    const size_t need_pages = static_cast<size_t>((tokens + pt - 1) / pt);
+    while (kv->table.size() < need_pages) {
+        const int32_t pg = take_page(kv);
+        if (pg != static_cast<int32_t>(kv->table.size())) {
+            if (pg >= 0) kv->free_pages.insert(kv->free_pages.begin(), pg);
+            return set_error(IFX_ERR_UNSUPPORTED, "ifx_kv_map: page allocator is not in identity order");
+        }
+        kv->table.push_back(pg);
+    }
+    if (k_rows) *k_rows = kv->k_base;
+    if (v_rows) *v_rows = kv->v_base;
     return IFX_OK;
 }
 

@@ -61,6 +61,17 @@ class MagiKVCacheManager:
                                                 use_mla=False)})
         inference_params.kv_cache_manager.allocate_slots(inference_params.kv_cache_request, spec)
 
+    def native_store(self, inference_params, dtype=torch.bfloat16):
+        """The layer's native cache (allocated on first use, reference :104-112).  The MAGI cache is only ever written
+        in place (reference :110-146), so logical row i is physical row i: the native layer writes the new K / V rows
+        at [start, start + n) through `store.map_rows` and attends rows [0, start + n) directly — the reference's
+        get_range copy (:118-123) and torch.cat (:149) disappear."""
+        mgr, req = inference_params.kv_cache_manager, inference_params.kv_cache_request
+        if self.layer_name not in mgr.layers(req):
+            self.allocate_key_value_memory(inference_params, inference_params.max_sequence_length,
+                                           inference_params.max_batch_size, dtype)
+        return mgr.store(req, self.layer_name)
+
     def _full_adjust_key_and_value(self, inference_params, key_and_value: torch.Tensor, meta_args):
         """reference :76-151.  Returns (key, value), each [history + new, kv_heads, D]."""
         mgr, req = inference_params.kv_cache_manager, inference_params.kv_cache_request

@@ -11,12 +11,13 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import EPI_BIAS, EPI_BIAS_GATE_RES, EPI_BIAS_GELU, KvPlan, RopeGrid
+from ._lib import EPI_BIAS, EPI_BIAS_GATE_RES, EPI_BIAS_GELU, EPI_BIAS_GELU_ERF, KvPlan, RopeGrid
 
 __all__ = [
     "ln_modulate", "gemm", "rmsnorm", "quantize_fp8", "ln_modulate_fp8", "gemm_fp8", "attention", "attention_gqa", "attention_ranges", "attention_partial", "attention_combine",
     "attention_workspace_bytes", "qk_norm_rope_append", "PagedKV", "rope_table",
-    "EPI_BIAS", "EPI_BIAS_GELU", "EPI_BIAS_GATE_RES",
+    "EPI_BIAS", "EPI_BIAS_GELU", "EPI_BIAS_GATE_RES", "EPI_BIAS_GELU_ERF",
+    "magi_qkv_post", "head_layernorm", "gate_norm_residual", "silu_mul",
 ]
 
 
@@ -325,6 +326,12 @@ class PagedKV:
         old_pages = [pg for pg in table if pg not in set(new_pages)]
         return _coalesce_pages(old_pages, self.page_tokens), _coalesce_pages(new_pages, self.page_tokens)
 
+    def map_rows(self, tokens: int):
+        """Map logical tokens [0, tokens) (identity order; never-rotated caches only) and return the row views
+        (k, v), each [tokens, H*D], aliasing the cache memory."""
+        _lib.check(_lib.load().ifx_kv_map(self.handle, tokens, None, None))
+        return self.k[:tokens], self.v[:tokens]
+
     def export(self, start: int, length: int):
         """Tokens [start, start+length) in the reference's logical order -> (k, v) each [length, H*D]."""
         width = self.heads * self.head_dim
@@ -375,3 +382,93 @@ def qk_norm_rope_append(qkv, norm_q_w, norm_k_w, freqs_table, grid: RopeGrid, he
         q_out.stride(0), kv.handle if kv is not None else None, C.byref(plan) if plan is not None else None,
         _ptr(k_out), _ptr(v_out), rows, heads, head_dim, eps, _stream()))
     return q_out, k_out, v_out
+
+
+# ----------------------------------------------------------------------------- MAGI-1 layer row kernels
+def _f32_vec(t: torch.Tensor, n: int, name: str) -> torch.Tensor:
+    if not t.is_cuda or t.dtype != torch.float32 or t.numel() != n or not t.is_contiguous():
+        raise ValueError(f"{name}: expected a contiguous CUDA float32 vector of {n} elements")
+    return t
+
+
+def magi_qkv_post(qkvx, q_heads, kv_heads, q_ln, k_ln, qx_ln, rope, q_out, k_dst, v_dst, qx_out, *, eps=1e-6,
+                  groups=1):
+    """dit_module.py:902-958 in one pass over the fused projection qkvx [rows, (2*q_heads + 2*kv_heads)*128]
+    (q | k | v | qx).  q_ln / k_ln: (weight, bias) fp32 [128]; qx_ln: (weight, bias) bf16 [128]; rope fp32
+    [rows, 2*half] = sin | cos.
+    groups == 1: q_out [rows, q_heads*128]; k_dst / v_dst [rows, kv_heads*128] row views with a common stride
+    (normally rows of the layer's KV cache).
+    groups == cp > 1 (Ulysses send layout): q_out [cp, rows, q_heads/cp*128], k_dst / v_dst [cp, rows, kv_heads/cp*128],
+    contiguous."""
+    qkvx = _bf16_2d(qkvx, "qkvx")
+    rows = qkvx.shape[0]
+    d = 128
+    if qkvx.shape[1] != (2 * q_heads + 2 * kv_heads) * d:
+        raise ValueError("qkvx must be [rows, (2*q_heads + 2*kv_heads)*128]")
+    if rope.dtype != torch.float32 or not rope.is_cuda or rope.dim() != 2 or rope.shape[0] != rows or rope.stride(1) != 1:
+        raise ValueError("rope must be a CUDA float32 [rows, 2*half] tensor")
+    qx_out = _bf16_2d(qx_out, "qx_out")
+    if qx_out.shape != (rows, q_heads * d):
+        raise ValueError("qx_out must be [rows, q_heads*128]")
+    if q_heads % groups or kv_heads % groups:
+        raise ValueError("groups must divide q_heads and kv_heads")
+    qg, kg = q_heads // groups, kv_heads // groups
+    if groups == 1:
+        q_out, k_dst, v_dst = _bf16_2d(q_out, "q_out"), _bf16_2d(k_dst, "k_dst"), _bf16_2d(v_dst, "v_dst")
+        if k_dst.shape != (rows, kv_heads * d) or v_dst.shape != k_dst.shape or k_dst.stride(0) != v_dst.stride(0):
+            raise ValueError("k_dst / v_dst must be [rows, kv_heads*128] views with a common row stride")
+        if q_out.shape != (rows, q_heads * d):
+            raise ValueError("q_out must be [rows, q_heads*128]")
+        ld_q, ld_kv, qgs, kgs = q_out.stride(0), k_dst.stride(0), 0, 0
+    else:
+        for t, w, name in ((q_out, qg, "q_out"), (k_dst, kg, "k_dst"), (v_dst, kg, "v_dst")):
+            if (t.dtype != torch.bfloat16 or not t.is_cuda or t.shape != (groups, rows, w * d) or not t.is_contiguous()):
+                raise ValueError(f"{name}: expected a contiguous CUDA bf16 [{groups}, {rows}, {w * d}] tensor")
+        ld_q, ld_kv, qgs, kgs = qg * d, kg * d, rows * qg * d, rows * kg * d
+    _lib.check(_lib.load().ifx_magi_qkv_post(
+        qkvx.data_ptr(), qkvx.stride(0), rows, q_heads, kv_heads, d,
+        _f32_vec(q_ln[0], d, "q_layernorm.weight").data_ptr(), _f32_vec(q_ln[1], d, "q_layernorm.bias").data_ptr(),
+        _f32_vec(k_ln[0], d, "k_layernorm.weight").data_ptr(), _f32_vec(k_ln[1], d, "k_layernorm.bias").data_ptr(),
+        _bf16_vec(qx_ln[0], d, "q_layernorm_xattn.weight").data_ptr(),
+        _bf16_vec(qx_ln[1], d, "q_layernorm_xattn.bias").data_ptr(), rope.data_ptr(), rope.stride(0),
+        rope.shape[1] // 2, eps, q_out.data_ptr(), ld_q, qg, qgs, k_dst.data_ptr(), v_dst.data_ptr(), ld_kv, kg, kgs,
+        qx_out.data_ptr(), qx_out.stride(0), _stream()))
+
+
+def head_layernorm(x, heads, weight, bias, out=None, *, eps=1e-6):
+    """Per-head LayerNorm (bf16 affine) on x [rows, heads*128] (any row stride); in place when out is None."""
+    x = _bf16_2d(x, "x")
+    out = x if out is None else _bf16_2d(out, "out")
+    if x.shape[1] != heads * 128 or out.shape != x.shape:
+        raise ValueError("head_layernorm: x / out must be [rows, heads*128]")
+    _lib.check(_lib.load().ifx_head_layernorm(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), x.shape[0],
+                                              heads, 128, _bf16_vec(weight, 128, "weight").data_ptr(),
+                                              _bf16_vec(bias, 128, "bias").data_ptr(), eps, _stream()))
+    return out
+
+
+def gate_norm_residual(x, gate, row_map, norm_w, norm_b, residual, out=None, *, eps=1e-6):
+    """bias_modulate_add (dit_module.py:295-313): bf16(LN_fp32(x * gate[row_map]) * norm_w + norm_b + residual).
+    gate bf16 [ranges, C]; row_map int32 [rows] (condition_map); norm_w / norm_b fp32 [C]."""
+    x, gate, residual = _bf16_2d(x, "x"), _bf16_2d(gate, "gate"), _bf16_2d(residual, "residual")
+    rows, cols = x.shape
+    if gate.shape[1] != cols or residual.shape != x.shape:
+        raise ValueError("gate_norm_residual: gate must be [ranges, C] and residual [rows, C]")
+    if row_map.dtype != torch.int32 or not row_map.is_cuda or row_map.numel() != rows or not row_map.is_contiguous():
+        raise ValueError("row_map must be a contiguous CUDA int32 vector with one entry per row")
+    out = torch.empty_like(x) if out is None else _bf16_2d(out, "out")
+    _lib.check(_lib.load().ifx_gate_norm_residual(
+        x.data_ptr(), x.stride(0), gate.data_ptr(), gate.stride(0), gate.shape[0], row_map.data_ptr(),
+        _f32_vec(norm_w, cols, "norm weight").data_ptr(), _f32_vec(norm_b, cols, "norm bias").data_ptr(),
+        residual.data_ptr(), residual.stride(0), out.data_ptr(), out.stride(0), rows, cols, eps, _stream()))
+    return out
+
+
+def silu_mul(x, out=None):
+    """flashinfer silu_and_mul: x [rows, 2F] -> bf16(silu(x[:, :F]) * x[:, F:])."""
+    x = _bf16_2d(x, "x")
+    rows, two_f = x.shape
+    out = torch.empty((rows, two_f // 2), dtype=torch.bfloat16, device=x.device) if out is None else _bf16_2d(out, "out")
+    _lib.check(_lib.load().ifx_silu_mul(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), rows, two_f // 2,
+                                        _stream()))
+    return out

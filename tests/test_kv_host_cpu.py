@@ -126,3 +126,28 @@ def test_unaligned_append_is_rejected():
     with pytest.raises(NotImplementedError):
         kv.plan(2, 4, 0)
     kv.close()
+
+
+def test_kv_map_identity_rows_and_refusals():
+    """ifx_kv_map (MAGI caches, magi_kv_cache_manager.py:110-146: written in place, never evicted): maps logical
+    tokens identity-wise, returns the row base pointers, refuses out-of-range requests and rotated tables."""
+    kv = HostKV(64, 1)
+    k, v = ctypes.c_void_p(), ctypes.c_void_p()
+    _lib.check(kv.lib.ifx_kv_map(kv.h, 40, ctypes.byref(k), ctypes.byref(v)))
+    assert (k.value, v.value) == (0x10000, 0x20000)
+    assert kv.state()[2] == list(range(40))
+    _lib.check(kv.lib.ifx_kv_map(kv.h, 16, None, None))            # shrinking request: table keeps its 40 entries
+    assert kv.state()[2] == list(range(40))
+    _lib.check(kv.lib.ifx_kv_map(kv.h, 64, None, None))
+    assert kv.state()[2] == list(range(64))
+    with pytest.raises(IndexError):
+        _lib.check(kv.lib.ifx_kv_map(kv.h, 65, None, None))
+    kv.close()
+    rolled = HostKV(4, 8)                                          # windowed cache: third block evicts -> rotated
+    for b in range(3):
+        rolled.plan(b * 16, 16, 0)
+    with pytest.raises(NotImplementedError):
+        _lib.check(rolled.lib.ifx_kv_map(rolled.h, 8, None, None))
+    _lib.check(rolled.lib.ifx_kv_reset(rolled.h))                  # reset clears the rotation
+    _lib.check(rolled.lib.ifx_kv_map(rolled.h, 8, None, None))
+    rolled.close()

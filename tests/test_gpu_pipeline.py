@@ -227,3 +227,41 @@ def test_wrong_dtype_and_device_fail_loudly():
         KVCacheManager("cpu")
     with pytest.raises(NotImplementedError):
         CausalWanModel(dim=512, num_heads=8)                                         # head_dim 64
+
+
+def test_long_horizon_256_blocks_eviction_steady_state():
+    """BASELINE config 5 (long-horizon eviction stress) at tiny widths on one GPU: 256 blocks = 768 latent frames
+    (< the 1024-row RoPE table) through an 8-block window with one sink frame and the shipped 4-step schedule.
+    Steady state from block 8 on: index trace == the oracle's arithmetic (causal_model.py:277-300) for all 2560
+    forwards, allocated memory does not grow, per-block time stays flat, latents stay finite."""
+    nblk, fpb, fs, window, sink = 256, 3, 64, 24, 1
+    from inferix_b200.synthetic import TINY
+    pipe = build(dict(TINY), window, sink, [1000, 750, 500, 250], 5.0)
+    g = torch.Generator().manual_seed(21)
+    noise = torch.randn(1, nblk * fpb, 16, 16, 16, generator=g).bfloat16().to(DEV)
+    ctx = torch.randn(1, 20, TINY["text_dim"], generator=g).bfloat16().to(DEV)
+    trace, mem = [], []
+    blk0 = pipe.generator.model.blocks[0]
+    hook = blk0.register_forward_hook(lambda m, i, o: trace.append(pipe.kv_cache_meta[0]["_ifx_plan"]))
+    out = pipe.inference(noise=noise, text_prompts=ctx, kv_cache_manager=KVCacheManager(DEV),
+                         kv_cache_requests=[KVCacheRequest("long")], decode_mode=DecodeMode.NO_DECODE, profile=True,
+                         free_cache_before_vae=False,
+                         block_callback=lambda lat, i: mem.append(torch.cuda.memory_allocated()))
+    hook.remove()
+    assert out.shape == noise.shape and bool(torch.isfinite(out.float()).all())
+    # --- indices, bit-exact against the oracle's restatement, every forward of every block
+    want, ge, le = [], 0, 0
+    for b in range(nblk):
+        for _ in range(5):                                                     # 4 noisy + 1 clean forward
+            ls, le, ge, ev = wo.plan_indices(window * fs, ge, le, b * fpb * fs, fpb * fs, sink * fs, True)
+            want.append((ls, le, ge, ev))
+    assert trace == want
+    assert trace[-1][1] == window * fs and trace[-1][2] == nblk * fpb * fs
+    assert sum(t[3] for t in trace) == (nblk - 8) * fpb * fs                   # every block past the window evicts once
+    # --- no growth in allocated memory once the window is full
+    assert max(mem[8:]) == min(mem[8:]), (min(mem[8:]), max(mem[8:]))
+    # --- flat per-block time in the steady state (median of the last 64 blocks vs blocks 8..72)
+    t = pipe.last_block_times_ms
+    early, late = sorted(t[8:72])[32], sorted(t[-64:])[32]
+    print(f"long horizon: block time early {early:.2f} ms, late {late:.2f} ms")
+    assert late <= 1.25 * early

@@ -175,6 +175,7 @@ class CausVidInferencePipeline(torch.nn.Module):
         self.generator.model._meta = None
         self.is_kv_cache_initialized = False
 
+    @torch.no_grad()   # inference only; the reference disables autograd globally (self_forcing/pipeline.py:62)
     def inference(self, noise: torch.Tensor, text_prompts, start_latents: Optional[torch.Tensor],
                   return_latents: bool = True, kv_cache_manager: Optional[KVCacheManager] = None,
                   kv_cache_requests: Optional[List] = None, vae_chunk_size: Optional[int] = None,

@@ -103,6 +103,7 @@ class CausalInferencePipeline(torch.nn.Module):
         self.last_block_times_ms: List[float] = []
 
     # ------------------------------------------------------------------------------------------ inference
+    @torch.no_grad()   # inference only; the reference disables autograd globally (self_forcing/pipeline.py:62)
     def inference(self, noise: torch.Tensor, text_prompts, kv_cache_manager: KVCacheManager,
                   kv_cache_requests: List[KVCacheRequest], initial_latent: Optional[torch.Tensor] = None,
                   return_latents: bool = False, profile: bool = False, low_memory: bool = False,
@@ -197,6 +198,7 @@ class CausalInferencePipeline(torch.nn.Module):
             video = (video * 0.5 + 0.5).clamp(0, 1)
         return (video, output) if return_latents else video
 
+    @torch.no_grad()   # inference only; the reference disables autograd globally (self_forcing/pipeline.py:62)
     def denoise_block(self, noisy_input: torch.Tensor, current_start_frame: int, common: dict) -> torch.Tensor:
         """One unit of the metric: T noisy forwards with re-noising in between (:276-310), then the clean re-run that
         rewrites the block's K/V (:352-361).  noisy_input [B, n, C, H, W] -> denoised x0 of the block."""

@@ -350,8 +350,14 @@ def main():
         kv_hbm = {}
         if app_n:
             app_bytes = 6.0 * S_local * C * 2          # read q|k|v rows, write q, roped-k and v (into the cache pages)
+            if world > 1 and getattr(pipe, "_peer_group", None) is not None:
+                app_bytes = (4.0 + 2.0 * world) * S_local * C * 2   # k and v rows stored into every rank's cache
             kv_hbm["append_norm_rope"] = {"gbs": app_bytes / (app_ms / app_n * 1e-3) / 1e9, "bytes_per_launch": app_bytes,
                                           "avg_launch_us": 1e3 * app_ms / app_n, "launches_timed": app_n}
+        wait_ms, wait_n = _lib.prof_read("peer_wait_kernel")
+        if wait_n:
+            kv_hbm["peer_wait"] = {"avg_launch_us": 1e3 * wait_ms / wait_n, "launches_timed": wait_n,
+                                   "note": "stream-ordered wait for all ranks' K/V stores before attention"}
         peak_tf, peak_bw, src = measured_peaks()
         roofline = None
         if attn_n:
@@ -392,6 +398,9 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": noise_host[0].numel() * 2,
                     "d2h_bytes_per_step": out_host.numel() * 2},
             "gpu_launches": int(launches),
+            "sp_exchange": (None if world == 1 else
+                            "peer_memory (K/V stored into every rank's cache by the norm+RoPE kernel over NVLink)"
+                            if getattr(pipe, "_peer_group", None) is not None else "nccl_all_gather"),
             "roofline": roofline,
             "kv_hbm": kv_hbm,
         }

@@ -180,6 +180,43 @@ ifx_status ifx_qk_norm_rope_append(const void* qkv, int64_t ld_qkv, const void* 
                                    void* v_dst, int64_t rows, int32_t heads, int32_t head_dim, float eps,
                                    void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Sequence parallel over peer memory (one NVSwitch box, <= 8 ranks).  Replaces the per-layer exchange of the
+ * reference (ring P2P + LSE merges, models/attention/distributed.py:564-712) and this library's own NCCL variant
+ * (staging -> all-gather -> ifx_kv_append_sp): the fused norm + RoPE kernel stores this rank's new K / V rows into the
+ * same cache rows of EVERY rank's replicated cache with 16-byte P2P stores over NVLink and then publishes an epoch
+ * number in every rank's flag array; ifx_peer_wait makes the attention that follows wait (on the stream) until all
+ * ranks have published.  Write-after-read safety: a rank reaches the next write of a layer's rows only after passing a
+ * later wait (next layer, or the head all-gather), which every rank signals after its attention of this layer.
+ * ------------------------------------------------------------------------------------------------------------ */
+#define IFX_MAX_PEERS 8
+#define IFX_PEER_HANDLE_BYTES 64
+
+typedef struct ifx_peer_dst {
+    int32_t world, rank;
+    void* k[IFX_MAX_PEERS];          /* this layer's cache K rows on every rank (entry `rank` = the local cache) */
+    void* v[IFX_MAX_PEERS];
+    int64_t* flags[IFX_MAX_PEERS];   /* every rank's flag array, int64[world]; this rank writes element `rank` */
+    int64_t epoch;                   /* > 0, increases by one per call, identical on all ranks */
+} ifx_peer_dst;
+
+/* CUDA IPC: handle of the allocation containing ptr (+ ptr's offset inside it), to be shipped to the other processes
+ * of the box; ifx_peer_open maps a received handle and returns the allocation's base in this process. */
+ifx_status ifx_peer_export(const void* ptr, void* handle /* IFX_PEER_HANDLE_BYTES */, int64_t* offset, uint64_t* base,
+                           uint64_t* size);
+ifx_status ifx_peer_open(const void* handle, void** base);
+ifx_status ifx_peer_close(void* base);
+
+/* ifx_qk_norm_rope_append for rank `peers->rank` of a sequence-parallel group: rows = frames * hw_count local tokens,
+ * plan = the (identical on every rank) plan of the whole block (rows * world tokens). */
+ifx_status ifx_qk_norm_rope_append_peers(const void* qkv, int64_t ld_qkv, const void* norm_q_weight,
+                                         const void* norm_k_weight, const double* freqs, const ifx_rope_grid* grid,
+                                         void* q_out, int64_t ld_q, ifx_kv* kv, const ifx_kv_plan* plan,
+                                         const ifx_peer_dst* peers, int64_t rows, int32_t heads, int32_t head_dim,
+                                         float eps, void* stream);
+/* Stream-ordered wait until flags[s] >= epoch for every s < world; traps after timeout_ms instead of hanging. */
+ifx_status ifx_peer_wait(const int64_t* flags, int32_t world, int64_t epoch, int32_t timeout_ms, void* stream);
+
 /* Copy already-normalised K / V rows (e.g. all-gathered from peers) into the pages named by `plan`. */
 ifx_status ifx_kv_append(ifx_kv* kv, const ifx_kv_plan* plan, const void* k_src, const void* v_src, int64_t ld_src,
                          int64_t rows, void* stream);

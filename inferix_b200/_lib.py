@@ -48,6 +48,19 @@ class RopeGrid(C.Structure):
     ]
 
 
+IFX_MAX_PEERS = 8
+IFX_PEER_HANDLE_BYTES = 64
+
+
+class PeerDst(C.Structure):
+    _fields_ = [
+        ("world", C.c_int32), ("rank", C.c_int32),
+        ("k", C.c_void_p * IFX_MAX_PEERS), ("v", C.c_void_p * IFX_MAX_PEERS),
+        ("flags", C.c_void_p * IFX_MAX_PEERS),
+        ("epoch", C.c_int64),
+    ]
+
+
 class WanBlockWeights(C.Structure):
     _fields_ = [
         ("dim", C.c_int32), ("ffn_dim", C.c_int32), ("heads", C.c_int32), ("head_dim", C.c_int32),
@@ -103,6 +116,12 @@ SIGNATURES = {
                                 _i64, _vp]),
     "ifx_qk_norm_rope_append": (C.c_int, [_vp, _i64, _vp, _vp, _vp, C.POINTER(RopeGrid), _vp, _i64, _vp,
                                           C.POINTER(KvPlan), _vp, _vp, _i64, _i32, _i32, _f32, _vp]),
+    "ifx_peer_export": (C.c_int, [_vp, _vp, C.POINTER(_i64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "ifx_peer_open": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "ifx_peer_close": (C.c_int, [_vp]),
+    "ifx_qk_norm_rope_append_peers": (C.c_int, [_vp, _i64, _vp, _vp, _vp, C.POINTER(RopeGrid), _vp, _i64, _vp,
+                                                C.POINTER(KvPlan), C.POINTER(PeerDst), _i64, _i32, _i32, _f32, _vp]),
+    "ifx_peer_wait": (C.c_int, [_vp, _i32, _i64, _i32, _vp]),
     "ifx_kv_append": (C.c_int, [_vp, C.POINTER(KvPlan), _vp, _vp, _i64, _i64, _vp]),
     "ifx_kv_append_sp": (C.c_int, [_vp, C.POINTER(KvPlan), _vp, _vp, _i64, _i32, _i32, _i32, _vp]),
     "ifx_rmsnorm": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _i64, _i32, _f32, _vp]),

@@ -149,6 +149,9 @@ class CausVidInferencePipeline(torch.nn.Module):
                                           sequence_length=self.kv_cache_frames * self.frame_seq_length, dtype=dtype,
                                           ulysses_size=self.parallel_config.ulysses_size,
                                           ring_size=self.parallel_config.ring_size, page_tokens=self.frame_seq_length)
+        from . import peer
+        self._peer_group = peer.setup_for_pipeline(self.generator.model, kv_cache_manager, kv_cache_requests,
+                                                   self.parallel_config)
 
     def _initialize_crossattn_cache(self, kv_cache_manager, kv_cache_requests, dtype):
         for layer_idx in range(self.num_transformer_blocks):
@@ -168,6 +171,10 @@ class CausVidInferencePipeline(torch.nn.Module):
         self.generator.model._meta = None
 
     def clear_cache(self, kv_cache_manager, kv_cache_requests):
+        if getattr(self, "_peer_group", None) is not None:      # unmap the other ranks' caches before anyone frees
+            self._peer_group.release()
+            torch.distributed.barrier(group=self.parallel_config.group)
+            self._peer_group = None
         for blk in self.generator.model.blocks:
             for req in kv_cache_requests:
                 blk.kv_cache_manager.clear_cache(kv_cache_manager=kv_cache_manager, kv_cache_request=req)

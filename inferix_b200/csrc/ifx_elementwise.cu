@@ -225,7 +225,25 @@ struct NormRopeParams {
     PageList pl;
     int32_t C, heads, head_dim;
     float eps;
+    // paged == 2 (sequence parallel over peer memory): this rank owns hw indices [hw_offset, hw_offset + hw_count) of
+    // every frame of the block; its K / V rows are stored into the SAME cache row of every rank's replicated cache
+    // (P2P stores over NVLink), then the last CTA publishes `epoch` in every rank's flag array.
+    int32_t sp_world, sp_rank;
+    __nv_bfloat16* peer_k[IFX_MAX_PEERS];
+    __nv_bfloat16* peer_v[IFX_MAX_PEERS];
+    long long* peer_flags[IFX_MAX_PEERS];
+    long long epoch;
+    unsigned int* done_counter;
 };
+
+__device__ __forceinline__ void st_release_sys(long long* p, long long v) {
+    asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ long long ld_acquire_sys(const long long* p) {
+    long long v;
+    asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
 
 // pair index inside a head -> which RoPE axis it rotates with (causal_model.py:37: split [c-2(c/3), c/3, c/3])
 __device__ __forceinline__ int rope_pos(int pair, int half, int t_pos, int h_pos, int w_pos) {
@@ -246,9 +264,14 @@ qk_norm_rope_append_kernel(const NormRopeParams p) {
 
     // destination row in the cache
     int64_t drow;
-    if (p.paged) {
+    if (p.paged == 1) {
         const int pg = static_cast<int>(t / p.page_tokens);
         drow = static_cast<int64_t>(p.pl.pages[pg]) * p.page_tokens + (t % p.page_tokens);
+    } else if (p.paged == 2) {
+        // token index inside the block in single-process order: (frame, rank, hw)  (causal_model.py:1016-1021)
+        const int64_t fs_full = static_cast<int64_t>(p.sp_world) * p.grid.hw_count;
+        const int64_t tb = (t / p.grid.hw_count) * fs_full + p.grid.hw_offset + (t % p.grid.hw_count);
+        drow = static_cast<int64_t>(p.pl.pages[tb / p.page_tokens]) * p.page_tokens + (tb % p.page_tokens);
     } else {
         drow = t;
     }
@@ -281,7 +304,15 @@ qk_norm_rope_append_kernel(const NormRopeParams p) {
                 ss[1] += k[i][e] * k[i][e];
             }
             // V is appended untouched
-            reinterpret_cast<uint4*>(p.v_dst + drow * C)[vi] = vr[vi];
+            if (p.paged == 2) {
+                const uint4 vv = vr[vi];
+                for (int d = 0; d < p.sp_world; ++d) {
+                    const int dst = (p.sp_rank + 1 + d) % p.sp_world;      // start at the neighbour: spread the links
+                    reinterpret_cast<uint4*>(p.peer_v[dst] + drow * C)[vi] = vv;
+                }
+            } else {
+                reinterpret_cast<uint4*>(p.v_dst + drow * C)[vi] = vr[vi];
+            }
         }
     }
     block_sum<2>(ss, scratch);
@@ -312,8 +343,47 @@ qk_norm_rope_append_kernel(const NormRopeParams p) {
                 ko[2 * e + 1] = static_cast<float>(ka * cs.y + kb * cs.x);
             }
             reinterpret_cast<uint4*>(p.q_out + t * p.ld_q)[vi] = pack8(qo);
-            reinterpret_cast<uint4*>(p.k_dst + drow * C)[vi] = pack8(ko);
+            if (p.paged == 2) {
+                const uint4 kk = pack8(ko);
+                for (int d = 0; d < p.sp_world; ++d) {
+                    const int dst = (p.sp_rank + 1 + d) % p.sp_world;
+                    reinterpret_cast<uint4*>(p.peer_k[dst] + drow * C)[vi] = kk;
+                }
+            } else {
+                reinterpret_cast<uint4*>(p.k_dst + drow * C)[vi] = pack8(ko);
+            }
         }
+    }
+    if (p.paged == 2) {
+        // every thread's peer stores are ordered before the CTA's arrival; the last CTA to arrive publishes the epoch
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned int prev = atomicAdd(p.done_counter, 1u);
+            if (prev == gridDim.x - 1) {
+                *p.done_counter = 0;                       // next launch on this stream starts from zero
+                __threadfence_system();
+                for (int d = 0; d < p.sp_world; ++d) st_release_sys(p.peer_flags[d] + p.sp_rank, p.epoch);
+            }
+        }
+    }
+}
+
+// Spin until every rank has published `epoch` in this rank's flag array (one lane per source rank).  Bounded: a rank
+// that never arrives traps the kernel after timeout_ns instead of hanging the GPU.
+__global__ void peer_wait_kernel(const long long* flags, int world, long long epoch, unsigned long long timeout_ns) {
+    const int s = threadIdx.x;
+    if (s >= world) return;
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+    while (ld_acquire_sys(flags + s) < epoch) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+        if (now - t0 > timeout_ns) {
+            printf("ifx peer_wait: rank %d did not publish epoch %lld (have %lld)\n", s, epoch, ld_acquire_sys(flags + s));
+            __trap();
+        }
+        __nanosleep(64);
     }
 }
 
@@ -506,11 +576,11 @@ extern "C" ifx_status ifx_rmsnorm(const void* x, int64_t ldx, const void* weight
     return IFX_OK;
 }
 
-extern "C" ifx_status ifx_qk_norm_rope_append(const void* qkv, int64_t ld_qkv, const void* norm_q_weight,
-                                              const void* norm_k_weight, const double* freqs,
-                                              const ifx_rope_grid* grid, void* q_out, int64_t ld_q, ifx_kv* kv_,
-                                              const ifx_kv_plan* plan, void* k_dst, void* v_dst, int64_t rows,
-                                              int32_t heads, int32_t head_dim, float eps, void* stream) {
+static ifx_status norm_rope_append_entry(const void* qkv, int64_t ld_qkv, const void* norm_q_weight,
+                                         const void* norm_k_weight, const double* freqs, const ifx_rope_grid* grid,
+                                         void* q_out, int64_t ld_q, ifx_kv* kv_, const ifx_kv_plan* plan, void* k_dst,
+                                         void* v_dst, const ifx_peer_dst* peers, int64_t rows, int32_t heads,
+                                         int32_t head_dim, float eps, void* stream) {
     IFX_CHECK_ARG(qkv && norm_q_weight && norm_k_weight && freqs && grid && q_out, "ifx_qk_norm_rope_append: null");
     const int C = heads * head_dim;
     IFX_CHECK_ARG(rows > 0 && C % 8 == 0 && C <= kRowThreads * kMaxVecPerThread * 8 && head_dim % 8 == 0 && head_dim <= 256,
@@ -523,7 +593,7 @@ extern "C" ifx_status ifx_qk_norm_rope_append(const void* qkv, int64_t ld_qkv, c
     IFX_CHECK_ARG(grid->start_frame >= 0 && grid->start_frame + grid->frames <= 1024 && grid->height <= 1024 &&
                       grid->width <= 1024,
                   "ifx_qk_norm_rope_append: RoPE table has 1024 positions");
-    NormRopeParams p;
+    NormRopeParams p = {};
     p.qkv = static_cast<const __nv_bfloat16*>(qkv);
     p.ld_qkv = ld_qkv;
     p.wq = static_cast<const __nv_bfloat16*>(norm_q_weight);
@@ -541,13 +611,39 @@ extern "C" ifx_status ifx_qk_norm_rope_append(const void* qkv, int64_t ld_qkv, c
         if (!kv) return set_error(IFX_ERR_HANDLE, "ifx_qk_norm_rope_append: bad kv handle");
         IFX_CHECK_ARG(plan != nullptr, "ifx_qk_norm_rope_append: plan required with kv");
         IFX_CHECK_ARG(kv->heads == heads && kv->head_dim == head_dim, "ifx_qk_norm_rope_append: kv shape mismatch");
-        IFX_CHECK_ARG(plan->local_end - plan->local_start == rows, "ifx_qk_norm_rope_append: plan covers %lld rows",
+        const int64_t plan_rows = peers ? rows * peers->world : rows;
+        IFX_CHECK_ARG(plan->local_end - plan->local_start == plan_rows, "ifx_qk_norm_rope_append: plan covers %lld rows",
                       (long long)(plan->local_end - plan->local_start));
-        IFX_CHECK_ARG((int64_t)plan->num_pages * kv->page_tokens == rows && plan->first_offset == 0,
+        IFX_CHECK_ARG((int64_t)plan->num_pages * kv->page_tokens == plan_rows && plan->first_offset == 0,
                       "ifx_qk_norm_rope_append: append must be page aligned");
         p.k_dst = static_cast<__nv_bfloat16*>(kv->k_base);
         p.v_dst = static_cast<__nv_bfloat16*>(kv->v_base);
         p.paged = 1;
+        if (peers) {
+            static unsigned int* g_done = nullptr;       // one arrival counter per process (launches are stream-ordered)
+            if (!g_done) {
+                IFX_CUDA_OK(cudaMalloc(&g_done, sizeof(unsigned int)));
+                IFX_CUDA_OK(cudaMemset(g_done, 0, sizeof(unsigned int)));
+            }
+            IFX_CHECK_ARG(peers->world >= 1 && peers->world <= IFX_MAX_PEERS && peers->rank >= 0 &&
+                              peers->rank < peers->world && peers->epoch > 0,
+                          "ifx_qk_norm_rope_append_peers: bad world / rank / epoch");
+            IFX_CHECK_ARG(grid->hw_offset == peers->rank * grid->hw_count,
+                          "ifx_qk_norm_rope_append_peers: grid.hw_offset must be rank * hw_count");
+            p.paged = 2;
+            p.sp_world = peers->world;
+            p.sp_rank = peers->rank;
+            p.epoch = peers->epoch;
+            p.done_counter = g_done;
+            for (int d = 0; d < peers->world; ++d) {
+                IFX_CHECK_ARG(peers->k[d] && peers->v[d] && peers->flags[d], "ifx_qk_norm_rope_append_peers: null peer %d", d);
+                p.peer_k[d] = static_cast<__nv_bfloat16*>(peers->k[d]);
+                p.peer_v[d] = static_cast<__nv_bfloat16*>(peers->v[d]);
+                p.peer_flags[d] = reinterpret_cast<long long*>(peers->flags[d]);
+            }
+            IFX_CHECK_ARG(peers->k[peers->rank] == kv->k_base && peers->v[peers->rank] == kv->v_base,
+                          "ifx_qk_norm_rope_append_peers: own entry must be this rank's cache");
+        }
         p.page_tokens = kv->page_tokens;
         p.pl.n = plan->num_pages;
         for (int i = 0; i < plan->num_pages; ++i) p.pl.pages[i] = plan->pages[i];
@@ -560,10 +656,41 @@ extern "C" ifx_status ifx_qk_norm_rope_append(const void* qkv, int64_t ld_qkv, c
         p.pl.n = 0;
     }
     {
-        ProfScope prof("qk_norm_rope_append_kernel", static_cast<cudaStream_t>(stream));
+        ProfScope prof(peers ? "qk_norm_rope_append_kernel<peers>" : "qk_norm_rope_append_kernel",
+                       static_cast<cudaStream_t>(stream));
         qk_norm_rope_append_kernel<<<static_cast<unsigned>(rows), row_threads(C), 0, static_cast<cudaStream_t>(stream)>>>(p);
     }
     IFX_LAUNCH_OK("qk_norm_rope_append_kernel");
+    return IFX_OK;
+}
+
+extern "C" ifx_status ifx_qk_norm_rope_append(const void* qkv, int64_t ld_qkv, const void* norm_q_weight,
+                                              const void* norm_k_weight, const double* freqs,
+                                              const ifx_rope_grid* grid, void* q_out, int64_t ld_q, ifx_kv* kv_,
+                                              const ifx_kv_plan* plan, void* k_dst, void* v_dst, int64_t rows,
+                                              int32_t heads, int32_t head_dim, float eps, void* stream) {
+    return norm_rope_append_entry(qkv, ld_qkv, norm_q_weight, norm_k_weight, freqs, grid, q_out, ld_q, kv_, plan, k_dst,
+                                  v_dst, nullptr, rows, heads, head_dim, eps, stream);
+}
+
+extern "C" ifx_status ifx_qk_norm_rope_append_peers(const void* qkv, int64_t ld_qkv, const void* norm_q_weight,
+                                                    const void* norm_k_weight, const double* freqs,
+                                                    const ifx_rope_grid* grid, void* q_out, int64_t ld_q, ifx_kv* kv_,
+                                                    const ifx_kv_plan* plan, const ifx_peer_dst* peers, int64_t rows,
+                                                    int32_t heads, int32_t head_dim, float eps, void* stream) {
+    IFX_CHECK_ARG(kv_ && plan && peers, "ifx_qk_norm_rope_append_peers: kv, plan and peers are required");
+    return norm_rope_append_entry(qkv, ld_qkv, norm_q_weight, norm_k_weight, freqs, grid, q_out, ld_q, kv_, plan, nullptr,
+                                  nullptr, peers, rows, heads, head_dim, eps, stream);
+}
+
+extern "C" ifx_status ifx_peer_wait(const int64_t* flags, int32_t world, int64_t epoch, int32_t timeout_ms, void* stream) {
+    IFX_CHECK_ARG(flags && world >= 1 && world <= IFX_MAX_PEERS && epoch > 0 && timeout_ms > 0, "ifx_peer_wait: bad argument");
+    {
+        ProfScope prof("peer_wait_kernel", static_cast<cudaStream_t>(stream));
+        peer_wait_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const long long*>(flags), world,
+                                                                         epoch, static_cast<unsigned long long>(timeout_ms) * 1000000ull);
+    }
+    IFX_LAUNCH_OK("peer_wait_kernel");
     return IFX_OK;
 }
 

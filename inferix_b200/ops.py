@@ -17,7 +17,7 @@ __all__ = [
     "ln_modulate", "gemm", "rmsnorm", "quantize_fp8", "ln_modulate_fp8", "gemm_fp8", "attention", "attention_gqa", "attention_ranges", "attention_partial", "attention_combine",
     "attention_workspace_bytes", "qk_norm_rope_append", "PagedKV", "rope_table",
     "EPI_BIAS", "EPI_BIAS_GELU", "EPI_BIAS_GATE_RES", "EPI_BIAS_GELU_ERF",
-    "magi_qkv_post", "head_layernorm", "gate_norm_residual", "silu_mul",
+    "qk_norm_rope_append_peers", "magi_qkv_post", "head_layernorm", "gate_norm_residual", "silu_mul",
 ]
 
 
@@ -382,6 +382,26 @@ def qk_norm_rope_append(qkv, norm_q_w, norm_k_w, freqs_table, grid: RopeGrid, he
         q_out.stride(0), kv.handle if kv is not None else None, C.byref(plan) if plan is not None else None,
         _ptr(k_out), _ptr(v_out), rows, heads, head_dim, eps, _stream()))
     return q_out, k_out, v_out
+
+
+def qk_norm_rope_append_peers(qkv, norm_q_w, norm_k_w, freqs_table, grid: RopeGrid, heads, head_dim, kv: "PagedKV",
+                              plan: KvPlan, peers, *, q_out=None, eps=1e-6):
+    """Sequence-parallel form of qk_norm_rope_append: this rank's K / V rows are stored into every rank's replicated
+    cache (peers: an `_lib.PeerDst` built by inferix_b200.peer) and the epoch flag is published."""
+    qkv = _bf16_2d(qkv, "qkv")
+    rows = qkv.shape[0]
+    C_ = heads * head_dim
+    if qkv.shape[1] != 3 * C_:
+        raise ValueError("qkv must be [rows, 3*heads*head_dim]")
+    if freqs_table.dtype != torch.float64 or not freqs_table.is_cuda or not freqs_table.is_contiguous():
+        raise ValueError("freqs_table: use ops.rope_table(model.freqs, device)")
+    if q_out is None:
+        q_out = torch.empty((rows, C_), dtype=torch.bfloat16, device=qkv.device)
+    _lib.check(_lib.load().ifx_qk_norm_rope_append_peers(
+        qkv.data_ptr(), qkv.stride(0), _bf16_vec(norm_q_w, C_, "norm_q").data_ptr(),
+        _bf16_vec(norm_k_w, C_, "norm_k").data_ptr(), freqs_table.data_ptr(), C.byref(grid), q_out.data_ptr(),
+        q_out.stride(0), kv.handle, C.byref(plan), C.byref(peers), rows, heads, head_dim, eps, _stream()))
+    return q_out
 
 
 # ----------------------------------------------------------------------------- MAGI-1 layer row kernels

@@ -247,6 +247,9 @@ class CausalInferencePipeline(torch.nn.Module):
                 adapter.allocate_kv_cache(kv_cache_manager=kv_cache_manager, kv_cache_request=req,
                                           sequence_length=kv_cache_size, dtype=dtype, ulysses_size=ulysses,
                                           ring_size=ring, page_tokens=self.frame_seq_length)
+        from . import peer
+        self._peer_group = peer.setup_for_pipeline(self.generator.model, kv_cache_manager, kv_cache_requests,
+                                                   self.parallel_config)
         device = kv_cache_manager.device
         # all layers' end indices are views of one tensor
         idx = torch.zeros((self.num_transformer_blocks, 2), dtype=torch.long, device=device)
@@ -274,6 +277,10 @@ class CausalInferencePipeline(torch.nn.Module):
 
     def clear_cache(self, kv_cache_manager, kv_cache_requests):
         """reference :494-502."""
+        if getattr(self, "_peer_group", None) is not None:      # unmap the other ranks' caches before anyone frees
+            self._peer_group.release()
+            torch.distributed.barrier(group=self.parallel_config.group)
+            self._peer_group = None
         for layer_idx in range(self.num_transformer_blocks):
             for req in kv_cache_requests:
                 self.generator.model.blocks[layer_idx].kv_cache_manager.clear_cache(

@@ -296,7 +296,17 @@ class CausalWanAttentionBlock(nn.Module):
         plan = store.plan_append(current_start, rows * world, sink_tokens, windowed)
         h, h8 = ln("qkv", shift=m[:, 0], scale=m[:, 1], tokens_per_frame=fs)
         linear("qkv", h, h8, qkv_w, qkv_b, ws.qkv)
-        if world > 1:
+        peer_dst = getattr(store, "peer", None) if world > 1 else None
+        if peer_dst is not None:
+            # exchange fused into the producer: K / V rows go straight into every rank's cache over NVLink, the
+            # attention is ordered after all ranks' epoch flags (inferix_b200/peer.py) — no collective in the layer
+            pg = store.peer_group
+            peer_dst.epoch = pg.next_epoch()
+            ops.qk_norm_rope_append_peers(ws.qkv, sa.norm_q.weight, sa.norm_k.weight, freqs, grid, heads, hd, store,
+                                          plan, peer_dst, q_out=ws.q, eps=self.eps)
+            pg.wait(peer_dst.epoch)
+            store.attention(ws.q, ws.attn)
+        elif world > 1:
             ops.qk_norm_rope_append(ws.qkv, sa.norm_q.weight, sa.norm_k.weight, freqs, grid, heads, hd, q_out=ws.q,
                                     k_out=ws.kv_new[0], v_out=ws.kv_new[1], eps=self.eps)
             old_ext, new_ext = store.split_extents(plan)

@@ -124,7 +124,9 @@ typedef enum ifx_epilogue {
     IFX_EPI_BIAS_GELU = 1,     /* out = bf16(gelu_tanh(bf16(acc + bias)))                 ffn[0:2]  :377-379   */
     IFX_EPI_BIAS_GATE_RES = 2, /* out = bf16(res + bf16(bf16(acc + bias) * gate[f]))      :444, :455-456;      */
                                /* gate == NULL -> out = bf16(res + bf16(acc + bias))      cross-attn  :448     */
-    IFX_EPI_BIAS_GELU_ERF = 3  /* out = bf16(gelu_erf(bf16(acc + bias)))   MAGI CustomMLP, dit_module.py:551   */
+    IFX_EPI_BIAS_GELU_ERF = 3, /* out = bf16(gelu_erf(bf16(acc + bias)))   MAGI CustomMLP, dit_module.py:551   */
+    IFX_EPI_BIAS_F32 = 4       /* out = fp32(acc + bias): `out` is float*, ldo counts floats (16-byte aligned     */
+                               /* rows); MAGI linear_proj under autocast(float32), dit_module.py:1291-1293     */
 } ifx_epilogue;
 
 /* out[M,N] = epilogue(A[M,K] @ W[N,K]^T): tcgen05 BF16 MMA, FP32 accumulation in TMEM, TMA-fed pipeline.
@@ -299,9 +301,11 @@ ifx_status ifx_head_layernorm(const void* x, int64_t ldx, void* out, int64_t ldo
 /* bias_modulate_add (dit_module.py:295-313): out[r] = bf16( LN_fp32( x[r] * gate[row_map[r]] ) * norm_w + norm_b +
  * residual[r] ), i.e. range_mod_triton (:205-292) + fp32 FusedLayerNorm + residual add in one pass.
  * gate bf16 [num_gates, cols] (softcapped AdaModulateLayer output half), row_map int32 [rows] on the device
- * (condition_map), norm_w / norm_b fp32 [cols].  out may alias x or residual. */
-ifx_status ifx_gate_norm_residual(const void* x, int64_t ldx, const void* gate, int64_t gate_stride, int32_t num_gates,
-                                  const int32_t* row_map, const float* norm_w, const float* norm_b,
+ * (condition_map), norm_w / norm_b fp32 [cols].  x is bf16 (the MLP branch) or, with x_is_f32, the fp32 result of the
+ * output projection (IFX_EPI_BIAS_F32; dit_module.py:1291-1293 runs it under autocast(float32)); ldx counts elements
+ * of x's type.  out (bf16) may alias residual, and x when x is bf16. */
+ifx_status ifx_gate_norm_residual(const void* x, int64_t ldx, int32_t x_is_f32, const void* gate, int64_t gate_stride,
+                                  int32_t num_gates, const int32_t* row_map, const float* norm_w, const float* norm_b,
                                   const void* residual, int64_t ldr, void* out, int64_t ldo, int64_t rows,
                                   int32_t cols, float eps, void* stream);
 

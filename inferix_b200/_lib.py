@@ -18,7 +18,7 @@ LIB_PATH = _HERE / "lib" / "libinferix_b200.so"
 IFX_KV_MAX_PLAN_PAGES = 32
 
 IFX_OK, IFX_ERR_INVALID, IFX_ERR_BOUNDS, IFX_ERR_HANDLE, IFX_ERR_OOM, IFX_ERR_CUDA, IFX_ERR_UNSUPPORTED = range(7)
-EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_GATE_RES, EPI_BIAS_GELU_ERF = 0, 1, 2, 3
+EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_GATE_RES, EPI_BIAS_GELU_ERF, EPI_BIAS_F32 = 0, 1, 2, 3, 4
 
 
 class NativeLibraryError(RuntimeError):
@@ -134,8 +134,8 @@ SIGNATURES = {
     "ifx_magi_qkv_post": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32,
                                     _vp, _i64, _i32, _i64, _vp, _vp, _i64, _i32, _i64, _vp, _i64, _vp]),
     "ifx_head_layernorm": (C.c_int, [_vp, _i64, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _f32, _vp]),
-    "ifx_gate_norm_residual": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i32,
-                                         _f32, _vp]),
+    "ifx_gate_norm_residual": (C.c_int, [_vp, _i64, _i32, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _i64,
+                                         _i32, _f32, _vp]),
     "ifx_silu_mul": (C.c_int, [_vp, _i64, _vp, _i64, _i64, _i32, _vp]),
     "ifx_wan_block_forward": (C.c_int, [C.POINTER(WanBlockWeights), C.POINTER(WanBlockIO), C.POINTER(KvPlan), _vp]),
 }

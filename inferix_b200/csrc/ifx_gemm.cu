@@ -219,7 +219,7 @@ static ifx_status gemm_entry(const void* A, int64_t lda, const void* W, int64_t 
     IFX_CHECK_ARG(N % 8 == 0 && K % kAlign == 0, "ifx_gemm: N %% 8 and K %% %d must be 0 (N=%d K=%d)", kAlign, N, K);
     IFX_CHECK_ARG(lda % kAlign == 0 && ldw % kAlign == 0 && ldo % 8 == 0, "ifx_gemm: strides must be 16-byte multiples");
     IFX_CHECK_ARG(lda >= K && ldw >= K && ldo >= N, "ifx_gemm_bf16: stride smaller than row");
-    IFX_CHECK_ARG(epilogue >= IFX_EPI_BIAS && epilogue <= IFX_EPI_BIAS_GELU_ERF, "ifx_gemm_bf16: bad epilogue %d",
+    IFX_CHECK_ARG(epilogue >= IFX_EPI_BIAS && epilogue <= IFX_EPI_BIAS_F32, "ifx_gemm_bf16: bad epilogue %d",
                   epilogue);
     if (epilogue == IFX_EPI_BIAS_GATE_RES) {
         IFX_CHECK_ARG(residual != nullptr && ldr >= N && ldr % 8 == 0, "ifx_gemm_bf16: residual required");
@@ -281,6 +281,7 @@ static ifx_status gemm_entry(const void* A, int64_t lda, const void* W, int64_t 
             case IFX_EPI_BIAS: return launch_gemm<IFX_EPI_BIAS, 256, kFp8>(tmA, tmB, p, s);
             case IFX_EPI_BIAS_GELU: return launch_gemm<IFX_EPI_BIAS_GELU, 256, kFp8>(tmA, tmB, p, s);
             case IFX_EPI_BIAS_GELU_ERF: return launch_gemm<IFX_EPI_BIAS_GELU_ERF, 256, kFp8>(tmA, tmB, p, s);
+            case IFX_EPI_BIAS_F32: return launch_gemm<IFX_EPI_BIAS_F32, 256, kFp8>(tmA, tmB, p, s);
             default: return launch_gemm<IFX_EPI_BIAS_GATE_RES, 256, kFp8>(tmA, tmB, p, s);
         }
     }
@@ -288,6 +289,7 @@ static ifx_status gemm_entry(const void* A, int64_t lda, const void* W, int64_t 
         case IFX_EPI_BIAS: return launch_gemm<IFX_EPI_BIAS, 128, kFp8>(tmA, tmB, p, s);
         case IFX_EPI_BIAS_GELU: return launch_gemm<IFX_EPI_BIAS_GELU, 128, kFp8>(tmA, tmB, p, s);
         case IFX_EPI_BIAS_GELU_ERF: return launch_gemm<IFX_EPI_BIAS_GELU_ERF, 128, kFp8>(tmA, tmB, p, s);
+        case IFX_EPI_BIAS_F32: return launch_gemm<IFX_EPI_BIAS_F32, 128, kFp8>(tmA, tmB, p, s);
         default: return launch_gemm<IFX_EPI_BIAS_GATE_RES, 128, kFp8>(tmA, tmB, p, s);
     }
 }

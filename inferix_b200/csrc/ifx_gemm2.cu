@@ -278,6 +278,7 @@ ifx_status gemm2_dispatch(bool fp8, int bn, const void* A, int64_t lda, const vo
         case IFX_EPI_BIAS: IFX_G2(IFX_EPI_BIAS);
         case IFX_EPI_BIAS_GELU: IFX_G2(IFX_EPI_BIAS_GELU);
         case IFX_EPI_BIAS_GELU_ERF: IFX_G2(IFX_EPI_BIAS_GELU_ERF);
+        case IFX_EPI_BIAS_F32: IFX_G2(IFX_EPI_BIAS_F32);
         default: IFX_G2(IFX_EPI_BIAS_GATE_RES);
     }
 #undef IFX_G2

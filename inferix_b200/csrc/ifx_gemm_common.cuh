@@ -36,6 +36,24 @@ template <int kEpi, bool kFp8>
 __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, const uint32_t (&acc)[32], int64_t row, int col0,
                                                     const __nv_bfloat16* gate_row) {
     __nv_bfloat16* optr = p.out + row * p.ldo + col0;
+    if (kEpi == IFX_EPI_BIAS_F32) {
+        // fp32 result, no bf16 rounding of the accumulator: MAGI's output projection runs under
+        // torch.autocast(dtype=float32) (dit_module.py:1291-1293) and feeds the fp32 gate / post-norm directly
+        float* fo = reinterpret_cast<float*>(p.out) + row * p.ldo + col0;
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+            if (col0 + v * 4 >= p.N) break;
+            float4 o;
+            float* oe = reinterpret_cast<float*>(&o);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float a = __uint_as_float(acc[v * 4 + e]);
+                oe[e] = (kFp8 ? a * p.alpha : a) + (p.bias ? __bfloat162float(p.bias[col0 + v * 4 + e]) : 0.f);
+            }
+            *reinterpret_cast<float4*>(fo + v * 4) = o;
+        }
+        return;
+    }
 #pragma unroll
     for (int v = 0; v < 4; ++v) {
         if (col0 + v * 8 >= p.N) break;

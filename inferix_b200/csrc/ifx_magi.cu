@@ -188,16 +188,18 @@ head_layernorm_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bfl
     store4(out + row * ldo + static_cast<int64_t>(head) * kHeadDim + lane * 4, v);
 }
 
-// out[row] = bf16( LN_fp32( x[row] * gate[map[row]] ) * w + b + residual[row] )
+// out[row] = bf16( LN_fp32( x[row] * gate[map[row]] ) * w + b + residual[row] );  x is bf16 or (kXF32) fp32
+template <bool kXF32>
 __global__ void __launch_bounds__(kRowThreadsMax)
-gate_norm_residual_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const __nv_bfloat16* __restrict__ gate,
+gate_norm_residual_kernel(const void* __restrict__ x_, int64_t ldx, const __nv_bfloat16* __restrict__ gate,
                           int64_t gate_stride, const int32_t* __restrict__ row_map, const float* __restrict__ nw,
                           const float* __restrict__ nb, const __nv_bfloat16* residual, int64_t ldr,
                           __nv_bfloat16* out, int64_t ldo, int cols, float eps) {
     __shared__ float scratch[32];
     const int64_t row = blockIdx.x;
     const int nvec = cols >> 3;
-    const uint4* xr = reinterpret_cast<const uint4*>(x + row * ldx);
+    const uint4* xr = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(x_) + (kXF32 ? 0 : row * ldx));
+    const float4* xf = reinterpret_cast<const float4*>(static_cast<const float*>(x_) + (kXF32 ? row * ldx : 0));
     const uint4* gr = reinterpret_cast<const uint4*>(gate + static_cast<int64_t>(__ldg(row_map + row)) * gate_stride);
     float v[kVecMax][8];
     float s = 0.f;
@@ -206,11 +208,17 @@ gate_norm_residual_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, cons
         const int vi = threadIdx.x + i * blockDim.x;
         if (vi < nvec) {
             float g[8];
-            unpack8f(xr[vi], v[i]);
+            if (kXF32) {
+                const float4 a = xf[2 * vi], b = xf[2 * vi + 1];
+                v[i][0] = a.x; v[i][1] = a.y; v[i][2] = a.z; v[i][3] = a.w;
+                v[i][4] = b.x; v[i][5] = b.y; v[i][6] = b.z; v[i][7] = b.w;
+            } else {
+                unpack8f(xr[vi], v[i]);
+            }
             unpack8f(__ldg(gr + vi), g);
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-                v[i][e] *= g[e];             // exact in fp32 (two bf16 factors)
+                v[i][e] *= g[e];             // x.float() * gate.float()  (exact when x is bf16)
                 s += v[i][e];
             }
         }
@@ -361,10 +369,11 @@ extern "C" ifx_status ifx_head_layernorm(const void* x, int64_t ldx, void* out, 
     return IFX_OK;
 }
 
-extern "C" ifx_status ifx_gate_norm_residual(const void* x, int64_t ldx, const void* gate, int64_t gate_stride,
-                                             int32_t num_gates, const int32_t* row_map, const float* norm_w,
-                                             const float* norm_b, const void* residual, int64_t ldr, void* out,
-                                             int64_t ldo, int64_t rows, int32_t cols, float eps, void* stream) {
+extern "C" ifx_status ifx_gate_norm_residual(const void* x, int64_t ldx, int32_t x_is_f32, const void* gate,
+                                             int64_t gate_stride, int32_t num_gates, const int32_t* row_map,
+                                             const float* norm_w, const float* norm_b, const void* residual,
+                                             int64_t ldr, void* out, int64_t ldo, int64_t rows, int32_t cols, float eps,
+                                             void* stream) {
     IFX_CHECK_ARG(x && gate && row_map && norm_w && norm_b && residual && out, "ifx_gate_norm_residual: null pointer");
     IFX_CHECK_ARG(rows > 0 && cols > 0 && cols % 8 == 0 && cols <= kRowThreadsMax * kVecMax * 8,
                   "ifx_gate_norm_residual: cols must be a multiple of 8 and <= %d (got %d)", kRowThreadsMax * kVecMax * 8,
@@ -376,10 +385,14 @@ extern "C" ifx_status ifx_gate_norm_residual(const void* x, int64_t ldx, const v
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     {
         ProfScope prof("gate_norm_residual_kernel", st);
-        gate_norm_residual_kernel<<<static_cast<unsigned>(rows), row_threads_for(cols), 0, st>>>(
-            static_cast<const __nv_bfloat16*>(x), ldx, static_cast<const __nv_bfloat16*>(gate), gate_stride, row_map,
-            norm_w, norm_b, static_cast<const __nv_bfloat16*>(residual), ldr, static_cast<__nv_bfloat16*>(out), ldo,
-            cols, eps);
+        if (x_is_f32)
+            gate_norm_residual_kernel<true><<<static_cast<unsigned>(rows), row_threads_for(cols), 0, st>>>(
+                x, ldx, static_cast<const __nv_bfloat16*>(gate), gate_stride, row_map, norm_w, norm_b,
+                static_cast<const __nv_bfloat16*>(residual), ldr, static_cast<__nv_bfloat16*>(out), ldo, cols, eps);
+        else
+            gate_norm_residual_kernel<false><<<static_cast<unsigned>(rows), row_threads_for(cols), 0, st>>>(
+                x, ldx, static_cast<const __nv_bfloat16*>(gate), gate_stride, row_map, norm_w, norm_b,
+                static_cast<const __nv_bfloat16*>(residual), ldr, static_cast<__nv_bfloat16*>(out), ldo, cols, eps);
     }
     IFX_LAUNCH_OK("gate_norm_residual_kernel");
     return IFX_OK;

@@ -13,7 +13,8 @@ libinferix_b200.so:
     core attention per denoising range ifx_attention_gqa  (grouped-query, keys = cache rows)        (:972-1015)
     caption K | V projection, k-LN     ifx_gemm_bf16 + ifx_head_layernorm                           (:960-968)
     cross attention per range          ifx_attention_gqa                                            (:1047-1085)
-    output projection                  ifx_gemm_bf16 on [core | cross] (weight columns pre-permuted for :1287)
+    output projection                  ifx_gemm_bf16 on [core | cross] (weight columns pre-permuted for :1287), fp32
+                                       result (IFX_EPI_BIAS_F32) as under the reference's autocast(float32) (:1291-1293)
     gate * x -> LN -> + residual       ifx_gate_norm_residual                                       (:295-313)
     MLP: LN, fc1 (+GELU-erf epilogue | + ifx_silu_mul), fc2, gate/LN/residual                       (:545-556)
 
@@ -347,12 +348,13 @@ class TransformerLayer(nn.Module):
             attn_cat[:, :hq * d].unflatten(1, (cp, qg * d)).copy_(back.transpose(0, 1))
 
         # ---- output projection, gate, post-norm, residual (:1281-1311)
-        proj = sc.get("proj", (s_loc, h), bf, dev)
-        _ops.gemm(attn_cat, pk["w_proj"], None, proj)
+        # the reference runs this projection under autocast(float32) (:1291-1293): its result is consumed in fp32
+        proj32 = sc.get("proj32", (s_loc, h), torch.float32, dev)
+        _ops.gemm(attn_cat, pk["w_proj"], None, proj32, epilogue=_ops.EPI_BIAS_F32)
         gate = softcap(F.linear(F.silu(condition.reshape(-1, condition.shape[-1])), pk["ada_w"], pk["ada_b"]), 1.0)
         gate = gate.to(bf).contiguous()                                          # [ranges, 2h]: gate_msa | gate_mlp
         x1 = torch.empty_like(x)
-        _ops.gate_norm_residual(proj, gate[:, :h], ctx.row_map, pk["post1"][0], pk["post1"][1], x, x1, eps=eps)
+        _ops.gate_norm_residual(proj32, gate[:, :h], ctx.row_map, pk["post1"][0], pk["post1"][1], x, x1, eps=eps)
 
         # ---- MLP (:545-556) + second gate / post-norm / residual (:1313-1317)
         f = mc.ffn_hidden_size
@@ -364,6 +366,7 @@ class TransformerLayer(nn.Module):
             _ops.silu_mul(ffn, act)
         else:
             _ops.gemm(hbuf, pk["fc1"], None, act, epilogue=_ops.EPI_BIAS_GELU_ERF)
+        proj = sc.get("proj", (s_loc, h), bf, dev)
         _ops.gemm(act, pk["fc2"], None, proj)
         _ops.gate_norm_residual(proj, gate[:, h:], ctx.row_map, pk["post2"][0], pk["post2"][1], x1, x1, eps=eps)
         return x1.view(s_loc, 1, h)

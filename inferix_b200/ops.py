@@ -11,12 +11,12 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import EPI_BIAS, EPI_BIAS_GATE_RES, EPI_BIAS_GELU, EPI_BIAS_GELU_ERF, KvPlan, RopeGrid
+from ._lib import EPI_BIAS, EPI_BIAS_F32, EPI_BIAS_GATE_RES, EPI_BIAS_GELU, EPI_BIAS_GELU_ERF, KvPlan, RopeGrid
 
 __all__ = [
     "ln_modulate", "gemm", "rmsnorm", "quantize_fp8", "ln_modulate_fp8", "gemm_fp8", "attention", "attention_gqa", "attention_ranges", "attention_partial", "attention_combine",
     "attention_workspace_bytes", "qk_norm_rope_append", "PagedKV", "rope_table",
-    "EPI_BIAS", "EPI_BIAS_GELU", "EPI_BIAS_GATE_RES", "EPI_BIAS_GELU_ERF",
+    "EPI_BIAS", "EPI_BIAS_GELU", "EPI_BIAS_GATE_RES", "EPI_BIAS_GELU_ERF", "EPI_BIAS_F32",
     "qk_norm_rope_append_peers", "magi_qkv_post", "head_layernorm", "gate_norm_residual", "silu_mul",
 ]
 
@@ -84,9 +84,17 @@ def gemm(a, w, bias=None, out=None, *, epilogue=EPI_BIAS, residual=None, gate=No
     N = w.shape[0]
     if w.shape[1] != K:
         raise ValueError(f"gemm: a is [{M},{K}] but w is {tuple(w.shape)}")
-    if out is None:
-        out = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
-    out = _bf16_2d(out, "out")
+    if epilogue == EPI_BIAS_F32:
+        if out is None:
+            out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+        if not out.is_cuda or out.dtype != torch.float32 or out.dim() != 2 or out.stride(1) != 1:
+            raise ValueError("out: EPI_BIAS_F32 writes a 2-D CUDA float32 tensor with unit inner stride")
+    else:
+        if out is None:
+            out = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+        out = _bf16_2d(out, "out")
+    if out.shape != (M, N):
+        raise ValueError(f"gemm: out must be [{M},{N}], got {tuple(out.shape)}")
     gstride = 0
     if gate is not None:
         if gate.dim() != 2 or gate.shape[1] != N or gate.stride(1) != 1:
@@ -469,16 +477,22 @@ def head_layernorm(x, heads, weight, bias, out=None, *, eps=1e-6):
 
 def gate_norm_residual(x, gate, row_map, norm_w, norm_b, residual, out=None, *, eps=1e-6):
     """bias_modulate_add (dit_module.py:295-313): bf16(LN_fp32(x * gate[row_map]) * norm_w + norm_b + residual).
-    gate bf16 [ranges, C]; row_map int32 [rows] (condition_map); norm_w / norm_b fp32 [C]."""
-    x, gate, residual = _bf16_2d(x, "x"), _bf16_2d(gate, "gate"), _bf16_2d(residual, "residual")
+    x bf16 or fp32 [rows, C]; gate bf16 [ranges, C]; row_map int32 [rows] (condition_map); norm_w / norm_b fp32 [C]."""
+    gate, residual = _bf16_2d(gate, "gate"), _bf16_2d(residual, "residual")
+    x_f32 = x.dtype == torch.float32
+    if x_f32:
+        if not x.is_cuda or x.dim() != 2 or x.stride(1) != 1:
+            raise ValueError("x: expected a 2-D CUDA tensor with unit inner stride")
+    else:
+        x = _bf16_2d(x, "x")
     rows, cols = x.shape
     if gate.shape[1] != cols or residual.shape != x.shape:
         raise ValueError("gate_norm_residual: gate must be [ranges, C] and residual [rows, C]")
     if row_map.dtype != torch.int32 or not row_map.is_cuda or row_map.numel() != rows or not row_map.is_contiguous():
         raise ValueError("row_map must be a contiguous CUDA int32 vector with one entry per row")
-    out = torch.empty_like(x) if out is None else _bf16_2d(out, "out")
+    out = torch.empty_like(residual) if out is None else _bf16_2d(out, "out")
     _lib.check(_lib.load().ifx_gate_norm_residual(
-        x.data_ptr(), x.stride(0), gate.data_ptr(), gate.stride(0), gate.shape[0], row_map.data_ptr(),
+        x.data_ptr(), x.stride(0), int(x_f32), gate.data_ptr(), gate.stride(0), gate.shape[0], row_map.data_ptr(),
         _f32_vec(norm_w, cols, "norm weight").data_ptr(), _f32_vec(norm_b, cols, "norm bias").data_ptr(),
         residual.data_ptr(), residual.stride(0), out.data_ptr(), out.stride(0), rows, cols, eps, _stream()))
     return out

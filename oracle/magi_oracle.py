@@ -10,7 +10,9 @@ Parity status: PINNED to the reference's own modules.  `oracle/make_golden_magi_
 `tests/golden/magi_layer_*.pt` / `magi_cp.json`; `tests/test_magi_layer_cpu.py` checks this restatement against those
 files bit-for-bit.  The reference layer calls five CUDA-only third-party kernels; the golden run replaces each by the
 torch statement of its published algorithm, which is also what this file restates — so for these five the pin is to
-the algorithm, not to the vendor's binary ("parity unpinned" at that boundary):
+the algorithm, not to the vendor's binary ("parity unpinned" at that boundary).  The golden run also
+emulates CUDA autocast(dtype=float32) — inactive on a CPU-only host — by casting the operands of `F.linear` to fp32
+inside the reference's `torch.autocast("cuda", dtype=torch.float32)` regions, which is what CUDA autocast does:
   flash_attn.flash_attn_func / flash_attn_varlen_func  -> softmax(q k^T / sqrt(d)) v with grouped KV heads, fp32 math
   flash_attn.layers.rotary.apply_rotary_emb             -> flash_attn's own `apply_rotary_emb_torch` (non-interleaved)
   range_mod_triton (in-tree Triton, dit_module.py:205-292) -> y[row] = x[row] * gatings[map[row]]
@@ -207,12 +209,16 @@ def layer_forward(sd, layer: int, cfg: MagiConfig, hidden, condition, condition_
     s, b, _ = attn.shape
     hd = attn.shape[2] // 16
     attn = attn.reshape(s, b, 2, 8, hd).transpose(2, 3).reshape(s, b, -1)                           # (n hn hd)->(hn n hd) :1287
-    h = F.linear(attn, sd[p + "self_attention.linear_proj.weight"])                                 # :1288-1293
+    # non-quantised projection runs under torch.autocast("cuda", dtype=float32) (:1291-1293): CUDA autocast casts the
+    # operands of `linear` to fp32, so the result stays fp32 through the gate / post-norm and is rounded only after
+    # the residual add (bias_modulate_add works in x's dtype, then `.to(params_dtype)`, :1306-1308)
+    pdt = hidden.dtype
+    h = F.linear(attn.float(), sd[p + "self_attention.linear_proj.weight"].float())
     gate = F.linear(F.silu(condition), sd[p + "ada_modulate_layer.proj.0.weight"],
                     sd[p + "ada_modulate_layer.proj.0.bias"])                                       # :196-198
     gate_msa, gate_mlp = softcap(gate, 1.0).chunk(2, dim=-1)                                        # :1300-1303
     h = bias_modulate_add(h, residual, condition_map, gate_msa, sd[p + "self_attn_post_norm.weight"],
-                          sd[p + "self_attn_post_norm.bias"], cfg)
+                          sd[p + "self_attn_post_norm.bias"], cfg).to(pdt)
     residual = h
     m = F.layer_norm(h, (cfg.hidden_size,), sd[p + "mlp.layer_norm.weight"], sd[p + "mlp.layer_norm.bias"],
                      cfg.layernorm_epsilon)                                                         # CustomMLP :545-556
@@ -275,6 +281,28 @@ def synth_state_dict(cfg: MagiConfig, seed: int = 0, dtype=torch.bfloat16) -> Di
         lin(p + "mlp.linear_fc2", h, f)
         norm(p + "mlp_post_norm", h, torch.float32)
     norm("final_layernorm", h, torch.float32)
+    return sd
+
+
+def synth_model_state_dict(module, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """Seeded weights for a whole VideoDiTModel (reference or native: same parameter names), one generator per
+    parameter NAME so the result does not depend on registration order; dtypes follow the module's."""
+    import zlib
+    sd = {}
+    for name, p in module.state_dict().items():
+        g = torch.Generator().manual_seed((zlib.crc32(name.encode()) + seed) & 0x7FFFFFFF)
+        if name.endswith("rope.bands"):
+            t = p.detach().float().clone()
+        elif p.dim() >= 2 and "null_caption" not in name:
+            fan_in = p[0].numel()
+            t = torch.randn(p.shape, generator=g) * fan_in ** -0.5
+        elif "null_caption" in name:
+            t = torch.randn(p.shape, generator=g) * 0.5
+        elif name.endswith("weight"):
+            t = 1.0 + 0.1 * torch.randn(p.shape, generator=g)
+        else:
+            t = 0.05 * torch.randn(p.shape, generator=g)
+        sd[name] = t.to(p.dtype)
     return sd
 
 

@@ -43,12 +43,35 @@ def import_reference():
     torch.cuda.get_device_capability = lambda *a: (8, 0)     # selects the flash_attn_func branch (:1000-1014)
 
     def flash_attn_func(q, k, v, deterministic=False):
-        assert q.shape[0] == 1
-        return mo.gqa_attention(q[0], k[0], v[0])[None]
+        return torch.stack([mo.gqa_attention(q[b], k[b], v[b]) for b in range(q.shape[0])])
 
     def flash_attn_varlen_func(q, k, v, cu_seqlens_q, cu_seqlens_k, max_seqlen_q, max_seqlen_k, deterministic=False):
         return mo.varlen_attention(q, k, v, cu_seqlens_q.tolist(), cu_seqlens_k.tolist())
 
+    class Fp32Autocast:
+        """What torch.autocast("cuda", dtype=torch.float32) does to `linear` on a GPU (it is a no-op on a CPU-only host):
+        operands cast to fp32.  Used by dit_module.py:1291-1293 and dit_model.py:278,344."""
+
+        def __init__(self, device_type=None, dtype=None, **kw):
+            assert dtype == torch.float32
+            self.orig = None
+
+        def __enter__(self):
+            self.orig = torch.nn.functional.linear
+            orig = self.orig
+            torch.nn.functional.linear = lambda x, w, b=None: orig(x.float(), w.float(), None if b is None else b.float())
+            return self
+
+        def __exit__(self, *exc):
+            torch.nn.functional.linear = self.orig
+            return False
+
+    import inferix.models.magi.dit.dit_model as dmodel
+    dm.torch = types.SimpleNamespace(**{k: getattr(torch, k) for k in dir(torch) if not k.startswith("__")})
+    dm.torch.autocast = Fp32Autocast
+    dmodel_torch = types.SimpleNamespace(**{k: getattr(torch, k) for k in dir(torch) if not k.startswith("__")})
+    dmodel_torch.autocast = Fp32Autocast
+    dmodel.torch = dmodel_torch
     dm.flash_attn_func = flash_attn_func
     dm.flash_attn_varlen_func = flash_attn_varlen_func
     dm.flash_apply_rotary_emb = lambda x, cos, sin: apply_rotary_emb_torch(x, cos, sin)

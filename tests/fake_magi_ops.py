@@ -9,7 +9,7 @@ import torch.nn.functional as F
 
 from oracle import magi_oracle as mo
 
-EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_GATE_RES, EPI_BIAS_GELU_ERF = 0, 1, 2, 3
+EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_GATE_RES, EPI_BIAS_GELU_ERF, EPI_BIAS_F32 = 0, 1, 2, 3, 4
 calls = []
 
 
@@ -22,11 +22,15 @@ def ln_modulate(x, out=None, *, weight=None, bias=None, shift=None, scale=None, 
 
 def gemm(a, w, bias=None, out=None, *, epilogue=EPI_BIAS, residual=None, gate=None, tokens_per_frame=0):
     calls.append("gemm")
-    y = F.linear(a, w, bias)
-    if epilogue == EPI_BIAS_GELU_ERF:
-        y = F.gelu(y)
+    if epilogue == EPI_BIAS_F32:
+        assert out.dtype == torch.float32
+        y = F.linear(a.float(), w.float(), None if bias is None else bias.float())
     else:
-        assert epilogue == EPI_BIAS
+        y = F.linear(a, w, bias)
+        if epilogue == EPI_BIAS_GELU_ERF:
+            y = F.gelu(y)
+        else:
+            assert epilogue == EPI_BIAS
     out.copy_(y)
     return out
 
@@ -100,7 +104,7 @@ def install(monkeypatch, magi_layer):
     """Route magi_layer's kernel calls and cache allocation to the doubles above."""
     me = types.SimpleNamespace(**{n: globals()[n] for n in (
         "ln_modulate", "gemm", "magi_qkv_post", "head_layernorm", "attention_gqa", "gate_norm_residual", "silu_mul",
-        "EPI_BIAS", "EPI_BIAS_GELU", "EPI_BIAS_GATE_RES", "EPI_BIAS_GELU_ERF")})
+        "EPI_BIAS", "EPI_BIAS_GELU", "EPI_BIAS_GATE_RES", "EPI_BIAS_GELU_ERF", "EPI_BIAS_F32")})
     monkeypatch.setattr(magi_layer, "_ops", me)
     stores = {}
 

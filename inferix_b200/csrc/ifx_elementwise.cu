@@ -252,6 +252,9 @@ __device__ __forceinline__ int rope_pos(int pair, int half, int t_pos, int h_pos
     return pair < n_t ? t_pos : (pair < n_t + third ? h_pos : w_pos);
 }
 
+// kPeers: compile the peer-memory stores + epoch publication in (sequence parallel); the single-GPU instantiation
+// keeps the register footprint and code of the plain append
+template <bool kPeers>
 __global__ void __launch_bounds__(kRowThreads)
 qk_norm_rope_append_kernel(const NormRopeParams p) {
     __shared__ float scratch[2 * 32];
@@ -267,7 +270,7 @@ qk_norm_rope_append_kernel(const NormRopeParams p) {
     if (p.paged == 1) {
         const int pg = static_cast<int>(t / p.page_tokens);
         drow = static_cast<int64_t>(p.pl.pages[pg]) * p.page_tokens + (t % p.page_tokens);
-    } else if (p.paged == 2) {
+    } else if (kPeers && p.paged == 2) {
         // token index inside the block in single-process order: (frame, rank, hw)  (causal_model.py:1016-1021)
         const int64_t fs_full = static_cast<int64_t>(p.sp_world) * p.grid.hw_count;
         const int64_t tb = (t / p.grid.hw_count) * fs_full + p.grid.hw_offset + (t % p.grid.hw_count);
@@ -304,7 +307,7 @@ qk_norm_rope_append_kernel(const NormRopeParams p) {
                 ss[1] += k[i][e] * k[i][e];
             }
             // V is appended untouched
-            if (p.paged == 2) {
+            if (kPeers && p.paged == 2) {
                 const uint4 vv = vr[vi];
                 for (int d = 0; d < p.sp_world; ++d) {
                     const int dst = (p.sp_rank + 1 + d) % p.sp_world;      // start at the neighbour: spread the links
@@ -343,7 +346,7 @@ qk_norm_rope_append_kernel(const NormRopeParams p) {
                 ko[2 * e + 1] = static_cast<float>(ka * cs.y + kb * cs.x);
             }
             reinterpret_cast<uint4*>(p.q_out + t * p.ld_q)[vi] = pack8(qo);
-            if (p.paged == 2) {
+            if (kPeers && p.paged == 2) {
                 const uint4 kk = pack8(ko);
                 for (int d = 0; d < p.sp_world; ++d) {
                     const int dst = (p.sp_rank + 1 + d) % p.sp_world;
@@ -354,7 +357,7 @@ qk_norm_rope_append_kernel(const NormRopeParams p) {
             }
         }
     }
-    if (p.paged == 2) {
+    if (kPeers && p.paged == 2) {
         // every thread's peer stores are ordered before the CTA's arrival; the last CTA to arrive publishes the epoch
         __threadfence_system();
         __syncthreads();
@@ -658,7 +661,10 @@ static ifx_status norm_rope_append_entry(const void* qkv, int64_t ld_qkv, const 
     {
         ProfScope prof(peers ? "qk_norm_rope_append_kernel<peers>" : "qk_norm_rope_append_kernel",
                        static_cast<cudaStream_t>(stream));
-        qk_norm_rope_append_kernel<<<static_cast<unsigned>(rows), row_threads(C), 0, static_cast<cudaStream_t>(stream)>>>(p);
+        if (peers)
+            qk_norm_rope_append_kernel<true><<<static_cast<unsigned>(rows), row_threads(C), 0, static_cast<cudaStream_t>(stream)>>>(p);
+        else
+            qk_norm_rope_append_kernel<false><<<static_cast<unsigned>(rows), row_threads(C), 0, static_cast<cudaStream_t>(stream)>>>(p);
     }
     IFX_LAUNCH_OK("qk_norm_rope_append_kernel");
     return IFX_OK;

@@ -113,3 +113,43 @@ def test_sp_oracle_equals_single_process_oracle():
         want = scatter_tokens(ref, frames, P, r)
         assert torch.allclose(out, want, rtol=1e-4, atol=1e-4)
         assert torch.allclose(cache.k[:, :cache.local_end], single.k[:, :single.local_end], rtol=1e-5, atol=1e-5)
+
+
+# ----------------------------------------------------------------------------- peer-memory exchange: collective-safe setup
+def _peer_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import types
+        import warnings
+        from inferix_b200 import peer
+        # CPU tensors cannot be exported through CUDA IPC: every rank must still take part in the handle exchange and
+        # the vote, agree on "no peer path", leave the stores untouched and return None (-> NCCL all-gather path)
+        stores = [types.SimpleNamespace(k=torch.zeros(8, 256, dtype=torch.bfloat16),
+                                        v=torch.zeros(8, 256, dtype=torch.bfloat16)) for _ in range(3)]
+        with warnings.catch_warnings(record=True) as w:
+            warnings.simplefilter("always")
+            pg = peer.try_setup(stores, world, rank, None, torch.device("cpu"))
+        ok = pg is None and all(s.peer is None and s.peer_group is None for s in stores)
+        ok = ok and (rank != 0 or any("peer-memory KV exchange unavailable" in str(x.message) for x in w))
+        # and the helper used by the pipelines is a no-op for a single rank / when disabled
+        pc1 = types.SimpleNamespace(world_size=1, rank=0, group=None)
+        ok = ok and peer.setup_for_pipeline(None, None, [], pc1) is None
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_peer_setup_falls_back_collectively_without_ipc():
+    world, port = 2, _free_port()
+    with mp.Manager() as m:
+        ret = m.dict()
+        mp.spawn(_peer_worker, args=(world, port, ret), nprocs=world, join=True)
+        assert dict(ret) == {0: True, 1: True}
+
+
+def test_peer_group_rejects_more_than_eight_ranks():
+    from inferix_b200 import peer
+    with pytest.raises(ValueError):
+        peer.PeerGroup(9, 0, None, "cpu")

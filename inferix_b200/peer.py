@@ -22,7 +22,7 @@ import torch.distributed as dist
 from . import _lib
 
 ENABLED = os.environ.get("IFX_SP_PEER", "1") != "0"
-WAIT_TIMEOUT_MS = int(os.environ.get("IFX_SP_PEER_TIMEOUT_MS", "20000"))
+WAIT_TIMEOUT_MS = int(os.environ.get("IFX_SP_PEER_TIMEOUT_MS", "60000"))
 
 
 class PeerGroup:

@@ -8,6 +8,11 @@ Import map for a user of the reference:
     inferix.models.schedulers.flow_match.FlowMatchScheduler -> inferix_b200.scheduler.FlowMatchScheduler
     inferix.pipeline.self_forcing.CausalInferencePipeline -> inferix_b200.pipeline.CausalInferencePipeline
     inferix.models.wan_base.ParallelConfig            -> inferix_b200.parallel.ParallelConfig
+    inferix.pipeline.causvid.CausalInferencePipeline / models.causvid.* -> inferix_b200.causvid.*
+    inferix.models.magi.dit.dit_module.{TransformerLayer,TransformerBlock,...} -> inferix_b200.magi_layer.*
+    inferix.models.magi.dit.dit_model.VideoDiTModel   -> inferix_b200.magi_model.VideoDiTModel
+    inferix.pipeline.magi.video_generate.SampleTransport (+ index helpers) -> inferix_b200.magi_pipeline / magi_schedule
+    inferix.distributed.parallelism.context_parallel (Ulysses) -> inferix_b200.magi_cp
 Everything computes through libinferix_b200.so (include/inferix_b200.h); there is no CPU fallback.
 """
 __version__ = "0.1.0"

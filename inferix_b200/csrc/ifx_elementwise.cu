@@ -236,8 +236,10 @@ struct NormRopeParams {
     unsigned int* done_counter;
 };
 
-__device__ __forceinline__ void st_release_sys(long long* p, long long v) {
-    asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+// relaxed system-scope store; the caller issues ONE __threadfence_system() before the flag stores (fence + relaxed
+// store = release pattern), instead of a membar per destination rank as st.release.sys would emit
+__device__ __forceinline__ void st_relaxed_sys(long long* p, long long v) {
+    asm volatile("st.relaxed.sys.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ long long ld_acquire_sys(const long long* p) {
     long long v;
@@ -366,7 +368,7 @@ qk_norm_rope_append_kernel(const NormRopeParams p) {
             if (prev == gridDim.x - 1) {
                 *p.done_counter = 0;                       // next launch on this stream starts from zero
                 __threadfence_system();
-                for (int d = 0; d < p.sp_world; ++d) st_release_sys(p.peer_flags[d] + p.sp_rank, p.epoch);
+                for (int d = 0; d < p.sp_world; ++d) st_relaxed_sys(p.peer_flags[d] + p.sp_rank, p.epoch);
             }
         }
     }

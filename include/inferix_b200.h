@@ -200,6 +200,8 @@ typedef struct ifx_peer_dst {
     void* v[IFX_MAX_PEERS];
     int64_t* flags[IFX_MAX_PEERS];   /* every rank's flag array, int64[world]; this rank writes element `rank` */
     int64_t epoch;                   /* > 0, increases by one per call, identical on all ranks */
+    int32_t local_only;              /* ifx_qk_norm_rope_append_peers: 1 = write this rank's cache only and publish  */
+                                     /* nothing; ifx_peer_push performs the exchange (overlap variant)               */
 } ifx_peer_dst;
 
 /* CUDA IPC: handle of the allocation containing ptr (+ ptr's offset inside it), to be shipped to the other processes
@@ -216,6 +218,12 @@ ifx_status ifx_qk_norm_rope_append_peers(const void* qkv, int64_t ld_qkv, const 
                                          void* q_out, int64_t ld_q, ifx_kv* kv, const ifx_kv_plan* plan,
                                          const ifx_peer_dst* peers, int64_t rows, int32_t heads, int32_t head_dim,
                                          float eps, void* stream);
+/* Exchange half of ifx_qk_norm_rope_append_peers as its own small grid (`ctas` CTAs of 1024 threads): copies this rank's
+ * rows of the block's new pages from its cache to every other rank's cache and publishes `peers->epoch`.  Meant for a
+ * side stream, next to the attention over the pages that were already cached (which needs no new K / V); the
+ * attention over the new pages then follows an ifx_peer_wait.  Experimental: built, not yet measured. */
+ifx_status ifx_peer_push(ifx_kv* kv, const ifx_kv_plan* plan, const ifx_peer_dst* peers, int32_t frames, int32_t chunk,
+                         int32_t ctas, void* stream);
 /* Stream-ordered wait until flags[s] >= epoch for every s < world; traps after timeout_ms instead of hanging. */
 ifx_status ifx_peer_wait(const int64_t* flags, int32_t world, int64_t epoch, int32_t timeout_ms, void* stream);
 

@@ -58,6 +58,7 @@ class PeerDst(C.Structure):
         ("k", C.c_void_p * IFX_MAX_PEERS), ("v", C.c_void_p * IFX_MAX_PEERS),
         ("flags", C.c_void_p * IFX_MAX_PEERS),
         ("epoch", C.c_int64),
+        ("local_only", C.c_int32),
     ]
 
 
@@ -122,6 +123,7 @@ SIGNATURES = {
     "ifx_qk_norm_rope_append_peers": (C.c_int, [_vp, _i64, _vp, _vp, _vp, C.POINTER(RopeGrid), _vp, _i64, _vp,
                                                 C.POINTER(KvPlan), C.POINTER(PeerDst), _i64, _i32, _i32, _f32, _vp]),
     "ifx_peer_wait": (C.c_int, [_vp, _i32, _i64, _i32, _vp]),
+    "ifx_peer_push": (C.c_int, [_vp, C.POINTER(KvPlan), C.POINTER(PeerDst), _i32, _i32, _i32, _vp]),
     "ifx_kv_append": (C.c_int, [_vp, C.POINTER(KvPlan), _vp, _vp, _i64, _i64, _vp]),
     "ifx_kv_append_sp": (C.c_int, [_vp, C.POINTER(KvPlan), _vp, _vp, _i64, _i32, _i32, _i32, _vp]),
     "ifx_rmsnorm": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _i64, _i32, _f32, _vp]),

@@ -234,6 +234,7 @@ struct NormRopeParams {
     long long* peer_flags[IFX_MAX_PEERS];
     long long epoch;
     unsigned int* done_counter;
+    int32_t local_only;      // 1: store into this rank's cache only and publish nothing (ifx_peer_push does the exchange)
 };
 
 // relaxed system-scope store; the caller issues ONE __threadfence_system() before the flag stores (fence + relaxed
@@ -311,9 +312,13 @@ qk_norm_rope_append_kernel(const NormRopeParams p) {
             // V is appended untouched
             if (kPeers && p.paged == 2) {
                 const uint4 vv = vr[vi];
-                for (int d = 0; d < p.sp_world; ++d) {
-                    const int dst = (p.sp_rank + 1 + d) % p.sp_world;      // start at the neighbour: spread the links
-                    reinterpret_cast<uint4*>(p.peer_v[dst] + drow * C)[vi] = vv;
+                if (p.local_only) {
+                    reinterpret_cast<uint4*>(p.peer_v[p.sp_rank] + drow * C)[vi] = vv;
+                } else {
+                    for (int d = 0; d < p.sp_world; ++d) {
+                        const int dst = (p.sp_rank + 1 + d) % p.sp_world;  // start at the neighbour: spread the links
+                        reinterpret_cast<uint4*>(p.peer_v[dst] + drow * C)[vi] = vv;
+                    }
                 }
             } else {
                 reinterpret_cast<uint4*>(p.v_dst + drow * C)[vi] = vr[vi];
@@ -350,16 +355,20 @@ qk_norm_rope_append_kernel(const NormRopeParams p) {
             reinterpret_cast<uint4*>(p.q_out + t * p.ld_q)[vi] = pack8(qo);
             if (kPeers && p.paged == 2) {
                 const uint4 kk = pack8(ko);
-                for (int d = 0; d < p.sp_world; ++d) {
-                    const int dst = (p.sp_rank + 1 + d) % p.sp_world;
-                    reinterpret_cast<uint4*>(p.peer_k[dst] + drow * C)[vi] = kk;
+                if (p.local_only) {
+                    reinterpret_cast<uint4*>(p.peer_k[p.sp_rank] + drow * C)[vi] = kk;
+                } else {
+                    for (int d = 0; d < p.sp_world; ++d) {
+                        const int dst = (p.sp_rank + 1 + d) % p.sp_world;
+                        reinterpret_cast<uint4*>(p.peer_k[dst] + drow * C)[vi] = kk;
+                    }
                 }
             } else {
                 reinterpret_cast<uint4*>(p.k_dst + drow * C)[vi] = pack8(ko);
             }
         }
     }
-    if (kPeers && p.paged == 2) {
+    if (kPeers && p.paged == 2 && !p.local_only) {
         // every thread's peer stores are ordered before the CTA's arrival; the last CTA to arrive publishes the epoch
         __threadfence_system();
         __syncthreads();
@@ -424,6 +433,52 @@ paged_copy_kernel(const PagedCopyParams p) {
             if (p.lin_v)
                 reinterpret_cast<uint4*>(p.lin_v + r * p.ld_lin)[vi] =
                     reinterpret_cast<const uint4*>(p.cache_v + crow * p.C)[vi];
+        }
+    }
+}
+
+// Copy this rank's rows of the block's new pages from its own cache to the same rows of every other rank's cache and
+// publish the epoch: the exchange half of qk_norm_rope_append_kernel<true>, as a separate small grid that runs on a
+// side stream next to the attention over the already-cached pages (which leaves a few SMs free at 4-8 ranks).
+struct PeerPushParams {
+    int32_t world, rank, frames, chunk, page_tokens, C;
+    PageList pl;
+    __nv_bfloat16* peer_k[IFX_MAX_PEERS];
+    __nv_bfloat16* peer_v[IFX_MAX_PEERS];
+    long long* peer_flags[IFX_MAX_PEERS];
+    long long epoch;
+    unsigned int* done_counter;
+};
+
+__global__ void __launch_bounds__(1024)
+peer_push_kernel(const PeerPushParams p) {
+    const int nvec = p.C >> 3;
+    const int64_t rows = static_cast<int64_t>(p.frames) * p.chunk;
+    const int64_t fs_full = static_cast<int64_t>(p.world) * p.chunk;
+    const int64_t total = rows * nvec * 2;                               // K and V
+    const __nv_bfloat16* src[2] = {p.peer_k[p.rank], p.peer_v[p.rank]};
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int which = static_cast<int>(i / (rows * nvec));
+        const int64_t r = (i / nvec) % rows;
+        const int vi = static_cast<int>(i % nvec);
+        const int64_t tb = (r / p.chunk) * fs_full + static_cast<int64_t>(p.rank) * p.chunk + r % p.chunk;
+        const int64_t crow = static_cast<int64_t>(p.pl.pages[tb / p.page_tokens]) * p.page_tokens + tb % p.page_tokens;
+        const uint4 val = reinterpret_cast<const uint4*>(src[which] + crow * p.C)[vi];
+        for (int d = 1; d < p.world; ++d) {
+            const int dst = (p.rank + d) % p.world;
+            __nv_bfloat16* base = which ? p.peer_v[dst] : p.peer_k[dst];
+            reinterpret_cast<uint4*>(base + crow * p.C)[vi] = val;
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(p.done_counter, 1u);
+        if (prev == gridDim.x - 1) {
+            *p.done_counter = 0;
+            __threadfence_system();
+            for (int d = 0; d < p.world; ++d) st_relaxed_sys(p.peer_flags[d] + p.rank, p.epoch);
         }
     }
 }
@@ -636,6 +691,7 @@ static ifx_status norm_rope_append_entry(const void* qkv, int64_t ld_qkv, const 
             IFX_CHECK_ARG(grid->hw_offset == peers->rank * grid->hw_count,
                           "ifx_qk_norm_rope_append_peers: grid.hw_offset must be rank * hw_count");
             p.paged = 2;
+            p.local_only = peers->local_only ? 1 : 0;
             p.sp_world = peers->world;
             p.sp_rank = peers->rank;
             p.epoch = peers->epoch;
@@ -689,6 +745,49 @@ extern "C" ifx_status ifx_qk_norm_rope_append_peers(const void* qkv, int64_t ld_
     IFX_CHECK_ARG(kv_ && plan && peers, "ifx_qk_norm_rope_append_peers: kv, plan and peers are required");
     return norm_rope_append_entry(qkv, ld_qkv, norm_q_weight, norm_k_weight, freqs, grid, q_out, ld_q, kv_, plan, nullptr,
                                   nullptr, peers, rows, heads, head_dim, eps, stream);
+}
+
+extern "C" ifx_status ifx_peer_push(ifx_kv* kv_, const ifx_kv_plan* plan, const ifx_peer_dst* peers, int32_t frames,
+                                    int32_t chunk, int32_t ctas, void* stream) {
+    KvImpl* kv = kv_cast(kv_);
+    if (!kv) return set_error(IFX_ERR_HANDLE, "ifx_peer_push: bad kv handle");
+    IFX_CHECK_ARG(plan && peers, "ifx_peer_push: null pointer");
+    IFX_CHECK_ARG(peers->world >= 2 && peers->world <= IFX_MAX_PEERS && peers->rank >= 0 && peers->rank < peers->world &&
+                      peers->epoch > 0, "ifx_peer_push: bad world / rank / epoch");
+    IFX_CHECK_ARG(frames > 0 && chunk > 0 && ctas > 0 && ctas <= 1024, "ifx_peer_push: bad geometry");
+    const int64_t rows = static_cast<int64_t>(peers->world) * frames * chunk;
+    IFX_CHECK_ARG(rows == plan->local_end - plan->local_start && rows == (int64_t)plan->num_pages * kv->page_tokens,
+                  "ifx_peer_push: world*frames*chunk (%lld) does not match the plan", (long long)rows);
+    static unsigned int* g_done_push = nullptr;    // separate from the append kernel's counter: the two may overlap
+    if (!g_done_push) {
+        IFX_CUDA_OK(cudaMalloc(&g_done_push, sizeof(unsigned int)));
+        IFX_CUDA_OK(cudaMemset(g_done_push, 0, sizeof(unsigned int)));
+    }
+    PeerPushParams p = {};
+    p.world = peers->world;
+    p.rank = peers->rank;
+    p.frames = frames;
+    p.chunk = chunk;
+    p.page_tokens = kv->page_tokens;
+    p.C = kv->heads * kv->head_dim;
+    p.pl.n = plan->num_pages;
+    for (int i = 0; i < plan->num_pages; ++i) p.pl.pages[i] = plan->pages[i];
+    for (int d = 0; d < peers->world; ++d) {
+        IFX_CHECK_ARG(peers->k[d] && peers->v[d] && peers->flags[d], "ifx_peer_push: null peer %d", d);
+        p.peer_k[d] = static_cast<__nv_bfloat16*>(peers->k[d]);
+        p.peer_v[d] = static_cast<__nv_bfloat16*>(peers->v[d]);
+        p.peer_flags[d] = reinterpret_cast<long long*>(peers->flags[d]);
+    }
+    IFX_CHECK_ARG(peers->k[peers->rank] == kv->k_base && peers->v[peers->rank] == kv->v_base,
+                  "ifx_peer_push: own entry must be this rank's cache");
+    p.epoch = peers->epoch;
+    p.done_counter = g_done_push;
+    {
+        ProfScope prof("peer_push_kernel", static_cast<cudaStream_t>(stream));
+        peer_push_kernel<<<ctas, 1024, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    }
+    IFX_LAUNCH_OK("peer_push_kernel");
+    return IFX_OK;
 }
 
 extern "C" ifx_status ifx_peer_wait(const int64_t* flags, int32_t world, int64_t epoch, int32_t timeout_ms, void* stream) {

@@ -17,7 +17,7 @@ __all__ = [
     "ln_modulate", "gemm", "rmsnorm", "quantize_fp8", "ln_modulate_fp8", "gemm_fp8", "attention", "attention_gqa", "attention_ranges", "attention_partial", "attention_combine",
     "attention_workspace_bytes", "qk_norm_rope_append", "PagedKV", "rope_table",
     "EPI_BIAS", "EPI_BIAS_GELU", "EPI_BIAS_GATE_RES", "EPI_BIAS_GELU_ERF", "EPI_BIAS_F32",
-    "qk_norm_rope_append_peers", "magi_qkv_post", "head_layernorm", "gate_norm_residual", "silu_mul",
+    "qk_norm_rope_append_peers", "peer_push", "magi_qkv_post", "head_layernorm", "gate_norm_residual", "silu_mul",
 ]
 
 
@@ -410,6 +410,12 @@ def qk_norm_rope_append_peers(qkv, norm_q_w, norm_k_w, freqs_table, grid: RopeGr
         _bf16_vec(norm_k_w, C_, "norm_k").data_ptr(), freqs_table.data_ptr(), C.byref(grid), q_out.data_ptr(),
         q_out.stride(0), kv.handle, C.byref(plan), C.byref(peers), rows, heads, head_dim, eps, _stream()))
     return q_out
+
+
+def peer_push(kv: "PagedKV", plan: KvPlan, peers, frames: int, chunk: int, *, ctas: int = 4):
+    """Exchange half of qk_norm_rope_append_peers as its own small grid (see ifx_peer_push): copies this rank's rows of
+    the block's new pages to every other rank's cache and publishes peers.epoch.  Runs on the current stream."""
+    _lib.check(_lib.load().ifx_peer_push(kv.handle, C.byref(plan), C.byref(peers), frames, chunk, ctas, _stream()))
 
 
 # ----------------------------------------------------------------------------- MAGI-1 layer row kernels

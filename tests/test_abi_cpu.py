@@ -38,6 +38,9 @@ def test_struct_layout_matches_header():
     # ifx_kv_plan: 4 x int64 + int32 + 32 x int32 + int32 (+ padding to 8)
     assert ctypes.sizeof(_lib.KvPlan) == 4 * 8 + 4 + 32 * 4 + 4
     assert ctypes.sizeof(_lib.RopeGrid) == 24
+    # ifx_peer_dst: 2 x int32, 3 x 8 pointers, int64 epoch, int32 local_only (+ 4 padding)
+    assert ctypes.sizeof(_lib.PeerDst) == 8 + 3 * 8 * 8 + 8 + 8
+    assert _lib.PeerDst.epoch.offset == 200 and _lib.PeerDst.local_only.offset == 208
 
 
 def test_errors_map_to_reference_exception_types():

@@ -109,7 +109,12 @@ class CausalInferencePipeline(torch.nn.Module):
                   return_latents: bool = False, profile: bool = False, low_memory: bool = False,
                   free_cache_before_vae: bool = True, decode_mode: DecodeMode = DecodeMode.AFTER_ALL,
                   vae_chunk_size: Optional[int] = None, block_callback: Optional[callable] = None,
-                  vae_decode_context=None) -> Union[torch.Tensor, tuple]:
+                  vae_decode_context=None, callback_stream: Optional["torch.cuda.Stream"] = None
+                  ) -> Union[torch.Tensor, tuple]:
+        """Reference signature (:108-131) plus `callback_stream`: when given, `block_callback` — the
+        PER_BLOCK VAE decode in the reference's streaming path (self_forcing/pipeline.py:677-699) — is issued on that
+        stream after an event that marks the block's latent final, so the decode of block i overlaps the denoising
+        of block i+1; the main stream re-joins it before `inference` returns."""
         perf = PerformanceProfiler(enabled=profile)
         batch_size, num_frames, num_channels, height, width = noise.shape
         assert num_frames % self.num_frame_per_block == 0
@@ -177,7 +182,17 @@ class CausalInferencePipeline(torch.nn.Module):
                             pass
                 current_start_frame += n
                 if block_callback is not None:
-                    block_callback(output[:, current_start_frame - n:current_start_frame], block_index)
+                    block_latent = output[:, current_start_frame - n:current_start_frame]
+                    if callback_stream is None:
+                        block_callback(block_latent, block_index)
+                    else:
+                        final = torch.cuda.Event()
+                        final.record()
+                        with torch.cuda.stream(callback_stream):
+                            callback_stream.wait_event(final)
+                            block_callback(block_latent, block_index)
+            if block_callback is not None and callback_stream is not None:
+                torch.cuda.current_stream().wait_stream(callback_stream)
             self.last_block_times_ms = block_times
 
         if free_cache_before_vae:

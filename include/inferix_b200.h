@@ -60,8 +60,10 @@ ifx_status ifx_prof_labels(char* buf, int32_t cap);
  * The caller owns the memory: two bf16 buffers k_base / v_base of shape [num_pages * page_tokens, heads*head_dim].
  * The handle owns only the block table (logical page -> physical page), the free list and the two end indices
  * the reference keeps in kv_cache_meta["global_end_index"/"local_end_index"].  Eviction rotates the table
- * (0 bytes moved) where the reference copies up to 4*(L-S)*C*2 bytes.  The allocator hands out pages so that
- * the set of valid physical pages is always the prefix [0, valid_pages) — attention streams it as one extent.
+ * (0 bytes moved) where the reference copies up to 4*(L-S)*C*2 bytes.  The allocator recycles before it takes fresh
+ * pages, so for the windows the reference produces the valid physical pages are the prefix [0, valid_pages) and the
+ * attention streams them as one dense extent; any other table is read as runs of consecutive pages
+ * (ifx_attention_kv); rows of unmapped pages are never attended, so the buffers may start uninitialised.
  * ------------------------------------------------------------------------------------------------ */
 typedef struct ifx_kv ifx_kv;
 
@@ -272,9 +274,29 @@ ifx_status ifx_attention_partial(const void* q, int64_t ldq, const void* k, cons
                                  int32_t piece_first, int32_t piece_count, void* stream);
 ifx_status ifx_attention_combine(const void* workspace, int32_t pieces_per_item, void* out, int64_t ldo,
                                  int64_t q_rows, int32_t heads, int32_t head_dim, void* stream);
-/* Same, keys/values taken from the valid prefix of a paged cache (rows [0, local_end)). */
+/* Attention over a LIST of key-row extents of k/v[0:kv_rows_total): up to IFX_ATTN_MAX_EXTENTS [row0, rows) pairs
+ * (runs of physically consecutive cache pages).  Rows that follow an extent in memory are never attended: their
+ * scores are masked and their V rows are zeroed in shared memory before the P V product, so unmapped pages may hold
+ * anything (NaN included).  This is how a paged cache whose valid pages are not a physical prefix is read. */
+#define IFX_ATTN_MAX_EXTENTS 32
+ifx_status ifx_attention_extents(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv,
+                                 int64_t kv_rows_total, const int64_t* extents, int32_t n_ext, void* out, int64_t ldo,
+                                 int64_t q_rows, int32_t heads, int32_t kv_heads, int32_t head_dim,
+                                 float softmax_scale, void* stream);
+/* Keys / values taken through the block table of a paged cache: the valid logical pages [0, local_end / page_tokens)
+ * are visited in PHYSICAL order (softmax attention does not depend on the key order) as runs of consecutive pages;
+ * when they form the physical prefix — what the allocator produces for every window the reference can express — the
+ * whole window is one dense TMA extent.  IFX_ERR_UNSUPPORTED beyond IFX_ATTN_MAX_EXTENTS runs. */
 ifx_status ifx_attention_kv(const void* q, int64_t ldq, const ifx_kv* kv, void* out, int64_t ldo, int64_t q_rows,
                             float softmax_scale, void* stream);
+/* Sequence-parallel form: the pages named by `fresh` (the plan of the block being appended) are still being stored
+ * by the peer ranks when the kernel starts.  Every CTA attends its share of the other pages first; its TMA producer
+ * thread then acquires the `world` epoch flags (int64[world], system scope, >= epoch; traps after timeout_ms) and only
+ * then loads the fresh pages.  The exchange is hidden behind the attention over the cached window instead of sitting
+ * in front of it (ifx_peer_wait).  Replaces the ring P2P + LSE merge of models/attention/distributed.py:564-712. */
+ifx_status ifx_attention_kv_wait(const void* q, int64_t ldq, const ifx_kv* kv, const ifx_kv_plan* fresh,
+                                 const int64_t* flags, int32_t world, int64_t epoch, int32_t timeout_ms, void* out,
+                                 int64_t ldo, int64_t q_rows, float softmax_scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * MAGI-1 transformer layer row kernels (inferix/models/magi/dit/dit_module.py).  head_dim must be 128.
@@ -370,6 +392,21 @@ typedef struct ifx_wan_block_io {
 
 ifx_status ifx_wan_block_forward(const ifx_wan_block_weights* w, const ifx_wan_block_io* io, ifx_kv_plan* plan_out,
                                  void* stream);
+
+/* The same block for rank `peers->rank` of a sequence-parallel group (causal_model.py:939-942: io->rows local tokens =
+ * frames * hw/P, io->tokens_per_frame = hw/P, io->grid.hw_offset / hw_count name the shard; the cache is replicated and
+ * the plan covers rows * world tokens).  One call per layer, no collective:
+ *   mode IFX_SP_STORE   : the norm + RoPE kernel stores K / V into every rank's cache, ifx_peer_wait, attention.
+ *   mode IFX_SP_OVERLAP : the norm + RoPE kernel writes the local cache only; a `push_ctas`-CTA copy grid ships the rows
+ *                         to the peers and publishes the epoch; the attention kernel is launched programmatically
+ *                         behind it (it starts as soon as the push grid is resident), attends the cached pages while
+ *                         the rows travel and acquires the epoch flags only before its first fresh-page tile
+ *                         (ifx_attention_kv_wait).  The exchange costs no time on the critical path. */
+#define IFX_SP_STORE 0
+#define IFX_SP_OVERLAP 1
+ifx_status ifx_wan_block_forward_sp(const ifx_wan_block_weights* w, const ifx_wan_block_io* io,
+                                    const ifx_peer_dst* peers, int32_t mode, int32_t push_ctas, int32_t timeout_ms,
+                                    ifx_kv_plan* plan_out, void* stream);
 
 #ifdef __cplusplus
 }

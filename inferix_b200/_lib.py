@@ -50,6 +50,8 @@ class RopeGrid(C.Structure):
 
 IFX_MAX_PEERS = 8
 IFX_PEER_HANDLE_BYTES = 64
+IFX_ATTN_MAX_EXTENTS = 32
+IFX_SP_STORE, IFX_SP_OVERLAP = 0, 1
 
 
 class PeerDst(C.Structure):
@@ -133,6 +135,10 @@ SIGNATURES = {
                                         _f32, _vp, _i64, _i32, _i32, _i32, _vp]),
     "ifx_attention_combine": (C.c_int, [_vp, _i32, _vp, _i64, _i64, _i32, _i32, _vp]),
     "ifx_attention_kv": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _i64, _f32, _vp]),
+    "ifx_attention_extents": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _i64, C.POINTER(_i64), _i32, _vp, _i64, _i64, _i32,
+                                        _i32, _i32, _f32, _vp]),
+    "ifx_attention_kv_wait": (C.c_int, [_vp, _i64, _vp, C.POINTER(KvPlan), _vp, _i32, _i64, _i32, _vp, _i64, _i64, _f32,
+                                        _vp]),
     "ifx_magi_qkv_post": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32,
                                     _vp, _i64, _i32, _i64, _vp, _vp, _i64, _i32, _i64, _vp, _i64, _vp]),
     "ifx_head_layernorm": (C.c_int, [_vp, _i64, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _f32, _vp]),
@@ -140,6 +146,8 @@ SIGNATURES = {
                                          _i32, _f32, _vp]),
     "ifx_silu_mul": (C.c_int, [_vp, _i64, _vp, _i64, _i64, _i32, _vp]),
     "ifx_wan_block_forward": (C.c_int, [C.POINTER(WanBlockWeights), C.POINTER(WanBlockIO), C.POINTER(KvPlan), _vp]),
+    "ifx_wan_block_forward_sp": (C.c_int, [C.POINTER(WanBlockWeights), C.POINTER(WanBlockIO), C.POINTER(PeerDst), _i32,
+                                           _i32, _i32, C.POINTER(KvPlan), _vp]),
 }
 
 _lib = None

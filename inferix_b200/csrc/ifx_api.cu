@@ -168,8 +168,10 @@ extern "C" ifx_status ifx_prof_labels(char* buf, int32_t cap) {
         if (_s != IFX_OK) return _s;      \
     } while (0)
 
-extern "C" ifx_status ifx_wan_block_forward(const ifx_wan_block_weights* w, const ifx_wan_block_io* io,
-                                            ifx_kv_plan* plan_out, void* stream) {
+// Shared body of the single-GPU and the sequence-parallel block.  peers == nullptr: single GPU.
+static ifx_status wan_block_forward_impl(const ifx_wan_block_weights* w, const ifx_wan_block_io* io,
+                                         const ifx_peer_dst* peers, int32_t sp_mode, int32_t push_ctas,
+                                         int32_t timeout_ms, ifx_kv_plan* plan_out, void* stream) {
     IFX_CHECK_ARG(w && io, "ifx_wan_block_forward: null argument");
     IFX_CHECK_ARG(io->x && io->mod && io->freqs && io->kv && io->cross_k && io->cross_v,
                   "ifx_wan_block_forward: null tensor");
@@ -181,21 +183,50 @@ extern "C" ifx_status ifx_wan_block_forward(const ifx_wan_block_weights* w, cons
     const int C = w->dim, F = w->ffn_dim;
     const int64_t S = io->rows, fs = io->tokens_per_frame;
     IFX_CHECK_ARG(S > 0 && fs > 0 && S % fs == 0, "ifx_wan_block_forward: rows must be whole frames");
+    const int world = peers ? peers->world : 1;
+    if (peers) {
+        IFX_CHECK_ARG(world >= 2 && world <= IFX_MAX_PEERS && peers->rank >= 0 && peers->rank < world && peers->epoch > 0,
+                      "ifx_wan_block_forward_sp: bad world / rank / epoch");
+        IFX_CHECK_ARG(sp_mode == IFX_SP_STORE || sp_mode == IFX_SP_OVERLAP, "ifx_wan_block_forward_sp: bad mode %d", sp_mode);
+        IFX_CHECK_ARG(timeout_ms > 0 && push_ctas > 0, "ifx_wan_block_forward_sp: timeout_ms / push_ctas must be positive");
+        IFX_CHECK_ARG(peers->flags[peers->rank] != nullptr, "ifx_wan_block_forward_sp: null flag array");
+    }
     const __nv_bfloat16* mod = static_cast<const __nv_bfloat16*>(io->mod);
     const int64_t mstride = 6ll * C;  // per-frame stride of [frames, 6, C]
     const float scale = 1.0f / std::sqrt(static_cast<float>(w->head_dim));
+    cudaStream_t cs = static_cast<cudaStream_t>(stream);
 
     // --- self-attention (causal_model.py:431-444)
     ifx_kv_plan plan;
-    IFX_TRY(ifx_kv_plan_append(io->kv, io->current_start, S, io->sink_tokens, io->windowed, &plan));
+    IFX_TRY(ifx_kv_plan_append(io->kv, io->current_start, S * world, io->sink_tokens, io->windowed, &plan));
     if (plan_out) *plan_out = plan;
     IFX_TRY(ifx_ln_modulate(io->x, io->ws_h, nullptr, nullptr, mod + 0 * C, mod + 1 * C, mstride, S, C, fs, w->eps,
                             stream));
     IFX_TRY(ifx_gemm_bf16(io->ws_h, C, w->qkv_w, C, w->qkv_b, io->ws_qkv, 3 * C, S, 3 * C, C, IFX_EPI_BIAS, nullptr, 0,
                           nullptr, 0, 0, stream));
-    IFX_TRY(ifx_qk_norm_rope_append(io->ws_qkv, 3 * C, w->norm_q_w, w->norm_k_w, io->freqs, &io->grid, io->ws_q, C,
-                                    io->kv, &plan, nullptr, nullptr, S, w->heads, w->head_dim, w->eps, stream));
-    IFX_TRY(ifx_attention_kv(io->ws_q, C, io->kv, io->ws_attn, C, S, scale, stream));
+    if (!peers) {
+        IFX_TRY(ifx_qk_norm_rope_append(io->ws_qkv, 3 * C, w->norm_q_w, w->norm_k_w, io->freqs, &io->grid, io->ws_q, C,
+                                        io->kv, &plan, nullptr, nullptr, S, w->heads, w->head_dim, w->eps, stream));
+        IFX_TRY(ifx_attention_kv(io->ws_q, C, io->kv, io->ws_attn, C, S, scale, stream));
+    } else if (sp_mode == IFX_SP_STORE) {
+        // exchange in front of the attention: K / V stored into every rank's cache by the producer kernel
+        ifx_peer_dst pd = *peers;
+        pd.local_only = 0;
+        IFX_TRY(ifx_qk_norm_rope_append_peers(io->ws_qkv, 3 * C, w->norm_q_w, w->norm_k_w, io->freqs, &io->grid,
+                                              io->ws_q, C, io->kv, &plan, &pd, S, w->heads, w->head_dim, w->eps, stream));
+        IFX_TRY(ifx_peer_wait(peers->flags[peers->rank], world, peers->epoch, timeout_ms, stream));
+        IFX_TRY(ifx_attention_kv(io->ws_q, C, io->kv, io->ws_attn, C, S, scale, stream));
+    } else {
+        // exchange behind the attention over the cached window (see the header)
+        ifx_peer_dst pd = *peers;
+        pd.local_only = 1;
+        IFX_TRY(ifx_qk_norm_rope_append_peers(io->ws_qkv, 3 * C, w->norm_q_w, w->norm_k_w, io->freqs, &io->grid,
+                                              io->ws_q, C, io->kv, &plan, &pd, S, w->heads, w->head_dim, w->eps, stream));
+        IFX_TRY(ifx_peer_push(io->kv, &plan, peers, static_cast<int32_t>(S / fs), static_cast<int32_t>(fs), push_ctas,
+                              stream));
+        IFX_TRY(attention_kv_launch(io->ws_q, C, io->kv, io->ws_attn, C, S, scale, &plan, peers->flags[peers->rank], world,
+                                    peers->epoch, timeout_ms, /*pdl=*/true, cs));
+    }
     IFX_TRY(ifx_gemm_bf16(io->ws_attn, C, w->o_w, C, w->o_b, io->x, C, S, C, C, IFX_EPI_BIAS_GATE_RES, io->x, C,
                           mod + 2 * C, mstride, fs, stream));
     // --- cross-attention (causal_model.py:448, wan_base/model.py:66-100)
@@ -215,4 +246,16 @@ extern "C" ifx_status ifx_wan_block_forward(const ifx_wan_block_weights* w, cons
     IFX_TRY(ifx_gemm_bf16(io->ws_ffn, F, w->ffn2_w, F, w->ffn2_b, io->x, C, S, C, F, IFX_EPI_BIAS_GATE_RES, io->x, C,
                           mod + 5 * C, mstride, fs, stream));
     return IFX_OK;
+}
+
+extern "C" ifx_status ifx_wan_block_forward(const ifx_wan_block_weights* w, const ifx_wan_block_io* io,
+                                            ifx_kv_plan* plan_out, void* stream) {
+    return wan_block_forward_impl(w, io, nullptr, 0, 0, 0, plan_out, stream);
+}
+
+extern "C" ifx_status ifx_wan_block_forward_sp(const ifx_wan_block_weights* w, const ifx_wan_block_io* io,
+                                               const ifx_peer_dst* peers, int32_t mode, int32_t push_ctas,
+                                               int32_t timeout_ms, ifx_kv_plan* plan_out, void* stream) {
+    IFX_CHECK_ARG(peers != nullptr, "ifx_wan_block_forward_sp: peers required");
+    return wan_block_forward_impl(w, io, peers, mode, push_ctas, timeout_ms, plan_out, stream);
 }

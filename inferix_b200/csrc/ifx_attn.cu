@@ -21,6 +21,9 @@
 // sites of the block: self-attention over cache[0:local_end] (causal_model.py:307-315) and text
 // cross-attention (wan_base/model.py:94-95).  Numerics follow FlashAttention-2: fp32 scores and running
 // sum (of the un-rounded probabilities), bf16 P for the PV product, one division by l at the end.
+#include <algorithm>
+#include <vector>
+
 #include "ifx_internal.h"
 #include "ifx_ptx.cuh"
 
@@ -36,6 +39,7 @@ constexpr int kAttnThreads = 384;
 constexpr int kAttnSmem = 2 * kTileBytes + kSlots * kTileBytes + 1024 + 256;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
 constexpr int kMaxSplit = 8;
+constexpr int kMaxExt = IFX_ATTN_MAX_EXTENTS;  // key-row extents (runs of physically consecutive cache pages) per launch
 #ifndef IFX_ATTN_POLY_EVERY
 #define IFX_ATTN_POLY_EVERY 0
 #endif
@@ -59,24 +63,72 @@ struct AttnParams {
     int32_t pieces_per_item;
     int32_t piece_first;
     int32_t piece_count;
-    int32_t n_ext;           // 0: one dense extent [0, kv_rows)
-    int32_t ext_row0[4];     // first key row of each extent
-    int32_t ext_rows[4];     // keys in each extent
-    int32_t ext_tile0[5];    // cumulative 128-key tile counts
+    int32_t n_ext;               // 0: one dense extent [0, kv_rows)
+    int32_t ext_row0[kMaxExt];   // first key row of each extent
+    int32_t ext_rows[kMaxExt];   // keys in each extent
+    int32_t ext_tile0[kMaxExt + 1];  // cumulative 128-key tile counts
+    // ---- ordered key tiles + in-kernel wait (sequence parallel over peer memory): tiles [0, n_old_tiles) are
+    // resident when the kernel starts; tiles [n_old_tiles, total) are rows the peers are still storing.  Every CTA
+    // walks its share of the old tiles first, then spins (producer thread only) until all `wait_world` epoch flags
+    // reached `wait_epoch`, then walks its share of the new tiles.  wait_flags == nullptr: no wait.
+    int32_t n_old_tiles;
+    int32_t wait_world;
+    const long long* wait_flags;
+    long long wait_epoch;
+    unsigned long long wait_timeout_ns;
 };
 
-// key tile j (over the concatenated extents) -> first key row and number of valid keys in the tile
-__device__ __forceinline__ void kv_tile_info(const AttnParams& p, int j, int& row0, int& valid) {
-    if (p.n_ext == 0) {
-        row0 = j * kKT;
-        valid = p.kv_rows - row0;
-        return;
-    }
+// Monotone cursor over the extent list: key tile j (over the concatenated extents) -> first key row and number of
+// valid keys in the tile.  Tiles are visited in increasing j by every role, so the extent index only moves forward.
+struct TileCursor {
     int e = 0;
-    while (e + 1 < p.n_ext && j >= p.ext_tile0[e + 1]) ++e;
-    const int lt = j - p.ext_tile0[e];
-    row0 = p.ext_row0[e] + lt * kKT;
-    valid = p.ext_rows[e] - lt * kKT;
+    __device__ __forceinline__ void locate(const AttnParams& p, int j, int& row0, int& valid) {
+        if (p.n_ext == 0) {
+            row0 = j * kKT;
+            valid = p.kv_rows - row0;
+            return;
+        }
+        while (e + 1 < p.n_ext && j >= p.ext_tile0[e + 1]) ++e;
+        const int lt = j - p.ext_tile0[e];
+        row0 = p.ext_row0[e] + lt * kKT;
+        valid = p.ext_rows[e] - lt * kKT;
+    }
+};
+
+// The key tiles one CTA owns: slice `sub` of `n` of the old tiles, then the same slice of the new tiles.
+struct TileRange {
+    int old_begin, n_old, new_begin, n_new;
+    __device__ __forceinline__ int count() const { return n_old + n_new; }
+    __device__ __forceinline__ int tile(int i) const { return i < n_old ? old_begin + i : new_begin + (i - n_old); }
+};
+__device__ __forceinline__ TileRange make_tile_range(int n_all, int n_old_tiles, int sub, int n) {
+    const int n_new_tiles = n_all - n_old_tiles;
+    TileRange r;
+    r.old_begin = static_cast<int>(static_cast<int64_t>(n_old_tiles) * sub / n);
+    r.n_old = static_cast<int>(static_cast<int64_t>(n_old_tiles) * (sub + 1) / n) - r.old_begin;
+    r.new_begin = n_old_tiles + static_cast<int>(static_cast<int64_t>(n_new_tiles) * sub / n);
+    r.n_new = n_old_tiles + static_cast<int>(static_cast<int64_t>(n_new_tiles) * (sub + 1) / n) - r.new_begin;
+    return r;
+}
+
+// Producer-side wait for the peers' K / V rows: acquire every rank's epoch flag at system scope, then order the TMA
+// (async proxy) reads that follow after the acquired generic-proxy view.  Bounded: traps instead of hanging the GPU.
+__device__ __forceinline__ void wait_peer_flags(const AttnParams& p) {
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+    for (int s = 0; s < p.wait_world; ++s) {
+        while (ld_acquire_sys(p.wait_flags + s) < p.wait_epoch) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+            if (now - t0 > p.wait_timeout_ns) {
+                printf("ifx attention: rank %d did not publish epoch %lld (have %lld)\n", s, p.wait_epoch,
+                       ld_acquire_sys(p.wait_flags + s));
+                __trap();
+            }
+            __nanosleep(200);
+        }
+    }
+    asm volatile("fence.proxy.async;" ::: "memory");
 }
 
 __global__ void __launch_bounds__(kAttnThreads, 1)
@@ -93,34 +145,43 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     uint64_t* s_full = q_full + 1;         // [2]
     uint64_t* p_full = s_full + 2;         // [2]
     uint64_t* o_full = p_full + 2;         // [1]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+    uint64_t* v_fixed = o_full + 1;        // [kSlots]  warp 3 -> MMA (extent mode): V tile checked, stale rows zeroed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(v_fixed + kSlots);
+    // valid keys of tile i at [i & 7], written by the producer before it arms the tile's K slot (release through the
+    // mbarrier chain kv_full -> s_full); the softmax warps read it after s_full.  The producer runs < 4 tiles ahead.
+    volatile int32_t* tile_valid = reinterpret_cast<volatile int32_t*>(tmem_slot + 1);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
-    // ---- which (item, key range) does this CTA own
+    // ---- which (item, key tiles) does this CTA own
     const int n_kv_all = p.n_ext ? p.ext_tile0[p.n_ext] : (p.kv_rows + kKT - 1) / kKT;
-    int item, piece = -1, kv_begin = 0, kv_end = n_kv_all;
+    const int n_old_all = p.wait_flags ? p.n_old_tiles : n_kv_all;
+    int item, piece = -1, sub = 0, nsub = 1;
     if (p.partial) {
         item = blockIdx.x / p.piece_count;
-        const int sub = blockIdx.x % p.piece_count;
+        sub = blockIdx.x % p.piece_count;
+        nsub = p.piece_count;
         piece = item * p.pieces_per_item + p.piece_first + sub;
-        kv_begin = static_cast<int>(static_cast<int64_t>(n_kv_all) * sub / p.piece_count);
-        kv_end = static_cast<int>(static_cast<int64_t>(n_kv_all) * (sub + 1) / p.piece_count);
     } else if (static_cast<int>(blockIdx.x) < p.n_whole) {
         item = blockIdx.x;
     } else {
         const int idx = blockIdx.x - p.n_whole;
         item = p.n_whole + idx / p.split;
-        const int sub = idx % p.split;
+        sub = idx % p.split;
+        nsub = p.split;
         piece = idx;
-        kv_begin = static_cast<int>(static_cast<int64_t>(n_kv_all) * sub / p.split);
-        kv_end = static_cast<int>(static_cast<int64_t>(n_kv_all) * (sub + 1) / p.split);
     }
+    const TileRange tiles = make_tile_range(n_kv_all, n_old_all, sub, nsub);
     const int head = item / p.num_q_pairs;
     const int q0 = (item % p.num_q_pairs) * (2 * kQT);
-    const int n_kv = kv_end - kv_begin;
+    const int n_kv = tiles.count();
     const bool two = q0 + kQT < p.q_rows;  // second tile has at least one real row
+    // extent mode: a tile at the end of an extent is followed in memory by rows of OTHER pages (unmapped, or being
+    // written by a peer).  Their scores are masked, but 0 x NaN would still poison P V, so warp 3 zeroes those V rows
+    // in shared memory before the MMA warp may consume the tile (v_fixed barrier).  The dense mode needs none of
+    // this: its tensor map ends at kv_rows and TMA zero-fills.
+    const bool fix_tails = p.n_ext != 0;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmQ);
@@ -138,21 +199,23 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             mbar_init(&p_full[i], 128);
         }
         mbar_init(o_full, 1);
+        for (int i = 0; i < kSlots; ++i) mbar_init(&v_fixed[i], 1);
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc<512>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    // each role re-reads the TMEM base from shared memory into its own registers (a single kernel-wide value gets
+    // spilled to local memory by ptxas and reloaded in front of every MMA)
+    auto tmem_base_of = [tmem_slot]() { return *reinterpret_cast<volatile uint32_t*>(tmem_slot); };
     // TMEM columns
-    const uint32_t tS[2] = {tmem_base + 0, tmem_base + 128};
-    const uint32_t tO[2] = {tmem_base + 256, tmem_base + 384};
+    // TMEM columns: S0 | S1 | O0 | O1 (128 each)
 
     // register re-balancing: the producer / MMA warpgroup needs few registers, the softmax warps hold a whole
-    // 128-wide score row per thread (the CTA owns 384 x 168 = 64512 registers = 128 x 56 + 256 x 224; asking for more deadlocks the inc)
+    // 128-wide score row per thread (the CTA owns 384 x 168 = 64512 registers = 128 x 72 + 256 x 216; asking for more deadlocks the inc)
     if (warp < 4) {
-      setmaxnreg_dec<56>();
+      setmaxnreg_dec<72>();
       if (warp == 0) {
         if (lane == 0) {
             // Q: one or two tiles x two 64-wide halves
@@ -164,9 +227,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     tma_load_2d_hint(sQ + w * kTileBytes + h * kHalfBytes, &tmQ, q_full, head * kHD + h * 64,
                                      q0 + w * kQT, kEvictFirst);
             int idx = 0;
-            for (int j = kv_begin; j < kv_end; ++j) {
+            TileCursor cur;
+            for (int i = 0; i < n_kv; ++i) {
+                if (i == tiles.n_old && p.wait_flags != nullptr) wait_peer_flags(p);
                 int krow0, kvalid;
-                kv_tile_info(p, j, krow0, kvalid);
+                cur.locate(p, tiles.tile(i), krow0, kvalid);
+                tile_valid[i & 7] = kvalid;
 #pragma unroll
                 for (int kv = 0; kv < 2; ++kv, ++idx) {
                     const int s = idx % kSlots;
@@ -181,8 +247,38 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 }
             }
         }
-    } else if (warp == 1) {
+      } else if (warp == 3) {
+        if (fix_tails) {
+            // every V tile passes through this warp on its way to the MMA warp (v_fixed instead of kv_full); tiles
+            // that end an extent get their rows past the extent zeroed first.  Same tile walk as the producer.
+            TileCursor cur;
+            for (int i = 0; i < n_kv; ++i) {
+                int krow0, kvalid;
+                cur.locate(p, tiles.tile(i), krow0, kvalid);
+                const int vi = 2 * i + 1;
+                const int slot = vi % kSlots;
+                mbar_wait(&kv_full[slot], static_cast<uint32_t>((vi / kSlots) & 1));
+                if (kvalid < kKT) {
+                    uint8_t* vt = sKV + slot * kTileBytes;
+                    // row r of the tile = 128 bytes at r * 128 in each 64-dim half (the swizzle permutes 16-byte
+                    // chunks inside the row only)
+                    const int n16 = (kKT - kvalid) * 8;   // 16-byte chunks per half
+                    for (int c = lane; c < 2 * n16; c += 32) {
+                        const int h = c / n16, o = c % n16;
+                        *reinterpret_cast<uint4*>(vt + h * kHalfBytes + kvalid * 128 + o * 16) = make_uint4(0, 0, 0, 0);
+                    }
+                    fence_proxy_async();
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&v_fixed[slot]);
+            }
+        }
+      }
+      if (warp == 1) {
         if (lane == 0) {
+            const uint32_t tmem_base = tmem_base_of();
+            auto tS = [tmem_base](int w) { return tmem_base + static_cast<uint32_t>(w) * 128u; };
+            auto tO = [tmem_base](int w) { return tmem_base + 256u + static_cast<uint32_t>(w) * 128u; };
             // S = Q K^T : A = Q (K-major), B = K (K-major), M = N = 128
             constexpr uint32_t idesc_qk = make_idesc_bf16(kQT, kKT, 0, 0);
             // O += P V  : A = P (TMEM),   B = V (MN-major: dims contiguous), M = 128, N = head_dim
@@ -193,7 +289,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
                 for (int k = 0; k < kHD / 16; ++k) {
                     const uint32_t off = (k >> 2) * kHalfBytes + (k & 3) * 32;
-                    umma_ss(tS[w], make_smem_desc_sw128(qa + off, 16, 1024), make_smem_desc_sw128(ka + off, 16, 1024),
+                    umma_ss(tS(w), make_smem_desc_sw128(qa + off, 16, 1024), make_smem_desc_sw128(ka + off, 16, 1024),
                             idesc_qk, k != 0);
                 }
             };
@@ -203,7 +299,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 for (int k = 0; k < kKT / 16; ++k) {
                     // 16 keys = 16 rows of 128 bytes; the two 64-dim halves are kHalfBytes apart (LBO), 8-key
                     // groups 1024 bytes apart (SBO).  P: 16 bf16 = 8 TMEM columns per step.
-                    umma_ts(tO[w], tS[w] + k * 8, make_smem_desc_sw128(va + k * 16 * 128, kHalfBytes, 1024), idesc_pv,
+                    umma_ts(tO(w), tS(w) + k * 8, make_smem_desc_sw128(va + k * 16 * 128, kHalfBytes, 1024), idesc_pv,
                             accumulate || k != 0);
                 }
             };
@@ -224,7 +320,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 const int vi = 2 * j + 1;
                 const int kn = 2 * j + 2;
                 const bool more = (j + 1 < n_kv);
-                mbar_wait(&kv_full[slot_of(vi)], phase_of(vi));
+                mbar_wait(fix_tails ? &v_fixed[slot_of(vi)] : &kv_full[slot_of(vi)], phase_of(vi));
                 mbar_wait(&p_full[0], j & 1);
                 tc_fence_after();
                 issue_pv(0, slot_of(vi), j > 0);
@@ -252,13 +348,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
       }
     } else {
-        setmaxnreg_inc<224>();
+        setmaxnreg_inc<216>();
         const int w = (warp - 4) >> 2;  // which query tile
         if (w == 0 || two) {
             const int quad = warp & 3;      // TMEM lane quadrant
             const uint32_t lane_sel = static_cast<uint32_t>(quad * 32) << 16;
-            const uint32_t tS_row = tS[w] + lane_sel;
-            const uint32_t tO_row = tO[w] + lane_sel;
+            const uint32_t tmem_base = tmem_base_of();
+            const uint32_t tS_row = tmem_base + static_cast<uint32_t>(w) * 128u + lane_sel;
+            const uint32_t tO_row = tmem_base + 256u + static_cast<uint32_t>(w) * 128u + lane_sel;
             const int row_in_pair = w * kQT + quad * 32 + lane;
             const int row = q0 + row_in_pair;
             const float sl2 = p.scale_log2;
@@ -272,8 +369,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
                 for (int c = 0; c < 4; ++c) tmem_ld32(tS_row + c * 32, s[c]);
                 tmem_wait_ld();
-                int krow0, valid;
-                kv_tile_info(p, kv_begin + j, krow0, valid);
+                const int valid = tile_valid[j & 7];
                 if (valid < kKT) {
 #pragma unroll
                     for (int c = 0; c < 4; ++c)
@@ -384,7 +480,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc<512>(tmem_base);
+        tmem_dealloc<512>(tmem_base_of());
     }
 }
 
@@ -421,15 +517,93 @@ attn_combine_kernel(const AttnParams p) {
     *reinterpret_cast<uint2*>(p.out + static_cast<int64_t>(row) * p.ldo + head * kHD + lane * 4) = pkt;
 }
 
-static void fill_defaults(AttnParams& p);
+// Which key rows a launch attends, and (sequence parallel) which of them are still in flight from the peers.
+struct KeySpec {
+    int n_ext = 0;                 // 0: dense rows [0, kv_rows)
+    int32_t row0[kMaxExt];
+    int32_t rows[kMaxExt];
+    int n_old_ext = -1;            // extents [0, n_old_ext) are resident, the rest sit behind the flag wait; -1: no wait
+    const long long* flags = nullptr;
+    int world = 0;
+    long long epoch = 0;
+    unsigned long long timeout_ns = 0;
+    bool pdl = false;              // launch with programmatic stream serialization (may start before the preceding
+                                   // kernel on the stream has finished; see ifx_wan_block_forward_sp)
+};
 
-// persistent scratch for split partials (grown on demand; one stream at a time, see header "not thread-safe")
-static float* g_part = nullptr;
-static size_t g_part_bytes = 0;
+static void fill_defaults(AttnParams& p) {
+    p.partial = 0;
+    p.pieces_per_item = p.piece_count = 1;
+    p.piece_first = 0;
+    p.n_ext = 0;
+    for (int i = 0; i < kMaxExt; ++i) p.ext_row0[i] = p.ext_rows[i] = 0;
+    for (int i = 0; i <= kMaxExt; ++i) p.ext_tile0[i] = 0;
+    p.n_old_tiles = 0;
+    p.wait_world = 0;
+    p.wait_flags = nullptr;
+    p.wait_epoch = 0;
+    p.wait_timeout_ns = 0;
+}
+
+// returns the total number of key tiles
+static int fill_keys(AttnParams& p, const KeySpec* ks, int64_t kv_rows) {
+    if (ks == nullptr || ks->n_ext == 0) return static_cast<int>((kv_rows + kKT - 1) / kKT);
+    p.n_ext = ks->n_ext;
+    int tiles = 0;
+    for (int i = 0; i < ks->n_ext; ++i) {
+        p.ext_row0[i] = ks->row0[i];
+        p.ext_rows[i] = ks->rows[i];
+        p.ext_tile0[i] = tiles;
+        if (i == ks->n_old_ext) p.n_old_tiles = tiles;
+        tiles += (ks->rows[i] + kKT - 1) / kKT;
+    }
+    for (int i = ks->n_ext; i <= kMaxExt; ++i) p.ext_tile0[i] = tiles;
+    if (ks->n_old_ext >= ks->n_ext) p.n_old_tiles = tiles;
+    if (ks->n_old_ext >= 0 && ks->flags != nullptr) {
+        p.wait_flags = ks->flags;
+        p.wait_world = ks->world;
+        p.wait_epoch = ks->epoch;
+        p.wait_timeout_ns = ks->timeout_ns;
+    }
+    return tiles;
+}
+
+static ifx_status launch_attn_kernel(int grid, const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
+                                     const AttnParams& p, bool pdl, cudaStream_t stream) {
+    // the opt-in shared-memory size is a per-device function attribute
+    static uint64_t configured_devices = 0;
+    int dev = 0;
+    IFX_CUDA_OK(cudaGetDevice(&dev));
+    if (dev >= 64 || !(configured_devices & (1ull << dev))) {
+        IFX_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+        if (dev < 64) configured_devices |= 1ull << dev;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(grid));
+    cfg.blockDim = dim3(kAttnThreads);
+    cfg.dynamicSmemBytes = kAttnSmem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    IFX_CUDA_OK(cudaLaunchKernelEx(&cfg, attn_fwd_kernel, tmQ, tmK, tmV, p));
+    return IFX_OK;
+}
+
+// scratch for the split partials of the tail wave, one per device (grown on demand; launches of one device are
+// expected on one stream at a time — see the header: handles and scratch are not thread-safe)
+struct PartScratch {
+    float* ptr = nullptr;
+    size_t bytes = 0;
+};
+static PartScratch g_part[64];
 
 static ifx_status attention_launch(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, void* out,
                                    int64_t ldo, int64_t q_rows, int64_t kv_rows, int32_t heads, int32_t head_dim,
-                                   float softmax_scale, cudaStream_t stream, int32_t kv_heads = 0) {
+                                   float softmax_scale, cudaStream_t stream, int32_t kv_heads = 0,
+                                   const KeySpec* keys = nullptr) {
     if (kv_heads <= 0) kv_heads = heads;
     IFX_CHECK_ARG(heads % kv_heads == 0, "ifx_attention: heads (%d) must be a multiple of kv_heads (%d)", heads, kv_heads);
     IFX_CHECK_ARG(q && k && v && out, "ifx_attention: null pointer");
@@ -451,11 +625,6 @@ static ifx_status attention_launch(const void* q, int64_t ldq, const void* k, co
     st = make_tmap_bf16_2d(&tmV, v, (uint64_t)kv_width, (uint64_t)kv_rows, (uint64_t)ldkv, 64, kKT);
     if (st != IFX_OK) return st;
 
-    static bool configured = false;
-    if (!configured) {
-        IFX_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
-        configured = true;
-    }
     AttnParams p;
     fill_defaults(p);
     p.q_rows = static_cast<int32_t>(q_rows);
@@ -468,11 +637,16 @@ static ifx_status attention_launch(const void* q, int64_t ldq, const void* k, co
     p.ldo = ldo;
     p.part_o = nullptr;
     p.part_ml = nullptr;
+    const int n_kv = fill_keys(p, keys, kv_rows);
+    int64_t key_rows = kv_rows;
+    if (p.n_ext) {
+        key_rows = 0;
+        for (int i = 0; i < p.n_ext; ++i) key_rows += p.ext_rows[i];
+    }
 
     // ---- grid shaping: split the items of the last partial wave along the keys
     const int items = p.num_q_pairs * heads;
     const int sms = sm_count();
-    const int n_kv = static_cast<int>((kv_rows + kKT - 1) / kKT);
     int rem = items % sms;
     int split = 1;
     if (rem != 0 && n_kv >= 2 * kMaxSplit) {
@@ -491,23 +665,28 @@ static ifx_status attention_launch(const void* q, int64_t ldq, const void* k, co
     p.split = split;
     const int pieces = rem * split;
     if (pieces > 0) {
+        int dev = 0;
+        IFX_CUDA_OK(cudaGetDevice(&dev));
+        IFX_CHECK_ARG(dev < 64, "ifx_attention: device ordinal %d not supported", dev);
+        PartScratch& sc = g_part[dev];
         const size_t need = static_cast<size_t>(pieces) * (2 * kQT) * (kHD + 2) * sizeof(float);
-        if (need > g_part_bytes) {
-            if (g_part) IFX_CUDA_OK(cudaFree(g_part));
-            g_part = nullptr;
-            g_part_bytes = 0;
-            IFX_CUDA_OK(cudaMalloc(&g_part, need));
-            g_part_bytes = need;
+        if (need > sc.bytes) {
+            if (sc.ptr) IFX_CUDA_OK(cudaFree(sc.ptr));
+            sc.ptr = nullptr;
+            sc.bytes = 0;
+            IFX_CUDA_OK(cudaMalloc(&sc.ptr, need));
+            sc.bytes = need;
         }
-        p.part_o = g_part;
-        p.part_ml = g_part + static_cast<size_t>(pieces) * (2 * kQT) * kHD;
+        p.part_o = sc.ptr;
+        p.part_ml = sc.ptr + static_cast<size_t>(pieces) * (2 * kQT) * kHD;
     }
     const int grid = p.n_whole + pieces;
     {
         char label[96];
-        snprintf(label, sizeof(label), "attn_fwd_kernel[Lq=%d,Lk=%d,H=%d]", p.q_rows, p.kv_rows, heads);
+        snprintf(label, sizeof(label), "attn_fwd_kernel[Lq=%d,Lk=%lld,H=%d]", p.q_rows, (long long)key_rows, heads);
         ProfScope prof(label, stream);
-        attn_fwd_kernel<<<grid, kAttnThreads, kAttnSmem, stream>>>(tmQ, tmK, tmV, p);
+        st = launch_attn_kernel(grid, tmQ, tmK, tmV, p, keys != nullptr && keys->pdl, stream);
+        if (st != IFX_OK) return st;
         if (pieces > 0) attn_combine_kernel<<<rem * (2 * kQT) / 8, 256, 0, stream>>>(p);
     }
     IFX_LAUNCH_OK("attn_fwd_kernel");
@@ -515,13 +694,42 @@ static ifx_status attention_launch(const void* q, int64_t ldq, const void* k, co
     return IFX_OK;
 }
 
-static void fill_defaults(AttnParams& p) {
-    p.partial = 0;
-    p.pieces_per_item = p.piece_count = 1;
-    p.piece_first = 0;
-    p.n_ext = 0;
-    for (int i = 0; i < 4; ++i) p.ext_row0[i] = p.ext_rows[i] = 0;
-    for (int i = 0; i < 5; ++i) p.ext_tile0[i] = 0;
+// Key extents of a paged cache: runs of physically consecutive valid pages, the pages of `fresh` (if any) last.
+// Softmax attention does not depend on the key order, so the pages are visited in physical order.
+static ifx_status kv_key_spec(const KvImpl* kv, const ifx_kv_plan* fresh, KeySpec& ks) {
+    const int64_t pt = kv->page_tokens;
+    std::vector<int32_t> old_pages, new_pages;
+    if (fresh != nullptr) new_pages.assign(fresh->pages, fresh->pages + fresh->num_pages);
+    const size_t n_valid = static_cast<size_t>(kv->local_end / pt);   // logical pages [0, n_valid) hold the window
+    for (size_t lp = 0; lp < n_valid && lp < kv->table.size(); ++lp) {
+        const int32_t pg = kv->table[lp];
+        bool is_new = false;
+        for (int32_t n : new_pages) is_new = is_new || (n == pg);
+        if (!is_new) old_pages.push_back(pg);
+    }
+    std::sort(old_pages.begin(), old_pages.end());
+    std::sort(new_pages.begin(), new_pages.end());
+    ks.n_ext = 0;
+    auto add_runs = [&](const std::vector<int32_t>& pages) -> bool {
+        size_t i = 0;
+        while (i < pages.size()) {
+            size_t j = i + 1;
+            while (j < pages.size() && pages[j] == pages[j - 1] + 1) ++j;
+            if (ks.n_ext == kMaxExt) return false;
+            ks.row0[ks.n_ext] = static_cast<int32_t>(pages[i] * pt);
+            ks.rows[ks.n_ext] = static_cast<int32_t>(static_cast<int64_t>(j - i) * pt);
+            ++ks.n_ext;
+            i = j;
+        }
+        return true;
+    };
+    if (!add_runs(old_pages)) return set_error(IFX_ERR_UNSUPPORTED, "attention: more than %d page runs in the block table", kMaxExt);
+    ks.n_old_ext = fresh != nullptr ? ks.n_ext : -1;
+    if (!add_runs(new_pages)) return set_error(IFX_ERR_UNSUPPORTED, "attention: more than %d page runs in the block table", kMaxExt);
+    // the common case — valid pages are the physical prefix, nothing to wait for — is one dense extent whose tensor
+    // map ends at local_end (TMA zero-fills the last partial tile; no tail fix-up needed)
+    if (fresh == nullptr && ks.n_ext == 1 && ks.row0[0] == 0) ks.n_ext = 0;
+    return IFX_OK;
 }
 
 }  // namespace ifx
@@ -536,7 +744,7 @@ extern "C" ifx_status ifx_attention_partial(const void* q, int64_t ldq, const vo
                                             void* stream) {
     IFX_CHECK_ARG(q && k && v && extents && workspace, "ifx_attention_partial: null pointer");
     IFX_CHECK_ARG(head_dim == kHD, "ifx_attention_partial: head_dim must be 128");
-    IFX_CHECK_ARG(n_ext >= 1 && n_ext <= 4, "ifx_attention_partial: 1..4 key extents (got %d)", n_ext);
+    IFX_CHECK_ARG(n_ext >= 1 && n_ext <= kMaxExt, "ifx_attention_partial: 1..%d key extents (got %d)", kMaxExt, n_ext);
     if (kv_heads <= 0) kv_heads = heads;
     IFX_CHECK_ARG(heads > 0 && heads % kv_heads == 0, "ifx_attention_partial: bad head counts");
     IFX_CHECK_ARG(q_rows > 0 && q_rows < (1ll << 31) && kv_rows_total > 0 && kv_rows_total < (1ll << 31),
@@ -547,19 +755,17 @@ extern "C" ifx_status ifx_attention_partial(const void* q, int64_t ldq, const vo
                   piece_first + piece_count, pieces_per_item);
     const int64_t width = static_cast<int64_t>(heads) * head_dim, kv_width = static_cast<int64_t>(kv_heads) * head_dim;
     IFX_CHECK_ARG(ldq >= width && ldkv >= kv_width && ldq % 8 == 0 && ldkv % 8 == 0, "ifx_attention_partial: strides");
-    AttnParams p;
-    fill_defaults(p);
-    p.n_ext = n_ext;
-    int tiles = 0;
+    KeySpec ks;
+    ks.n_ext = n_ext;
     for (int i = 0; i < n_ext; ++i) {
         const int64_t r0 = extents[2 * i], n = extents[2 * i + 1];
         IFX_CHECK_ARG(r0 >= 0 && n > 0 && r0 + n <= kv_rows_total, "ifx_attention_partial: extent %d out of range", i);
-        p.ext_row0[i] = static_cast<int32_t>(r0);
-        p.ext_rows[i] = static_cast<int32_t>(n);
-        p.ext_tile0[i] = tiles;
-        tiles += static_cast<int>((n + kKT - 1) / kKT);
+        ks.row0[i] = static_cast<int32_t>(r0);
+        ks.rows[i] = static_cast<int32_t>(n);
     }
-    for (int i = n_ext; i < 5; ++i) p.ext_tile0[i] = tiles;
+    AttnParams p;
+    fill_defaults(p);
+    const int tiles = fill_keys(p, &ks, kv_rows_total);
     IFX_CHECK_ARG(tiles >= piece_count, "ifx_attention_partial: more pieces (%d) than key tiles (%d)", piece_count, tiles);
     p.q_rows = static_cast<int32_t>(q_rows);
     p.kv_rows = static_cast<int32_t>(kv_rows_total);
@@ -589,13 +795,13 @@ extern "C" ifx_status ifx_attention_partial(const void* q, int64_t ldq, const vo
     if (st != IFX_OK) return st;
     st = make_tmap_bf16_2d(&tmV, v, (uint64_t)kv_width, (uint64_t)kv_rows_total, (uint64_t)ldkv, 64, kKT);
     if (st != IFX_OK) return st;
-    IFX_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     {
         char label[96];
         snprintf(label, sizeof(label), "attn_fwd_kernel<partial>[Lq=%d,tiles=%d,H=%d]", p.q_rows, tiles, heads);
         ProfScope prof(label, s);
-        attn_fwd_kernel<<<items * piece_count, kAttnThreads, kAttnSmem, s>>>(tmQ, tmK, tmV, p);
+        st = launch_attn_kernel(items * piece_count, tmQ, tmK, tmV, p, false, s);
+        if (st != IFX_OK) return st;
     }
     IFX_LAUNCH_OK("attn_fwd_kernel<partial>");
     return IFX_OK;
@@ -641,14 +847,65 @@ extern "C" ifx_status ifx_attention_gqa(const void* q, int64_t ldq, const void* 
                             static_cast<cudaStream_t>(stream), kv_heads);
 }
 
-extern "C" ifx_status ifx_attention_kv(const void* q, int64_t ldq, const ifx_kv* kv_, void* out, int64_t ldo,
-                                       int64_t q_rows, float softmax_scale, void* stream) {
+extern "C" ifx_status ifx_attention_extents(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv,
+                                            int64_t kv_rows_total, const int64_t* extents, int32_t n_ext, void* out,
+                                            int64_t ldo, int64_t q_rows, int32_t heads, int32_t kv_heads,
+                                            int32_t head_dim, float softmax_scale, void* stream) {
+    IFX_CHECK_ARG(extents != nullptr && n_ext >= 1 && n_ext <= kMaxExt, "ifx_attention_extents: 1..%d key extents (got %d)",
+                  kMaxExt, n_ext);
+    IFX_CHECK_ARG(kv_rows_total > 0 && kv_rows_total < (1ll << 31), "ifx_attention_extents: bad kv_rows_total");
+    KeySpec ks;
+    ks.n_ext = n_ext;
+    for (int i = 0; i < n_ext; ++i) {
+        const int64_t r0 = extents[2 * i], n = extents[2 * i + 1];
+        IFX_CHECK_ARG(r0 >= 0 && n > 0 && r0 + n <= kv_rows_total, "ifx_attention_extents: extent %d out of range", i);
+        ks.row0[i] = static_cast<int32_t>(r0);
+        ks.rows[i] = static_cast<int32_t>(n);
+    }
+    return attention_launch(q, ldq, k, v, ldkv, out, ldo, q_rows, kv_rows_total, heads, head_dim, softmax_scale,
+                            static_cast<cudaStream_t>(stream), kv_heads, &ks);
+}
+
+namespace ifx {
+ifx_status attention_kv_launch(const void* q, int64_t ldq, const ifx_kv* kv_, void* out, int64_t ldo, int64_t q_rows,
+                               float softmax_scale, const ifx_kv_plan* fresh, const int64_t* flags, int32_t world,
+                               int64_t epoch, int32_t timeout_ms, bool pdl, cudaStream_t stream) {
     const KvImpl* kv = kv_cast(kv_);
     if (!kv) return set_error(IFX_ERR_HANDLE, "ifx_attention_kv: bad kv handle");
     IFX_CHECK_ARG(kv->local_end > 0, "ifx_attention_kv: cache is empty");
-    // the allocator keeps valid pages as the physical prefix, and attention is invariant to key order,
-    // so the logical window [0, local_end) is read as one dense extent.
+    IFX_CHECK_ARG(kv->local_end % kv->page_tokens == 0 &&
+                      kv->local_end <= static_cast<int64_t>(kv->table.size()) * kv->page_tokens,
+                  "ifx_attention_kv: the valid window (%lld tokens) must be whole mapped pages", (long long)kv->local_end);
+    KeySpec ks;
+    ifx_status st = kv_key_spec(kv, fresh, ks);
+    if (st != IFX_OK) return st;
+    if (fresh != nullptr) {
+        IFX_CHECK_ARG(flags != nullptr && world >= 1 && world <= IFX_MAX_PEERS && epoch > 0 && timeout_ms > 0,
+                      "ifx_attention_kv_wait: bad flags / world / epoch / timeout");
+        ks.flags = reinterpret_cast<const long long*>(flags);
+        ks.world = world;
+        ks.epoch = epoch;
+        ks.timeout_ns = static_cast<unsigned long long>(timeout_ms) * 1000000ull;
+    }
+    ks.pdl = pdl;
     const int64_t width = static_cast<int64_t>(kv->heads) * kv->head_dim;
-    return attention_launch(q, ldq, kv->k_base, kv->v_base, width, out, ldo, q_rows, kv->local_end, kv->heads,
-                            kv->head_dim, softmax_scale, static_cast<cudaStream_t>(stream));
+    // dense: the tensor map ends at local_end; extents: it covers the whole buffer
+    const int64_t map_rows = ks.n_ext == 0 ? kv->local_end : static_cast<int64_t>(kv->num_pages) * kv->page_tokens;
+    return attention_launch(q, ldq, kv->k_base, kv->v_base, width, out, ldo, q_rows, map_rows, kv->heads, kv->head_dim,
+                            softmax_scale, stream, 0, &ks);
+}
+}  // namespace ifx
+
+extern "C" ifx_status ifx_attention_kv(const void* q, int64_t ldq, const ifx_kv* kv_, void* out, int64_t ldo,
+                                       int64_t q_rows, float softmax_scale, void* stream) {
+    return attention_kv_launch(q, ldq, kv_, out, ldo, q_rows, softmax_scale, nullptr, nullptr, 0, 0, 0, false,
+                               static_cast<cudaStream_t>(stream));
+}
+
+extern "C" ifx_status ifx_attention_kv_wait(const void* q, int64_t ldq, const ifx_kv* kv_, const ifx_kv_plan* fresh,
+                                            const int64_t* flags, int32_t world, int64_t epoch, int32_t timeout_ms,
+                                            void* out, int64_t ldo, int64_t q_rows, float softmax_scale, void* stream) {
+    IFX_CHECK_ARG(fresh != nullptr, "ifx_attention_kv_wait: the plan naming the in-flight pages is required");
+    return attention_kv_launch(q, ldq, kv_, out, ldo, q_rows, softmax_scale, fresh, flags, world, epoch, timeout_ms, false,
+                               static_cast<cudaStream_t>(stream));
 }

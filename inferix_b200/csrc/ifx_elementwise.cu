@@ -237,17 +237,6 @@ struct NormRopeParams {
     int32_t local_only;      // 1: store into this rank's cache only and publish nothing (ifx_peer_push does the exchange)
 };
 
-// relaxed system-scope store; the caller issues ONE __threadfence_system() before the flag stores (fence + relaxed
-// store = release pattern), instead of a membar per destination rank as st.release.sys would emit
-__device__ __forceinline__ void st_relaxed_sys(long long* p, long long v) {
-    asm volatile("st.relaxed.sys.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ long long ld_acquire_sys(const long long* p) {
-    long long v;
-    asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-
 // pair index inside a head -> which RoPE axis it rotates with (causal_model.py:37: split [c-2(c/3), c/3, c/3])
 __device__ __forceinline__ int rope_pos(int pair, int half, int t_pos, int h_pos, int w_pos) {
     const int third = half / 3;
@@ -452,23 +441,41 @@ struct PeerPushParams {
 
 __global__ void __launch_bounds__(1024)
 peer_push_kernel(const PeerPushParams p) {
+    // the attention kernel that follows on the stream is launched programmatically behind this grid: let it start
+    // right away (it needs nothing this grid writes locally; the rows it must wait for are ordered by the epoch flags)
+    griddep_launch();
     const int nvec = p.C >> 3;
     const int64_t rows = static_cast<int64_t>(p.frames) * p.chunk;
     const int64_t fs_full = static_cast<int64_t>(p.world) * p.chunk;
     const int64_t total = rows * nvec * 2;                               // K and V
     const __nv_bfloat16* src[2] = {p.peer_k[p.rank], p.peer_v[p.rank]};
-    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
-         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        const int which = static_cast<int>(i / (rows * nvec));
-        const int64_t r = (i / nvec) % rows;
-        const int vi = static_cast<int>(i % nvec);
-        const int64_t tb = (r / p.chunk) * fs_full + static_cast<int64_t>(p.rank) * p.chunk + r % p.chunk;
-        const int64_t crow = static_cast<int64_t>(p.pl.pages[tb / p.page_tokens]) * p.page_tokens + tb % p.page_tokens;
-        const uint4 val = reinterpret_cast<const uint4*>(src[which] + crow * p.C)[vi];
+    constexpr int kUnroll = 4;                                           // 16-byte loads in flight per thread
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t i0 = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i0 < total; i0 += stride * kUnroll) {
+        uint4 val[kUnroll];
+        int64_t off[kUnroll];
+        int which[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const int64_t i = i0 + u * stride;
+            off[u] = -1;
+            if (i < total) {
+                which[u] = static_cast<int>(i / (rows * nvec));
+                const int64_t r = (i / nvec) % rows;
+                const int vi = static_cast<int>(i % nvec);
+                const int64_t tb = (r / p.chunk) * fs_full + static_cast<int64_t>(p.rank) * p.chunk + r % p.chunk;
+                const int64_t crow =
+                    static_cast<int64_t>(p.pl.pages[tb / p.page_tokens]) * p.page_tokens + tb % p.page_tokens;
+                off[u] = crow * p.C + vi * 8;
+                val[u] = *reinterpret_cast<const uint4*>(src[which[u]] + off[u]);
+            }
+        }
         for (int d = 1; d < p.world; ++d) {
-            const int dst = (p.rank + d) % p.world;
-            __nv_bfloat16* base = which ? p.peer_v[dst] : p.peer_k[dst];
-            reinterpret_cast<uint4*>(base + crow * p.C)[vi] = val;
+            const int dst = (p.rank + d) % p.world;                      // start at the neighbour: spread the links
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u)
+                if (off[u] >= 0)
+                    *reinterpret_cast<uint4*>((which[u] ? p.peer_v[dst] : p.peer_k[dst]) + off[u]) = val[u];
         }
     }
     __threadfence_system();

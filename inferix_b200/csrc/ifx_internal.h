@@ -93,6 +93,12 @@ struct PagedCopyParams {
 };
 ifx_status launch_paged_copy(const PagedCopyParams& p, cudaStream_t stream);
 
+// attention over a paged cache; fresh != nullptr: the plan's pages sit behind the flag wait (ifx_attention_kv_wait);
+// pdl: programmatic stream serialization (the kernel may start before its predecessor on the stream has finished)
+ifx_status attention_kv_launch(const void* q, int64_t ldq, const ifx_kv* kv, void* out, int64_t ldo, int64_t q_rows,
+                               float softmax_scale, const ifx_kv_plan* fresh, const int64_t* flags, int32_t world,
+                               int64_t epoch, int32_t timeout_ms, bool pdl, cudaStream_t stream);
+
 constexpr uint32_t kKvMagic = 0x4B564958u;  // "XIVK"
 KvImpl* kv_cast(ifx_kv* kv);
 const KvImpl* kv_cast(const ifx_kv* kv);

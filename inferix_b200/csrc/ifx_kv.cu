@@ -31,17 +31,6 @@ static int32_t take_page(KvImpl* kv) {
     return -1;
 }
 
-// valid pages must be exactly the physical prefix [0, table.size())
-static bool is_prefix(const KvImpl* kv) {
-    const size_t n = kv->table.size();
-    std::vector<char> seen(n, 0);
-    for (int32_t p : kv->table) {
-        if (p < 0 || static_cast<size_t>(p) >= n || seen[p]) return false;
-        seen[p] = 1;
-    }
-    return true;
-}
-
 }  // namespace ifx
 
 using namespace ifx;
@@ -159,9 +148,6 @@ extern "C" ifx_status ifx_kv_plan_append(ifx_kv* kv_, int64_t current_start, int
     kv->next_fresh = next_fresh;
     kv->global_end = current_end;
     kv->local_end = local_end_new;
-    if (!is_prefix(kv))
-        return set_error(IFX_ERR_UNSUPPORTED,
-                         "ifx_kv_plan_append: valid pages no longer form a physical prefix; ifx_kv_reset() first");
 
     plan->local_start = local_start;
     plan->local_end = local_end_new;

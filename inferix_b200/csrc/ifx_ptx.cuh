@@ -251,6 +251,24 @@ __device__ __forceinline__ float ex2_poly(float x) {
     return __int_as_float(__float_as_int(r) + (__float_as_int(t) << 23));
 }
 
+// ---------------------------------------------------------------- system-scope flags (peer-memory exchange)
+// relaxed system-scope store; the caller issues ONE __threadfence_system() before the flag stores (fence + relaxed
+// store = release pattern), instead of a membar per destination rank as st.release.sys would emit
+__device__ __forceinline__ void st_relaxed_sys(long long* p, long long v) {
+    asm volatile("st.relaxed.sys.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ long long ld_acquire_sys(const long long* p) {
+    long long v;
+    asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// ---------------------------------------------------------------- programmatic dependent launch
+// griddep_wait: block until every kernel this one was programmatically launched behind has completed and its memory
+// is visible (no-op for a normal launch).  griddep_launch: allow the dependent kernel's CTAs to be scheduled.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 template <int kRegs>
 __device__ __forceinline__ void setmaxnreg_inc() {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs));

@@ -15,7 +15,7 @@ from ._lib import EPI_BIAS, EPI_BIAS_F32, EPI_BIAS_GATE_RES, EPI_BIAS_GELU, EPI_
 
 __all__ = [
     "ln_modulate", "gemm", "rmsnorm", "quantize_fp8", "ln_modulate_fp8", "gemm_fp8", "attention", "attention_gqa", "attention_ranges", "attention_partial", "attention_combine",
-    "attention_workspace_bytes", "qk_norm_rope_append", "PagedKV", "rope_table",
+    "attention_workspace_bytes", "attention_extents", "qk_norm_rope_append", "PagedKV", "rope_table",
     "EPI_BIAS", "EPI_BIAS_GELU", "EPI_BIAS_GATE_RES", "EPI_BIAS_GELU_ERF", "EPI_BIAS_F32",
     "qk_norm_rope_append_peers", "peer_push", "magi_qkv_post", "head_layernorm", "gate_norm_residual", "silu_mul",
 ]
@@ -255,6 +255,24 @@ def attention_combine(workspace, pieces_per_item, out, heads):
     return out
 
 
+def attention_extents(q, k, v, extents, heads, out=None, *, kv_heads=None, softmax_scale=None):
+    """q [Lq, heads*D] against the key-row extents [(row0, rows), ...] of k/v (runs of consecutive cache pages).  Rows
+    that follow an extent in memory are never attended, whatever they hold."""
+    q, k, v = _bf16_2d(q, "q"), _bf16_2d(k, "k"), _bf16_2d(v, "v")
+    kv_heads = kv_heads or heads
+    head_dim = q.shape[1] // heads
+    if k.shape != v.shape or k.stride(0) != v.stride(0):
+        raise ValueError("attention_extents: k and v must have identical shape / stride")
+    if out is None:
+        out = torch.empty((q.shape[0], q.shape[1]), dtype=torch.bfloat16, device=q.device)
+    ext = (C.c_int64 * (2 * len(extents)))(*[int(x) for e in extents for x in e])
+    scale = softmax_scale if softmax_scale is not None else head_dim ** -0.5
+    _lib.check(_lib.load().ifx_attention_extents(
+        q.data_ptr(), q.stride(0), k.data_ptr(), v.data_ptr(), k.stride(0), k.shape[0], ext, len(extents),
+        out.data_ptr(), out.stride(0), q.shape[0], heads, kv_heads, head_dim, scale, _stream()))
+    return out
+
+
 def attention_workspace_bytes(q_rows: int, heads: int, pieces_per_item: int) -> int:
     return heads * ((q_rows + 255) // 256) * pieces_per_item * 256 * 130 * 4
 
@@ -355,13 +373,24 @@ class PagedKV:
         _lib.check(_lib.load().ifx_kv_import(self.handle, k_rows.data_ptr(), v_rows.data_ptr(), start,
                                              k_rows.shape[0], _stream()))
 
-    def attention(self, q: torch.Tensor, out=None, *, softmax_scale=None):
+    def attention(self, q: torch.Tensor, out=None, *, softmax_scale=None, fresh: Optional[KvPlan] = None,
+                  flags: Optional[torch.Tensor] = None, epoch: int = 0, timeout_ms: int = 60000):
+        """Attention of q over the cached window, read through the block table.  With `fresh` (the plan of the block
+        being appended) and `flags` (int64 [world] epoch flags of the peer-memory exchange) the fresh pages are
+        attended last, after every rank's flag reached `epoch` (ifx_attention_kv_wait)."""
         q = _bf16_2d(q, "q")
         if out is None:
             out = torch.empty((q.shape[0], self.heads * self.head_dim), dtype=torch.bfloat16, device=q.device)
         scale = softmax_scale if softmax_scale is not None else self.head_dim ** -0.5
-        _lib.check(_lib.load().ifx_attention_kv(q.data_ptr(), q.stride(0), self.handle, out.data_ptr(), out.stride(0),
-                                                q.shape[0], scale, _stream()))
+        if fresh is None:
+            _lib.check(_lib.load().ifx_attention_kv(q.data_ptr(), q.stride(0), self.handle, out.data_ptr(),
+                                                    out.stride(0), q.shape[0], scale, _stream()))
+        else:
+            if flags is None or flags.dtype != torch.int64 or not flags.is_cuda or not flags.is_contiguous():
+                raise ValueError("flags must be a contiguous CUDA int64 vector (one epoch flag per rank)")
+            _lib.check(_lib.load().ifx_attention_kv_wait(
+                q.data_ptr(), q.stride(0), self.handle, C.byref(fresh), flags.data_ptr(), flags.numel(), int(epoch),
+                int(timeout_ms), out.data_ptr(), out.stride(0), q.shape[0], scale, _stream()))
         return out
 
 

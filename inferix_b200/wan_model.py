@@ -178,9 +178,10 @@ class CausalWanAttentionBlock(nn.Module):
     def forward(self, x, e, seq_lens, grid_sizes, freqs, context, context_lens, block_mask, kv_cache_meta=None,
                 crossattn_cache_meta=None, current_start=0, cache_start=None,
                 kv_cache_manager: Optional[KVCacheManager] = None,
-                kv_cache_requests: Optional[List[KVCacheRequest]] = None, workspace=None):
+                kv_cache_requests: Optional[List[KVCacheRequest]] = None, workspace=None, mod=None):
         """x [B, L, C]; e [B, F, 6, C]; freqs: float64 (cos, sin) table from ops.rope_table.  Updates x in place and
-        returns it.  kv_cache_meta / crossattn_cache_meta are the reference's per-layer dicts (mutated in place)."""
+        returns it.  kv_cache_meta / crossattn_cache_meta are the reference's per-layer dicts (mutated in place).
+        mod: optional precomputed `modulation + e` [B, F, 6, C] (the model adds all layers' tables in one launch)."""
         if kv_cache_meta is None:
             raise NotImplementedError("only the KV-cached inference branch is built")
         assert kv_cache_manager is not None and kv_cache_requests is not None
@@ -192,7 +193,8 @@ class CausalWanAttentionBlock(nn.Module):
         rank = pc.rank if pc is not None else 0
         f_, h_, w_ = (int(v) for v in grid_sizes[0])
         frame_seqlen = h_ * w_                                    # global tokens per frame (causal_model.py:255)
-        mod = (self.modulation.unsqueeze(1) + e).contiguous()     # [B, F, 6, C]   causal_model.py:412
+        if mod is None:
+            mod = (self.modulation.unsqueeze(1) + e).contiguous() # [B, F, 6, C]   causal_model.py:412
         ws = workspace if workspace is not None else _Workspace(rows, c, self.ffn_dim, x.device)
         stream = torch.cuda.current_stream().cuda_stream
         lib = _lib.load()
@@ -209,7 +211,9 @@ class CausalWanAttentionBlock(nn.Module):
             xb = x[bi]
             if not xb.is_contiguous():
                 raise ValueError("x must be contiguous per sample")
-            if world == 1 and getattr(self, "_fp8", None) is None and self._amax is None:
+            peer_dst = getattr(store, "peer", None) if world > 1 else None
+            native_block = getattr(self, "_fp8", None) is None and self._amax is None
+            if native_block and (world == 1 or (peer_dst is not None and _SP_MODE in ("overlap", "store"))):
                 io = WanBlockIO()
                 io.x, io.rows, io.tokens_per_frame = xb.data_ptr(), rows, fs
                 io.mod, io.freqs, io.grid = mod[bi].data_ptr(), freqs.data_ptr(), grid
@@ -218,7 +222,16 @@ class CausalWanAttentionBlock(nn.Module):
                 io.ws_h, io.ws_qkv, io.ws_q = ws.h.data_ptr(), ws.qkv.data_ptr(), ws.q.data_ptr()
                 io.ws_attn, io.ws_ffn = ws.attn.data_ptr(), ws.ffn.data_ptr()
                 plan = KvPlan()
-                _lib.check(lib.ifx_wan_block_forward(C.byref(w), C.byref(io), C.byref(plan), stream))
+                if world == 1:
+                    _lib.check(lib.ifx_wan_block_forward(C.byref(w), C.byref(io), C.byref(plan), stream))
+                else:
+                    # sequence parallel: ONE call per layer, the K/V exchange over peer memory inside it
+                    from . import peer as _peer
+                    peer_dst.epoch = store.peer_group.next_epoch()
+                    mode = _lib.IFX_SP_OVERLAP if _SP_MODE == "overlap" else _lib.IFX_SP_STORE
+                    _lib.check(lib.ifx_wan_block_forward_sp(C.byref(w), C.byref(io), C.byref(peer_dst), mode,
+                                                            _sp_push_ctas(world), _peer.WAIT_TIMEOUT_MS,
+                                                            C.byref(plan), stream))
             else:
                 plan = self._forward_ops(xb, mod[bi], fs, frames, grid, freqs, store, cstore, current_start,
                                          sink_tokens, windowed, ws, qkv_w, qkv_b, pc, amax=self._amax)
@@ -384,6 +397,24 @@ class CausalWanAttentionBlock(nn.Module):
         return plan
 
 
+# IFX_SP_MODE selects how the sequence-parallel layer exchanges the block's new K / V over peer memory:
+#   overlap (default) one C-ABI call per layer; the rows travel behind the attention over the cached window
+#                     (push grid + programmatically launched attention with an in-kernel flag wait)
+#   store             one C-ABI call per layer; the norm+RoPE kernel stores into every rank's cache, then a wait kernel
+#   ops               the round-1 op-by-op path below (also what FP8 / calibration / the NCCL fallback use)
+_SP_MODE = __import__("os").environ.get("IFX_SP_MODE", "overlap")
+if _SP_MODE not in ("overlap", "store", "ops"):
+    raise ValueError(f"IFX_SP_MODE={_SP_MODE!r}: expected overlap, store or ops")
+
+
+def _sp_push_ctas(world: int) -> int:
+    """CTAs of the push grid: the attention grid leaves these SMs free at 4-8 ranks (132 / 144 of 148 CTAs)."""
+    env = __import__("os").environ.get("IFX_SP_PUSH_CTAS")
+    if env:
+        return max(1, int(env))
+    return {2: 8, 4: 16}.get(world, 4)
+
+
 # IFX_SP_OVERLAP=1 turns on the exchange/compute overlap of the sequence-parallel path: local queries attend the pages
 # already in the cache (phase 1) while the all-gather of the new K/V runs on a side stream, then the new pages
 # (phase 2), merged by attn_combine_kernel.  Off by default: measured 4 % SLOWER at 2 GPUs (the gather is only
@@ -491,6 +522,7 @@ class CausalWanModel(nn.Module):
                                 rope_params(1024, 2 * (d // 6))], dim=1)          # complex128, causal_model.py:634-641
         self._freqs_table = None
         self._workspace = None
+        self._mod_table = None        # [layers, 1, 1, 6, C] stack of the blocks' modulation parameters
         self.block_mask = None
         self.num_frame_per_block = 1
         self.independent_first_frame = False
@@ -499,6 +531,7 @@ class CausalWanModel(nn.Module):
         out = super().load_state_dict(state_dict, strict=strict, assign=assign)
         for blk in self.blocks:
             blk.invalidate_packed()
+        self._mod_table = None
         return out
 
     def _apply(self, fn, *a, **k):
@@ -507,6 +540,7 @@ class CausalWanModel(nn.Module):
             blk.invalidate_packed()
         self._freqs_table = None
         self._workspace = None
+        self._mod_table = None
         return out
 
     # ------------------------------------------------------------------ FP8
@@ -565,12 +599,16 @@ class CausalWanModel(nn.Module):
                 [torch.cat([u, u.new_zeros(self.text_len - u.size(0), u.size(1))]) for u in context]))
 
         ws = self._get_workspace(x.shape[1], device)
+        # every layer's `modulation + e` (causal_model.py:412) in one launch: [layers, B, F, 6, C]
+        if self._mod_table is None:
+            self._mod_table = torch.stack([blk.modulation for blk in self.blocks]).unsqueeze(2).detach()
+        mods = self._mod_table + e0.unsqueeze(0)
         for i, block in enumerate(self.blocks):
             x = block(x, e=e0, seq_lens=None, grid_sizes=grid_sizes, freqs=self._freqs_table, context=ctx,
                       context_lens=None, block_mask=None, kv_cache_meta=kv_cache_meta[i],
                       crossattn_cache_meta=crossattn_cache_meta[i], current_start=current_start,
                       cache_start=cache_start, kv_cache_manager=kv_cache_manager,
-                      kv_cache_requests=kv_cache_requests, workspace=ws)
+                      kv_cache_requests=kv_cache_requests, workspace=ws, mod=mods[i])
 
         x = self.head(x, e.unflatten(dim=0, sizes=t.shape).unsqueeze(2))             # [B, F, hw/P, 64]
         x = x.flatten(1, 2)

@@ -1,0 +1,118 @@
+"""Attention read through the block table: extent lists, non-prefix tables, poisoned unmapped pages, and the in-kernel
+wait for pages that are still being written (the sequence-parallel exchange) — all on one GPU, through the C ABI."""
+import pytest
+import torch
+
+from inferix_b200 import _lib, ops
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda", 0)
+
+
+def rel_l2(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return ((a - b).norm() / b.norm()).item()
+
+
+def sdpa_ref(q, k, v, heads):
+    """fp32 softmax attention (the oracle's SDPA branch, flash_attention.py:185-199) on [L, H*D] tensors."""
+    d = q.shape[1] // heads
+    qh, kh, vh = (t.float().view(t.shape[0], heads, d).transpose(0, 1) for t in (q, k, v))
+    o = torch.nn.functional.scaled_dot_product_attention(qh, kh, vh)
+    return o.transpose(0, 1).reshape(q.shape[0], heads * d)
+
+
+@pytest.mark.parametrize("page_tokens,extent_pages", [(200, [(0, 2), (5, 1), (3, 1)]), (1560, [(1, 2), (4, 1)]),
+                                                     (100, [(i, 1) for i in range(0, 40, 2)])])
+def test_attention_extents_ignore_poisoned_pages(page_tokens, extent_pages):
+    """Key extents whose length is not a multiple of the 128-key tile: the rows that follow an extent in memory belong
+    to other pages.  Fill every unmapped page with NaN (0 x NaN in the P V product) — the result must be
+    the attention over the mapped rows only."""
+    heads, d, lq = 2, 128, 300
+    num_pages = max(p + n for p, n in extent_pages) + 1
+    g = torch.Generator(device=DEV).manual_seed(0)
+    k = torch.full((num_pages * page_tokens, heads * d), float("nan"), dtype=torch.bfloat16, device=DEV)
+    v = torch.full_like(k, float("nan"))
+    q = torch.randn(lq, heads * d, device=DEV, generator=g).bfloat16()
+    ext, ks, vs = [], [], []
+    for p0, n in extent_pages:
+        r0, rows = p0 * page_tokens, n * page_tokens
+        k[r0:r0 + rows] = torch.randn(rows, heads * d, device=DEV, generator=g).bfloat16()
+        v[r0:r0 + rows] = torch.randn(rows, heads * d, device=DEV, generator=g).bfloat16()
+        ext.append((r0, rows))
+        ks.append(k[r0:r0 + rows])
+        vs.append(v[r0:r0 + rows])
+    out = ops.attention_extents(q, k, v, ext, heads)
+    assert torch.isfinite(out.float()).all(), "unmapped rows leaked into the output"
+    ref = sdpa_ref(q, torch.cat(ks), torch.cat(vs), heads)
+    assert rel_l2(out, ref) <= 4e-3                      # FlashAttention-2 distance (bf16 P), as in test_gpu_kernels
+
+
+def test_attention_kv_reads_non_prefix_table():
+    """A window whose valid pages are NOT the physical prefix (sink page kept, tail dropped after a rotation — the
+    'write position moved backwards' case of ADVICE r1) is attended through the table as page runs."""
+    heads, d, pt, pages = 2, 128, 72, 6
+    store = ops.PagedKV(pages, pt, heads, d, DEV)
+    store.k.fill_(float("nan"))
+    store.v.fill_(float("nan"))
+    g = torch.Generator(device=DEV).manual_seed(1)
+
+    def rows(n):
+        return (torch.randn(n, heads * d, device=DEV, generator=g).bfloat16(),
+                torch.randn(n, heads * d, device=DEV, generator=g).bfloat16())
+    sink = pt
+    plan = store.plan_append(0, 3 * pt, sink, True)
+    store.append(plan, *rows(3 * pt))
+    plan = store.plan_append(3 * pt, 3 * pt, sink, True)
+    store.append(plan, *rows(3 * pt))
+    plan = store.plan_append(6 * pt, 3 * pt, sink, True)          # evicts 3 pages behind the sink, rotates the table
+    store.append(plan, *rows(3 * pt))
+    plan = store.plan_append(7 * pt, pt, sink, True)              # write position moves backwards: tail dropped
+    store.append(plan, *rows(pt))
+    _, local_end, table = store.state()
+    assert sorted(table) != list(range(len(table))), f"expected a non-prefix table, got {table}"
+    q = torch.randn(200, heads * d, device=DEV, generator=g).bfloat16()
+    out = store.attention(q)
+    kl, vl = store.export(0, local_end)                           # logical order, through the same table
+    assert torch.isfinite(kl.float()).all()
+    assert rel_l2(out, sdpa_ref(q, kl, vl, heads)) <= 4e-3
+    assert torch.isfinite(out.float()).all()
+
+
+@pytest.mark.parametrize("lq,pt,old_pages,split_hint", [(300, 200, 9, "whole"), (1350, 450, 21, "split")])
+def test_attention_waits_for_fresh_pages_in_kernel(lq, pt, old_pages, split_hint):
+    """ifx_attention_kv_wait: the fresh pages hold NaN when the attention kernel starts; a second stream writes the
+    real rows and only then raises the epoch flags.  The kernel must attend the cached pages first, acquire the flags,
+    then read the fresh pages — the result equals the plain attention over the final cache."""
+    heads, d = 12, 128
+    pages = old_pages + 3
+    store = ops.PagedKV(pages, pt, heads, d, DEV)
+    g = torch.Generator(device=DEV).manual_seed(2)
+    plan = None
+    for blk in range(pages // 3):
+        plan = store.plan_append(blk * 3 * pt, 3 * pt, 0, True)
+        if blk < pages // 3 - 1:
+            store.append(plan, torch.randn(3 * pt, heads * d, device=DEV, generator=g).bfloat16(),
+                         torch.randn(3 * pt, heads * d, device=DEV, generator=g).bfloat16())
+    k_new = torch.randn(3 * pt, heads * d, device=DEV, generator=g).bfloat16()
+    v_new = torch.randn(3 * pt, heads * d, device=DEV, generator=g).bfloat16()
+    q = torch.randn(lq, heads * d, device=DEV, generator=g).bfloat16()
+    # fresh pages poisoned until the "peer" (a side stream) delivers them
+    poison = torch.full_like(k_new, float("nan"))
+    store.append(plan, poison, poison)
+    flags = torch.zeros(4, dtype=torch.int64, device=DEV)
+    out = torch.empty_like(q)
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream(device=DEV)
+    store.attention(q, out, fresh=plan, flags=flags, epoch=7, timeout_ms=20000)      # main stream: starts, then spins
+    with torch.cuda.stream(side):
+        torch.cuda._sleep(int(2e6))                                                  # ~1 ms: the attention is running
+        store.append(plan, k_new, v_new)
+        flags.fill_(7)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all(), "fresh pages were read before the flags were raised"
+    ref = store.attention(q)                                                         # plain attention, final cache
+    torch.cuda.synchronize()
+    assert rel_l2(out, ref) <= 2e-3                                                  # same kernel, other key order
+    kl, vl = store.export(0, pages * pt)
+    assert rel_l2(out, sdpa_ref(q, kl, vl, heads)) <= 4e-3

@@ -9,11 +9,17 @@ Workload (BASELINE.json configs[1]): Self-Forcing 720p, Wan-1.3B dims, bf16, blo
 timesteps + 1 clean re-run per block, KV window 8 blocks (24 frames = 86 400 tokens), steady state (window full,
 every block evicts three frames).  One "step" = one block.  Synthetic weights / latents (inferix_b200.synthetic).
 
-value   = latent frames / s with the block's noise already in HBM (CUDA events, max over ranks)
+value   = latent frames / s with the block's noise already in HBM (CUDA events, max over ranks); nothing but the
+          pipeline runs inside this region (per-kernel event timing is OFF)
 e2e     = same through the public pipeline call with HOST buffers: pinned noise -> H2D, denoise_block, x0 -> D2H
-roofline= self-attention kernel: algorithmic FLOPs (4 * S * L * C) / its mean device time inside the timed steps,
-          against the sustained bf16 peak of MEASURED_PEAKS.json
+roofline= self-attention kernel: algorithmic FLOPs (4 * S * L * C) / its mean device time, from per-launch CUDA events
+          recorded in a SEPARATE pass of the same steps right after the timed regions (round 1 timed them inside the
+          `value` region, which taxed the headline by two event records per launch), against the sustained bf16 peak
+          of MEASURED_PEAKS.json
 cpu_baseline / --impl reference = the reference's CPU PyTorch path (oracle port) on the host cores, bounded sample.
+ref_gpu = (N = 1) the UNMODIFIED reference on this GPU with flash-attn (tools/ref_gpu_bench.py, baseline/_ref)
+sp_parity = (N > 1) the N-rank pipeline against the single-GPU pipeline on rank 0, same inputs, outside the timed
+          regions: rel-L2 of the latents, bit equality, KV index trace equality (10 blocks at 720p, with eviction)
 """
 from __future__ import annotations
 
@@ -59,6 +65,9 @@ def parse():
     ap.add_argument("--workload", default="self_forcing_720p", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the baseline sample")
+    ap.add_argument("--profile-steps", type=int, default=2, help="steps of the separate per-kernel timing pass")
+    ap.add_argument("--no-ref-gpu", action="store_true", help="skip the reference-on-GPU comparator (N = 1)")
+    ap.add_argument("--no-sp-parity", action="store_true", help="skip the N-rank vs 1-rank parity run (N > 1)")
     return ap.parse_args()
 
 
@@ -209,6 +218,92 @@ def workload_config(args, wl):
             "l2": "per-step working set (KV window + weights, >18 GB) exceeds L2; no explicit flush"}
 
 
+
+def sp_exchange_name(pipe):
+    from inferix_b200 import wan_model
+    if getattr(pipe, "_peer_group", None) is None:
+        return "nccl_all_gather"
+    return {"overlap": "peer_memory_overlap (push grid + attention launched programmatically behind it, flag wait "
+                       "inside the attention kernel before its first fresh-page tile; one C-ABI call per layer)",
+            "store": "peer_memory_store (K/V stored into every rank's cache by the norm+RoPE kernel, wait kernel; one "
+                     "C-ABI call per layer)",
+            "ops": "peer_memory_store, op by op from Python"}[wan_model._SP_MODE]
+
+
+def run_ref_gpu():
+    """The unmodified reference on this GPU (tools/ref_gpu_bench.py, its own process).  Never raises."""
+    tool = ROOT / "tools" / "ref_gpu_bench.py"
+    if not (ROOT / "baseline" / "_ref" / "inferix").exists():
+        return {"unavailable": "baseline/_ref/inferix missing (tools/install_reference.sh)"}
+    try:
+        p = subprocess.run([sys.executable, str(tool), "--offload", "0", "--blocks", "10"], capture_output=True,
+                           text=True, timeout=420)
+        lines = [l for l in p.stdout.splitlines() if l.startswith("{")]
+        if p.returncode != 0 or not lines:
+            return {"unavailable": f"rc={p.returncode}: {p.stderr.strip().splitlines()[-1][:300] if p.stderr.strip() else ''}"}
+        return json.loads(lines[-1])
+    except Exception as ex:  # noqa: BLE001
+        return {"unavailable": repr(ex)[:300]}
+
+
+def run_sp_parity(args, wl, cfg_d, pc, gen, dev, rank, world):
+    """N-rank pipeline vs the single-GPU pipeline (rank 0) on the same inputs at the benchmark's shape: 10 blocks
+    through the 8-block window (two evictions), 1 denoising step + the clean pass per block.  Collective."""
+    import torch.distributed as dist
+    from inferix_b200 import synthetic
+    from inferix_b200.kvcache_manager import KVCacheManager, KVCacheRequest
+    from inferix_b200.parallel import ParallelConfig
+    from inferix_b200.pipeline import CausalInferencePipeline, DecodeMode
+    from inferix_b200.wan_model import CausalWanModel
+    from inferix_b200.wrapper import WanDiffusionWrapper
+
+    n = wl["frames_per_block"]
+    H, W = wl["latent_hw"]
+    blocks = wl["window_blocks"] + 2
+    pargs = types.SimpleNamespace(denoising_step_list=[1000], warp_denoising_step=True, num_frame_per_block=n,
+                                  context_noise=0)
+    g = torch.Generator().manual_seed(123)
+    noise = torch.randn(1, blocks * n, 16, H, W, generator=g).bfloat16()
+    context = torch.randn(1, 20, cfg_d["text_dim"], generator=g).bfloat16()
+
+    def run(generator, pcfg, tag):
+        pipe = CausalInferencePipeline(pargs, dev, generator=generator, parallel_config=pcfg)
+        rg = torch.Generator().manual_seed(99)
+        pipe.renoise_fn = lambda x: torch.randn(x.shape, generator=rg, dtype=torch.float32).to(x.dtype).to(x.device)
+        trace = []
+        hook = generator.model.blocks[0].register_forward_hook(
+            lambda m, i, o: trace.append(pipe.kv_cache_meta[0]["_ifx_plan"]))
+        mgr = KVCacheManager(dev)
+        out = pipe.inference(noise=noise.to(dev), text_prompts=context.to(dev), kv_cache_manager=mgr,
+                             kv_cache_requests=[KVCacheRequest(tag)], decode_mode=DecodeMode.NO_DECODE)
+        hook.remove()                      # inference() frees the caches (and unmaps the peers) before it returns
+        torch.cuda.synchronize()
+        return out, trace
+
+    out_sp, trace_sp = run(gen, pc, "sp_parity")
+    dist.barrier()
+    res = None
+    if rank == 0:
+        model1 = CausalWanModel(**cfg_d, local_attn_size=wl["window_blocks"] * n, sink_size=0,
+                                parallel_config=ParallelConfig())
+        with torch.device("cpu"):
+            sd = synthetic.synth_state_dict(cfg_d, seed=0, dtype=torch.bfloat16)
+        model1.load_state_dict(sd)
+        del sd
+        model1 = model1.to(torch.bfloat16).to(dev)
+        gen1 = WanDiffusionWrapper(model=model1, timestep_shift=5.0, parallel_config=ParallelConfig())
+        out_1, trace_1 = run(gen1, ParallelConfig(), "single")
+        rel = ((out_sp.float() - out_1.float()).norm() / out_1.float().norm()).item()
+        res = {"rel_l2": rel, "bit_equal": bool(torch.equal(out_sp, out_1)),
+               "index_trace_equal": trace_sp == trace_1, "blocks": blocks, "forwards": len(trace_1),
+               "shape": f"720p, {blocks} blocks through the {wl['window_blocks']}-block window, [1000] + clean pass",
+               "vs": "single-GPU pipeline on rank 0, same weights / noise / re-noise stream"}
+        del model1, gen1
+        torch.cuda.empty_cache()
+    dist.barrier()
+    return res
+
+
 # ------------------------------------------------------------------------------------------------ native arm
 def main():
     args = parse()
@@ -276,7 +371,8 @@ def main():
             meta["local_end_index"].fill_((blk + 1) * n * fs)
     frame0 = (wl["window_blocks"] - 1) * n
 
-    total = args.warmup + 2 * args.steps
+    prof_steps = max(1, min(args.profile_steps, args.steps))
+    total = args.warmup + 2 * args.steps + prof_steps
     noise_dev = [torch.randn(1, n, 16, H, W, device=dev, generator=g).bfloat16() for _ in range(total)]
     noise_host = [t.cpu().pin_memory() for t in noise_dev]
     out_host = torch.empty((1, n, 16, H, W), dtype=torch.bfloat16).pin_memory()
@@ -303,10 +399,9 @@ def main():
         pipe.denoise_block(noise_dev[step], frame0 + step * n, common)
         step += 1
 
-    # ---- timed region 1: inputs resident in HBM
+    # ---- timed region 1: inputs resident in HBM (no per-kernel events in here)
     clocks = ClockSampler(local_rank) if rank == 0 else None
-    _lib.prof_reset()
-    _lib.prof_enable(True)
+    _lib.prof_enable(False)
     barrier()
     _lib.reset_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -317,7 +412,6 @@ def main():
     e1.record()
     barrier()
     launches = _lib.launch_count()
-    _lib.prof_enable(False)
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     clock_info = clocks.stop() if clocks else None
 
@@ -335,6 +429,24 @@ def main():
     barrier()
     ms_e2e = max_over_ranks(e2.elapsed_time(e3))
 
+    # ---- separate pass: the same steps again with two CUDA events around every kernel launch of the library
+    _lib.prof_reset()
+    _lib.prof_enable(True)
+    barrier()
+    e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e4.record()
+    for _ in range(prof_steps):
+        pipe.denoise_block(noise_dev[step], frame0 + step * n, common)
+        step += 1
+    e5.record()
+    barrier()
+    _lib.prof_enable(False)
+    ms_prof = e4.elapsed_time(e5)                          # this rank's own clock: shares are per rank
+
+    sp_parity = None
+    if world > 1 and not args.no_sp_parity and args.workload != "tiny":
+        sp_parity = run_sp_parity(args, wl, cfg_d, pc, gen, dev, rank, world)
+
     if rank == 0:
         ms_step = ms_total / args.steps
         value = n / (ms_step / 1e3)
@@ -342,6 +454,7 @@ def main():
         # --- roofline of the dominant kernel (self-attention), from the per-launch events of timed region 1
         S_local = n * fs // world
         L = window_frames * fs
+        ms_total_prof = ms_prof
         attn_ms, attn_n = _lib.prof_read(f"attn_fwd_kernel[Lq={S_local},Lk={L},")
         all_ms, all_n = _lib.prof_read("")
         gemm_ms, gemm_n = _lib.prof_read("gemm_")
@@ -358,6 +471,14 @@ def main():
         if wait_n:
             kv_hbm["peer_wait"] = {"avg_launch_us": 1e3 * wait_ms / wait_n, "launches_timed": wait_n,
                                    "note": "stream-ordered wait for all ranks' K/V stores before attention"}
+        push_ms, push_n = _lib.prof_read("peer_push_kernel")
+        if push_n:
+            push_bytes = 2.0 * (world - 1) * S_local * C * 2     # this rank's K and V rows to every other rank
+            kv_hbm["peer_push"] = {"avg_launch_us": 1e3 * push_ms / push_n, "launches_timed": push_n,
+                                   "nvlink_bytes_out_per_launch": push_bytes,
+                                   "gbs_out": push_bytes / (push_ms / push_n * 1e-3) / 1e9,
+                                   "note": "copy grid shipping the block's new K/V to the peers; the attention kernel "
+                                           "is launched programmatically behind it and overlaps it"}
         peak_tf, peak_bw, src = measured_peaks()
         roofline = None
         if attn_n:
@@ -372,8 +493,11 @@ def main():
                         "peak_source": f"{src} bf16_tflops_sustained", "traffic": traffic,
                         "algorithmic_flops_per_launch": flops, "avg_launch_ms": attn_ms / attn_n,
                         "launches_timed": attn_n,
-                        "share_of_step": {"attention_self": attn_ms / ms_total, "gemm": gemm_ms / ms_total,
-                                          "all_kernels": all_ms / ms_total}}
+                        "timing": f"per-launch CUDA events in a separate pass of {prof_steps} step(s) after the timed "
+                                  f"regions ({ms_prof / prof_steps:.1f} ms/step with events on vs "
+                                  f"{ms_total / args.steps:.1f} ms/step timed)",
+                        "share_of_step": {"attention_self": attn_ms / ms_total_prof, "gemm": gemm_ms / ms_total_prof,
+                                          "all_kernels": all_ms / ms_total_prof}}
         _lib.prof_reset()
         # gather of one layer's whole window through the block table (what get()/get_range() cost), timed alone
         store0 = model.blocks[0].kv_cache_manager.store(mgr, reqs[0])
@@ -398,12 +522,14 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": noise_host[0].numel() * 2,
                     "d2h_bytes_per_step": out_host.numel() * 2},
             "gpu_launches": int(launches),
-            "sp_exchange": (None if world == 1 else
-                            "peer_memory (K/V stored into every rank's cache by the norm+RoPE kernel over NVLink)"
-                            if getattr(pipe, "_peer_group", None) is not None else "nccl_all_gather"),
+            "launches_per_step": int(launches) // max(1, args.steps),
+            "sp_exchange": (None if world == 1 else sp_exchange_name(pipe)),
+            "sp_parity": sp_parity,
             "roofline": roofline,
             "kv_hbm": kv_hbm,
         }
+        if world == 1 and not args.no_ref_gpu and args.workload == "self_forcing_720p":
+            line["ref_gpu"] = run_ref_gpu()
         if world == 1 and not args.no_cpu_baseline:
             try:
                 v, info = cpu_reference_sample(wl, args.cpu_seconds)

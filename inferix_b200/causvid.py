@@ -48,7 +48,7 @@ class CausVidCausalWanModel(CausalWanModel):
     def _metas(self, device):
         if self._meta is None or self._meta[0]["global_end_index"].device != device:
             idx = torch.zeros((self.num_layers, 2), dtype=torch.long, device=device)
-            self._meta = [{"global_end_index": idx[i, 0:1], "local_end_index": idx[i, 1:2]}
+            self._meta = [{"global_end_index": idx[i, 0:1], "local_end_index": idx[i, 1:2], "_ifx_shared": idx}
                           for i in range(self.num_layers)]
         return self._meta
 

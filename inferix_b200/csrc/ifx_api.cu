@@ -2,6 +2,7 @@
 // strings the 13 kernels of CausalWanAttentionBlock.forward (causal_model.py:384-484) together.
 #include <atomic>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include <string>
@@ -46,6 +47,15 @@ ifx_status set_error(ifx_status code, const char* fmt, ...) {
     return code;
 }
 void count_launch(int n) { g_launches.fetch_add(static_cast<uint64_t>(n), std::memory_order_relaxed); }
+
+bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("IFX_PDL");
+        v = (e == nullptr || e[0] != '0') ? 1 : 0;
+    }
+    return v == 1;
+}
 
 int sm_count() {
     static int cached = 0;

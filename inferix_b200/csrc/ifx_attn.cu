@@ -76,6 +76,7 @@ struct AttnParams {
     const long long* wait_flags;
     long long wait_epoch;
     unsigned long long wait_timeout_ns;
+    int32_t no_dep_wait;     // 1: do not griddepcontrol.wait (see the kernel prologue)
 };
 
 // Monotone cursor over the extent list: key tile j (over the concatenated extents) -> first key row and number of
@@ -209,6 +210,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // each role re-reads the TMEM base from shared memory into its own registers (a single kernel-wide value gets
     // spilled to local memory by ptxas and reloaded in front of every MMA)
     auto tmem_base_of = [tmem_slot]() { return *reinterpret_cast<volatile uint32_t*>(tmem_slot); };
+    // Programmatic dependent launch.  Normal case: wait for the producer of q / K / V before the first global access.
+    // Sequence-parallel overlap (p.no_dep_wait): the preceding kernel on the stream is the peer-push grid, which this
+    // kernel deliberately overlaps — it released us only after the kernel that wrote q and the local rows had
+    // completed (peer_push_kernel), and the peers' rows are ordered by the epoch flags.
+    griddep_launch();
+    if (!p.no_dep_wait) griddep_wait();
     // TMEM columns
     // TMEM columns: S0 | S1 | O0 | O1 (128 each)
 
@@ -487,6 +494,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 // Merge the key-range pieces of the split items: one warp per query row, lane owns 4 of the 128 dims.
 __global__ void __launch_bounds__(256)
 attn_combine_kernel(const AttnParams p) {
+    griddep_launch();
+    griddep_wait();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int gw = blockIdx.x * 8 + warp;  // (split item, row in pair)
     const int sitem = gw / (2 * kQT);
@@ -543,6 +552,7 @@ static void fill_defaults(AttnParams& p) {
     p.wait_flags = nullptr;
     p.wait_epoch = 0;
     p.wait_timeout_ns = 0;
+    p.no_dep_wait = 0;
 }
 
 // returns the total number of key tiles
@@ -569,7 +579,7 @@ static int fill_keys(AttnParams& p, const KeySpec* ks, int64_t kv_rows) {
 }
 
 static ifx_status launch_attn_kernel(int grid, const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
-                                     const AttnParams& p, bool pdl, cudaStream_t stream) {
+                                     const AttnParams& p, bool overlap_prev, cudaStream_t stream) {
     // the opt-in shared-memory size is a per-device function attribute
     static uint64_t configured_devices = 0;
     int dev = 0;
@@ -578,17 +588,12 @@ static ifx_status launch_attn_kernel(int grid, const CUtensorMap& tmQ, const CUt
         IFX_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
         if (dev < 64) configured_devices |= 1ull << dev;
     }
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(static_cast<unsigned>(grid));
-    cfg.blockDim = dim3(kAttnThreads);
-    cfg.dynamicSmemBytes = kAttnSmem;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = pdl ? 1 : 0;
-    IFX_CUDA_OK(cudaLaunchKernelEx(&cfg, attn_fwd_kernel, tmQ, tmK, tmV, p));
+    // overlap_prev: start next to the preceding kernel instead of after it.  Needs the launch attribute; with
+    // IFX_PDL=0 the launch is an ordinary one (stream order), which is still correct — only the overlap is lost.
+    AttnParams pp = p;
+    pp.no_dep_wait = overlap_prev ? 1 : 0;
+    IFX_CUDA_OK(launch_kernel(attn_fwd_kernel, dim3(static_cast<unsigned>(grid)), dim3(kAttnThreads), kAttnSmem, stream,
+                              true, tmQ, tmK, tmV, pp));
     return IFX_OK;
 }
 
@@ -687,7 +692,8 @@ static ifx_status attention_launch(const void* q, int64_t ldq, const void* k, co
         ProfScope prof(label, stream);
         st = launch_attn_kernel(grid, tmQ, tmK, tmV, p, keys != nullptr && keys->pdl, stream);
         if (st != IFX_OK) return st;
-        if (pieces > 0) attn_combine_kernel<<<rem * (2 * kQT) / 8, 256, 0, stream>>>(p);
+        if (pieces > 0)
+            IFX_CUDA_OK(launch_kernel(attn_combine_kernel, dim3(rem * (2 * kQT) / 8), dim3(256), 0, stream, true, p));
     }
     IFX_LAUNCH_OK("attn_fwd_kernel");
     if (pieces > 0) count_launch();
@@ -827,7 +833,7 @@ extern "C" ifx_status ifx_attention_combine(const void* workspace, int32_t piece
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     {
         ProfScope prof("attn_combine_kernel", s);
-        attn_combine_kernel<<<items * (2 * kQT) / 8, 256, 0, s>>>(p);
+        IFX_CUDA_OK(launch_kernel(attn_combine_kernel, dim3(items * (2 * kQT) / 8), dim3(256), 0, s, true, p));
     }
     IFX_LAUNCH_OK("attn_combine_kernel");
     return IFX_OK;

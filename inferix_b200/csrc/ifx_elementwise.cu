@@ -12,11 +12,58 @@ constexpr int kMaxVecPerThread = 8;  // cols <= 256 * 8 * 8; one warp per row up
 // threads per row CTA: one 16-byte vector per thread when the row fits, rounded up to whole warps
 // Rows up to 2048 columns get ONE WARP (each lane keeps up to 8 x 16 B loads in flight and the row statistics need
 // only shuffles); wider rows fall back to a multi-warp CTA with a shared-memory reduction.
+// launch geometry of a row kernel (see RowGeom)
+struct RowLaunch {
+    unsigned grid, block;
+    int warp_rows;
+};
+static inline int row_threads(int cols);
+static inline RowLaunch row_launch(int64_t rows, int cols) {
+    RowLaunch r;
+    if ((cols >> 3) <= 32 * 8) {                 // one warp per row
+        const int64_t ctas = (rows + 7) / 8;
+        const int64_t cap = static_cast<int64_t>(sm_count()) * 6;
+        r.grid = static_cast<unsigned>(ctas < cap ? ctas : cap);
+        r.block = 256;
+        r.warp_rows = 1;
+    } else {
+        r.grid = static_cast<unsigned>(rows);
+        r.block = static_cast<unsigned>(row_threads(cols));
+        r.warp_rows = 0;
+    }
+    return r;
+}
 static inline int row_threads(int cols) {
     const int nvec = cols >> 3;
     if (nvec <= 32 * kMaxVecPerThread) return 32;
     int t = ((nvec + kMaxVecPerThread - 1) / kMaxVecPerThread + 31) / 32 * 32;
     return t > kRowThreads ? kRowThreads : t;
+}
+
+// Row geometry shared by the row kernels.  Rows that fit one warp (<= 2048 columns: the Wan / MAGI widths) run in
+// "warp rows" mode: a CTA is 8 independent warps and every warp walks rows with a grid-wide stride — a few hundred
+// resident CTAs instead of one 32-thread CTA per token (whose launch rate, not HBM, bounded the round-1 kernels).
+// Wider rows keep one multi-warp CTA per row.
+struct RowGeom {
+    int t;          // this thread's index inside its row group
+    int tpr;        // threads per row
+    int64_t row;    // first row of this group
+    int64_t step;   // row stride
+};
+__device__ __forceinline__ RowGeom row_geom(int warp_rows) {
+    RowGeom g;
+    if (warp_rows) {
+        g.t = threadIdx.x & 31;
+        g.tpr = 32;
+        g.row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+        g.step = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
+    } else {
+        g.t = threadIdx.x;
+        g.tpr = blockDim.x;
+        g.row = blockIdx.x;
+        g.step = gridDim.x;
+    }
+    return g;
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -27,8 +74,8 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // block-wide sum of up to two values; result broadcast to all threads
 template <int kN>
-__device__ __forceinline__ void block_sum(float (&v)[kN], float* scratch /* [kN][32] */) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+__device__ __forceinline__ void block_sum(float (&v)[kN], float* scratch /* [kN][32] */, int tpr) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = tpr >> 5;
 #pragma unroll
     for (int i = 0; i < kN; ++i) v[i] = warp_sum(v[i]);
     if (nwarps == 1) {       // one warp per row: done (uniform branch)
@@ -82,76 +129,81 @@ __global__ void __launch_bounds__(kRowThreads)
 ln_modulate_kernel(const __nv_bfloat16* __restrict__ x, void* __restrict__ out_,
                    const __nv_bfloat16* __restrict__ ln_w, const __nv_bfloat16* __restrict__ ln_b,
                    const __nv_bfloat16* __restrict__ shift, const __nv_bfloat16* __restrict__ scale,
-                   int64_t mod_frame_stride, int cols, int64_t tokens_per_frame, float eps, float out_scale) {
+                   int64_t mod_frame_stride, int64_t rows, int cols, int64_t tokens_per_frame, float eps,
+                   float out_scale, int warp_rows) {
     __shared__ float scratch[2 * 32];
-    const int64_t row = blockIdx.x;
+    griddep_launch();
+    griddep_wait();
+    const RowGeom g = row_geom(warp_rows);
     const int nvec = cols >> 3;
-    const uint4* xr = reinterpret_cast<const uint4*>(x + row * cols);
-    float v[kMaxVecPerThread][8];
-    float acc[2] = {0.f, 0.f};
+    for (int64_t row = g.row; row < rows; row += g.step) {
+        const uint4* xr = reinterpret_cast<const uint4*>(x + row * cols);
+        float v[kMaxVecPerThread][8];
+        float acc[2] = {0.f, 0.f};
 #pragma unroll
-    for (int i = 0; i < kMaxVecPerThread; ++i) {
-        const int vi = threadIdx.x + i * blockDim.x;
-        if (vi < nvec) {
-            unpack8(xr[vi], v[i]);
+        for (int i = 0; i < kMaxVecPerThread; ++i) {
+            const int vi = g.t + i * g.tpr;
+            if (vi < nvec) {
+                unpack8(xr[vi], v[i]);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) acc[0] += v[i][e];
+                for (int e = 0; e < 8; ++e) acc[0] += v[i][e];
+            }
         }
-    }
-    float s1[1] = {acc[0]};
-    block_sum<1>(s1, scratch);
-    const float mean = s1[0] / cols;
-    // two-pass variance (matches at::native RowwiseMoments to fp32 rounding)
+        float s1[1] = {acc[0]};
+        block_sum<1>(s1, scratch, g.tpr);
+        const float mean = s1[0] / cols;
+        // two-pass variance (matches at::native RowwiseMoments to fp32 rounding)
 #pragma unroll
-    for (int i = 0; i < kMaxVecPerThread; ++i) {
-        const int vi = threadIdx.x + i * blockDim.x;
-        if (vi < nvec)
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const float d = v[i][e] - mean;
-                acc[1] += d * d;
-            }
-    }
-    float s2[1] = {acc[1]};
-    block_sum<1>(s2, scratch);
-    const float rstd = rsqrtf(s2[0] / cols + eps);
-
-    const int64_t frame = row / tokens_per_frame;
-    const uint4* sh = shift ? reinterpret_cast<const uint4*>(shift + frame * mod_frame_stride) : nullptr;
-    const uint4* sc = scale ? reinterpret_cast<const uint4*>(scale + frame * mod_frame_stride) : nullptr;
-    uint4* orow = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(out_) + row * cols);
-    uint2* orow8 = reinterpret_cast<uint2*>(static_cast<uint8_t*>(out_) + row * cols);
-#pragma unroll
-    for (int i = 0; i < kMaxVecPerThread; ++i) {
-        const int vi = threadIdx.x + i * blockDim.x;
-        if (vi < nvec) {
-            float y[8];
-            if (ln_w) {
-                float w[8], b[8];
-                unpack8(__ldg(reinterpret_cast<const uint4*>(ln_w) + vi), w);
-                unpack8(__ldg(reinterpret_cast<const uint4*>(ln_b) + vi), b);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) y[e] = bf16_round((v[i][e] - mean) * rstd * w[e] + b[e]);
-            } else {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) y[e] = bf16_round((v[i][e] - mean) * rstd);
-            }
-            if (sc) {
-                float a[8], b[8];
-                unpack8(__ldg(sc + vi), a);
-                unpack8(__ldg(sh + vi), b);
+        for (int i = 0; i < kMaxVecPerThread; ++i) {
+            const int vi = g.t + i * g.tpr;
+            if (vi < nvec)
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                    const float one_plus = bf16_round(1.0f + a[e]);
-                    y[e] = bf16_round(y[e] * one_plus) + b[e];  // final rounding happens in pack8
+                    const float d = v[i][e] - mean;
+                    acc[1] += d * d;
                 }
-            }
-            if (kOutFp8) {
+        }
+        float s2[1] = {acc[1]};
+        block_sum<1>(s2, scratch, g.tpr);
+        const float rstd = rsqrtf(s2[0] / cols + eps);
+
+        const int64_t frame = row / tokens_per_frame;
+        const uint4* sh = shift ? reinterpret_cast<const uint4*>(shift + frame * mod_frame_stride) : nullptr;
+        const uint4* sc = scale ? reinterpret_cast<const uint4*>(scale + frame * mod_frame_stride) : nullptr;
+        uint4* orow = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(out_) + row * cols);
+        uint2* orow8 = reinterpret_cast<uint2*>(static_cast<uint8_t*>(out_) + row * cols);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) y[e] = bf16_round(y[e]);  // the bf16 tensor the reference would quantise
-                orow8[vi] = quant8_e4m3(y, out_scale);
-            } else {
-                orow[vi] = pack8(y);
+        for (int i = 0; i < kMaxVecPerThread; ++i) {
+            const int vi = g.t + i * g.tpr;
+            if (vi < nvec) {
+                float y[8];
+                if (ln_w) {
+                    float w[8], b[8];
+                    unpack8(__ldg(reinterpret_cast<const uint4*>(ln_w) + vi), w);
+                    unpack8(__ldg(reinterpret_cast<const uint4*>(ln_b) + vi), b);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) y[e] = bf16_round((v[i][e] - mean) * rstd * w[e] + b[e]);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) y[e] = bf16_round((v[i][e] - mean) * rstd);
+                }
+                if (sc) {
+                    float a[8], b[8];
+                    unpack8(__ldg(sc + vi), a);
+                    unpack8(__ldg(sh + vi), b);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const float one_plus = bf16_round(1.0f + a[e]);
+                        y[e] = bf16_round(y[e] * one_plus) + b[e];  // final rounding happens in pack8
+                    }
+                }
+                if (kOutFp8) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) y[e] = bf16_round(y[e]);  // the bf16 tensor the reference would quantise
+                    orow8[vi] = quant8_e4m3(y, out_scale);
+                } else {
+                    orow[vi] = pack8(y);
+                }
             }
         }
     }
@@ -176,34 +228,38 @@ quantize_fp8_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, uint8_t* _
 // ------------------------------------------------------------------ WanRMSNorm
 __global__ void __launch_bounds__(kRowThreads)
 rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const __nv_bfloat16* __restrict__ w,
-               __nv_bfloat16* __restrict__ out, int64_t ldo, int cols, float eps) {
+               __nv_bfloat16* __restrict__ out, int64_t ldo, int64_t rows, int cols, float eps, int warp_rows) {
     __shared__ float scratch[32];
-    const int64_t row = blockIdx.x;
+    griddep_launch();
+    griddep_wait();
+    const RowGeom g = row_geom(warp_rows);
     const int nvec = cols >> 3;
-    const uint4* xr = reinterpret_cast<const uint4*>(x + row * ldx);
-    float v[kMaxVecPerThread][8];
-    float ss[1] = {0.f};
+    for (int64_t row = g.row; row < rows; row += g.step) {
+        const uint4* xr = reinterpret_cast<const uint4*>(x + row * ldx);
+        float v[kMaxVecPerThread][8];
+        float ss[1] = {0.f};
 #pragma unroll
-    for (int i = 0; i < kMaxVecPerThread; ++i) {
-        const int vi = threadIdx.x + i * blockDim.x;
-        if (vi < nvec) {
-            unpack8(xr[vi], v[i]);
+        for (int i = 0; i < kMaxVecPerThread; ++i) {
+            const int vi = g.t + i * g.tpr;
+            if (vi < nvec) {
+                unpack8(xr[vi], v[i]);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) ss[0] += v[i][e] * v[i][e];
+                for (int e = 0; e < 8; ++e) ss[0] += v[i][e] * v[i][e];
+            }
         }
-    }
-    block_sum<1>(ss, scratch);
-    const float r = rsqrtf(ss[0] / cols + eps);
-    uint4* orow = reinterpret_cast<uint4*>(out + row * ldo);
+        block_sum<1>(ss, scratch, g.tpr);
+        const float r = rsqrtf(ss[0] / cols + eps);
+        uint4* orow = reinterpret_cast<uint4*>(out + row * ldo);
 #pragma unroll
-    for (int i = 0; i < kMaxVecPerThread; ++i) {
-        const int vi = threadIdx.x + i * blockDim.x;
-        if (vi < nvec) {
-            float wv[8], y[8];
-            unpack8(__ldg(reinterpret_cast<const uint4*>(w) + vi), wv);
+        for (int i = 0; i < kMaxVecPerThread; ++i) {
+            const int vi = g.t + i * g.tpr;
+            if (vi < nvec) {
+                float wv[8], y[8];
+                unpack8(__ldg(reinterpret_cast<const uint4*>(w) + vi), wv);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) y[e] = bf16_round(v[i][e] * r) * wv[e];
-            orow[vi] = pack8(y);
+                for (int e = 0; e < 8; ++e) y[e] = bf16_round(v[i][e] * r) * wv[e];
+                orow[vi] = pack8(y);
+            }
         }
     }
 }
@@ -235,6 +291,8 @@ struct NormRopeParams {
     long long epoch;
     unsigned int* done_counter;
     int32_t local_only;      // 1: store into this rank's cache only and publish nothing (ifx_peer_push does the exchange)
+    int64_t rows;
+    int32_t warp_rows;       // RowGeom mode
 };
 
 // pair index inside a head -> which RoPE axis it rotates with (causal_model.py:37: split [c-2(c/3), c/3, c/3])
@@ -250,110 +308,118 @@ template <bool kPeers>
 __global__ void __launch_bounds__(kRowThreads)
 qk_norm_rope_append_kernel(const NormRopeParams p) {
     __shared__ float scratch[2 * 32];
-    const int64_t t = blockIdx.x;  // token row
+    // one 1-KiB table of rotation factors per row group (= per warp in warp-rows mode)
+    __shared__ double2 cs_all[(kRowThreads / 32) * 128];
+    griddep_launch();
+    griddep_wait();
+    const RowGeom g = row_geom(p.warp_rows);
     const int C = p.C;
     const int nvec = C >> 3;
-    const uint4* qr = reinterpret_cast<const uint4*>(p.qkv + t * p.ld_qkv);
-    const uint4* kr = reinterpret_cast<const uint4*>(p.qkv + t * p.ld_qkv + C);
-    const uint4* vr = reinterpret_cast<const uint4*>(p.qkv + t * p.ld_qkv + 2 * C);
-
-    // destination row in the cache
-    int64_t drow;
-    if (p.paged == 1) {
-        const int pg = static_cast<int>(t / p.page_tokens);
-        drow = static_cast<int64_t>(p.pl.pages[pg]) * p.page_tokens + (t % p.page_tokens);
-    } else if (kPeers && p.paged == 2) {
-        // token index inside the block in single-process order: (frame, rank, hw)  (causal_model.py:1016-1021)
-        const int64_t fs_full = static_cast<int64_t>(p.sp_world) * p.grid.hw_count;
-        const int64_t tb = (t / p.grid.hw_count) * fs_full + p.grid.hw_offset + (t % p.grid.hw_count);
-        drow = static_cast<int64_t>(p.pl.pages[tb / p.page_tokens]) * p.page_tokens + (tb % p.page_tokens);
-    } else {
-        drow = t;
-    }
-    // (frame, h, w) of this token; under sequence parallelism the rank owns hw indices [hw_offset, +hw_count)
-    const int f = static_cast<int>(t / p.grid.hw_count);
-    const int hw = p.grid.hw_offset + static_cast<int>(t % p.grid.hw_count);
-    const int t_pos = p.grid.start_frame + f;
-    const int h_pos = hw / p.grid.width;
-    const int w_pos = hw % p.grid.width;
-
-    // this token's 64 rotation factors are shared by every head and by q and k: stage them once (1 KiB) instead of
-    // re-reading the table from L2 for each of the 2 x heads x 64 pairs
-    __shared__ double2 cs_s[128];
     const int half = p.head_dim >> 1;
-    for (int pr = threadIdx.x; pr < half; pr += blockDim.x)
-        cs_s[pr] = __ldg(&p.freqs[rope_pos(pr, half, t_pos, h_pos, w_pos) * half + pr]);
-    __syncthreads();
+    double2* cs_s = cs_all + (p.warp_rows ? (threadIdx.x >> 5) * 128 : 0);
 
-    float q[kMaxVecPerThread][8], k[kMaxVecPerThread][8];
-    float ss[2] = {0.f, 0.f};
+    for (int64_t t = g.row; t < p.rows; t += g.step) {   // t: token row
+        const uint4* qr = reinterpret_cast<const uint4*>(p.qkv + t * p.ld_qkv);
+        const uint4* kr = reinterpret_cast<const uint4*>(p.qkv + t * p.ld_qkv + C);
+        const uint4* vr = reinterpret_cast<const uint4*>(p.qkv + t * p.ld_qkv + 2 * C);
+
+        // destination row in the cache
+        int64_t drow;
+        if (p.paged == 1) {
+            const int pg = static_cast<int>(t / p.page_tokens);
+            drow = static_cast<int64_t>(p.pl.pages[pg]) * p.page_tokens + (t % p.page_tokens);
+        } else if (kPeers && p.paged == 2) {
+            // token index inside the block in single-process order: (frame, rank, hw)  (causal_model.py:1016-1021)
+            const int64_t fs_full = static_cast<int64_t>(p.sp_world) * p.grid.hw_count;
+            const int64_t tb = (t / p.grid.hw_count) * fs_full + p.grid.hw_offset + (t % p.grid.hw_count);
+            drow = static_cast<int64_t>(p.pl.pages[tb / p.page_tokens]) * p.page_tokens + (tb % p.page_tokens);
+        } else {
+            drow = t;
+        }
+        // (frame, h, w) of this token; under sequence parallelism the rank owns hw indices [hw_offset, +hw_count)
+        const int f = static_cast<int>(t / p.grid.hw_count);
+        const int hw = p.grid.hw_offset + static_cast<int>(t % p.grid.hw_count);
+        const int t_pos = p.grid.start_frame + f;
+        const int h_pos = hw / p.grid.width;
+        const int w_pos = hw % p.grid.width;
+
+        // this token's rotation factors are shared by every head and by q and k: stage them once instead of
+        // re-reading the table from L2 for each of the 2 x heads x 64 pairs
+        if (p.warp_rows) __syncwarp(); else __syncthreads();      // previous row's readers are done
+        for (int pr = g.t; pr < half; pr += g.tpr)
+            cs_s[pr] = __ldg(&p.freqs[rope_pos(pr, half, t_pos, h_pos, w_pos) * half + pr]);
+        if (p.warp_rows) __syncwarp(); else __syncthreads();
+
+        float q[kMaxVecPerThread][8], k[kMaxVecPerThread][8];
+        float ss[2] = {0.f, 0.f};
 #pragma unroll
-    for (int i = 0; i < kMaxVecPerThread; ++i) {
-        const int vi = threadIdx.x + i * blockDim.x;
-        if (vi < nvec) {
-            unpack8(qr[vi], q[i]);
-            unpack8(kr[vi], k[i]);
+        for (int i = 0; i < kMaxVecPerThread; ++i) {
+            const int vi = g.t + i * g.tpr;
+            if (vi < nvec) {
+                unpack8(qr[vi], q[i]);
+                unpack8(kr[vi], k[i]);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                ss[0] += q[i][e] * q[i][e];
-                ss[1] += k[i][e] * k[i][e];
-            }
-            // V is appended untouched
-            if (kPeers && p.paged == 2) {
-                const uint4 vv = vr[vi];
-                if (p.local_only) {
-                    reinterpret_cast<uint4*>(p.peer_v[p.sp_rank] + drow * C)[vi] = vv;
-                } else {
-                    for (int d = 0; d < p.sp_world; ++d) {
-                        const int dst = (p.sp_rank + 1 + d) % p.sp_world;  // start at the neighbour: spread the links
-                        reinterpret_cast<uint4*>(p.peer_v[dst] + drow * C)[vi] = vv;
-                    }
+                for (int e = 0; e < 8; ++e) {
+                    ss[0] += q[i][e] * q[i][e];
+                    ss[1] += k[i][e] * k[i][e];
                 }
-            } else {
-                reinterpret_cast<uint4*>(p.v_dst + drow * C)[vi] = vr[vi];
+                // V is appended untouched
+                if (kPeers && p.paged == 2) {
+                    const uint4 vv = vr[vi];
+                    if (p.local_only) {
+                        reinterpret_cast<uint4*>(p.peer_v[p.sp_rank] + drow * C)[vi] = vv;
+                    } else {
+                        for (int d = 0; d < p.sp_world; ++d) {
+                            const int dst = (p.sp_rank + 1 + d) % p.sp_world;  // start at the neighbour: spread the links
+                            reinterpret_cast<uint4*>(p.peer_v[dst] + drow * C)[vi] = vv;
+                        }
+                    }
+                } else {
+                    reinterpret_cast<uint4*>(p.v_dst + drow * C)[vi] = vr[vi];
+                }
             }
         }
-    }
-    block_sum<2>(ss, scratch);
-    const float rq = rsqrtf(ss[0] / C + p.eps);
-    const float rk = rsqrtf(ss[1] / C + p.eps);
+        block_sum<2>(ss, scratch, g.tpr);
+        const float rq = rsqrtf(ss[0] / C + p.eps);
+        const float rk = rsqrtf(ss[1] / C + p.eps);
 #pragma unroll
-    for (int i = 0; i < kMaxVecPerThread; ++i) {
-        const int vi = threadIdx.x + i * blockDim.x;
-        if (vi < nvec) {
-            float wq[8], wk[8], qo[8], ko[8];
-            unpack8(__ldg(reinterpret_cast<const uint4*>(p.wq) + vi), wq);
-            unpack8(__ldg(reinterpret_cast<const uint4*>(p.wk) + vi), wk);
-            const int col0 = vi * 8;
-            const int pair0 = (col0 % p.head_dim) >> 1;
+        for (int i = 0; i < kMaxVecPerThread; ++i) {
+            const int vi = g.t + i * g.tpr;
+            if (vi < nvec) {
+                float wq[8], wk[8], qo[8], ko[8];
+                unpack8(__ldg(reinterpret_cast<const uint4*>(p.wq) + vi), wq);
+                unpack8(__ldg(reinterpret_cast<const uint4*>(p.wk) + vi), wk);
+                const int col0 = vi * 8;
+                const int pair0 = (col0 % p.head_dim) >> 1;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int pair = pair0 + e;
-                const double2 cs = cs_s[pair];
-                // RMSNorm: bf16(x * rsqrt) then bf16(.. * weight)  (components.py:118-126)
-                const double qa = bf16_round(bf16_round(q[i][2 * e] * rq) * wq[2 * e]);
-                const double qb = bf16_round(bf16_round(q[i][2 * e + 1] * rq) * wq[2 * e + 1]);
-                const double ka = bf16_round(bf16_round(k[i][2 * e] * rk) * wk[2 * e]);
-                const double kb = bf16_round(bf16_round(k[i][2 * e + 1] * rk) * wk[2 * e + 1]);
-                // complex multiply in fp64 (causal_model.py:46-56), rounded once to bf16
-                qo[2 * e] = static_cast<float>(qa * cs.x - qb * cs.y);
-                qo[2 * e + 1] = static_cast<float>(qa * cs.y + qb * cs.x);
-                ko[2 * e] = static_cast<float>(ka * cs.x - kb * cs.y);
-                ko[2 * e + 1] = static_cast<float>(ka * cs.y + kb * cs.x);
-            }
-            reinterpret_cast<uint4*>(p.q_out + t * p.ld_q)[vi] = pack8(qo);
-            if (kPeers && p.paged == 2) {
-                const uint4 kk = pack8(ko);
-                if (p.local_only) {
-                    reinterpret_cast<uint4*>(p.peer_k[p.sp_rank] + drow * C)[vi] = kk;
-                } else {
-                    for (int d = 0; d < p.sp_world; ++d) {
-                        const int dst = (p.sp_rank + 1 + d) % p.sp_world;
-                        reinterpret_cast<uint4*>(p.peer_k[dst] + drow * C)[vi] = kk;
-                    }
+                for (int e = 0; e < 4; ++e) {
+                    const int pair = pair0 + e;
+                    const double2 cs = cs_s[pair];
+                    // RMSNorm: bf16(x * rsqrt) then bf16(.. * weight)  (components.py:118-126)
+                    const double qa = bf16_round(bf16_round(q[i][2 * e] * rq) * wq[2 * e]);
+                    const double qb = bf16_round(bf16_round(q[i][2 * e + 1] * rq) * wq[2 * e + 1]);
+                    const double ka = bf16_round(bf16_round(k[i][2 * e] * rk) * wk[2 * e]);
+                    const double kb = bf16_round(bf16_round(k[i][2 * e + 1] * rk) * wk[2 * e + 1]);
+                    // complex multiply in fp64 (causal_model.py:46-56), rounded once to bf16
+                    qo[2 * e] = static_cast<float>(qa * cs.x - qb * cs.y);
+                    qo[2 * e + 1] = static_cast<float>(qa * cs.y + qb * cs.x);
+                    ko[2 * e] = static_cast<float>(ka * cs.x - kb * cs.y);
+                    ko[2 * e + 1] = static_cast<float>(ka * cs.y + kb * cs.x);
                 }
-            } else {
-                reinterpret_cast<uint4*>(p.k_dst + drow * C)[vi] = pack8(ko);
+                reinterpret_cast<uint4*>(p.q_out + t * p.ld_q)[vi] = pack8(qo);
+                if (kPeers && p.paged == 2) {
+                    const uint4 kk = pack8(ko);
+                    if (p.local_only) {
+                        reinterpret_cast<uint4*>(p.peer_k[p.sp_rank] + drow * C)[vi] = kk;
+                    } else {
+                        for (int d = 0; d < p.sp_world; ++d) {
+                            const int dst = (p.sp_rank + 1 + d) % p.sp_world;
+                            reinterpret_cast<uint4*>(p.peer_k[dst] + drow * C)[vi] = kk;
+                        }
+                    }
+                } else {
+                    reinterpret_cast<uint4*>(p.k_dst + drow * C)[vi] = pack8(ko);
+                }
             }
         }
     }
@@ -375,6 +441,8 @@ qk_norm_rope_append_kernel(const NormRopeParams p) {
 // Spin until every rank has published `epoch` in this rank's flag array (one lane per source rank).  Bounded: a rank
 // that never arrives traps the kernel after timeout_ns instead of hanging the GPU.
 __global__ void peer_wait_kernel(const long long* flags, int world, long long epoch, unsigned long long timeout_ns) {
+    griddep_launch();
+    griddep_wait();
     const int s = threadIdx.x;
     if (s >= world) return;
     unsigned long long t0;
@@ -441,8 +509,11 @@ struct PeerPushParams {
 
 __global__ void __launch_bounds__(1024)
 peer_push_kernel(const PeerPushParams p) {
-    // the attention kernel that follows on the stream is launched programmatically behind this grid: let it start
-    // right away (it needs nothing this grid writes locally; the rows it must wait for are ordered by the epoch flags)
+    // This grid is itself launched programmatically behind the norm + RoPE kernel that wrote the rows it ships: wait
+    // for that kernel first, THEN release the attention kernel queued behind this grid.  The attention does not wait
+    // for this grid (it needs nothing written locally here; the peers' rows are ordered by the epoch flags), but it
+    // must not start before the norm + RoPE kernel has produced q and the local rows — hence wait before launch.
+    griddep_wait();
     griddep_launch();
     const int nvec = p.C >> 3;
     const int64_t rows = static_cast<int64_t>(p.frames) * p.chunk;
@@ -577,16 +648,12 @@ static ifx_status ln_modulate_entry(const void* x, void* out, const void* ln_wei
     const int64_t tpf = tokens_per_frame > 0 ? tokens_per_frame : 1;
     {
         ProfScope prof(fp8 ? "ln_modulate_kernel<fp8>" : "ln_modulate_kernel", st);
-        if (fp8)
-            ln_modulate_kernel<true><<<static_cast<unsigned>(rows), row_threads(cols), 0, st>>>(
-                static_cast<const __nv_bfloat16*>(x), out, static_cast<const __nv_bfloat16*>(ln_weight),
-                static_cast<const __nv_bfloat16*>(ln_bias), static_cast<const __nv_bfloat16*>(shift),
-                static_cast<const __nv_bfloat16*>(scale), mod_frame_stride, cols, tpf, eps, out_scale);
-        else
-            ln_modulate_kernel<false><<<static_cast<unsigned>(rows), row_threads(cols), 0, st>>>(
-                static_cast<const __nv_bfloat16*>(x), out, static_cast<const __nv_bfloat16*>(ln_weight),
-                static_cast<const __nv_bfloat16*>(ln_bias), static_cast<const __nv_bfloat16*>(shift),
-                static_cast<const __nv_bfloat16*>(scale), mod_frame_stride, cols, tpf, eps, 1.0f);
+        const RowLaunch rl = row_launch(rows, cols);
+        IFX_CUDA_OK(launch_kernel(fp8 ? ln_modulate_kernel<true> : ln_modulate_kernel<false>, dim3(rl.grid), dim3(rl.block),
+                                  0, st, true, static_cast<const __nv_bfloat16*>(x), out,
+                                  static_cast<const __nv_bfloat16*>(ln_weight), static_cast<const __nv_bfloat16*>(ln_bias),
+                                  static_cast<const __nv_bfloat16*>(shift), static_cast<const __nv_bfloat16*>(scale),
+                                  mod_frame_stride, rows, cols, tpf, eps, fp8 ? out_scale : 1.0f, rl.warp_rows));
     }
     IFX_LAUNCH_OK("ln_modulate_kernel");
     return IFX_OK;
@@ -635,9 +702,10 @@ extern "C" ifx_status ifx_rmsnorm(const void* x, int64_t ldx, const void* weight
     IFX_CHECK_ARG(ldx % 8 == 0 && ldo % 8 == 0 && ldx >= cols && ldo >= cols, "ifx_rmsnorm: bad strides");
     {
         ProfScope prof("rmsnorm_kernel", static_cast<cudaStream_t>(stream));
-        rmsnorm_kernel<<<static_cast<unsigned>(rows), row_threads(cols), 0, static_cast<cudaStream_t>(stream)>>>(
-            static_cast<const __nv_bfloat16*>(x), ldx, static_cast<const __nv_bfloat16*>(weight),
-            static_cast<__nv_bfloat16*>(out), ldo, cols, eps);
+        const RowLaunch rl = row_launch(rows, cols);
+        IFX_CUDA_OK(launch_kernel(rmsnorm_kernel, dim3(rl.grid), dim3(rl.block), 0, static_cast<cudaStream_t>(stream), true,
+                                  static_cast<const __nv_bfloat16*>(x), ldx, static_cast<const __nv_bfloat16*>(weight),
+                                  static_cast<__nv_bfloat16*>(out), ldo, rows, cols, eps, rl.warp_rows));
     }
     IFX_LAUNCH_OK("rmsnorm_kernel");
     return IFX_OK;
@@ -726,10 +794,11 @@ static ifx_status norm_rope_append_entry(const void* qkv, int64_t ld_qkv, const 
     {
         ProfScope prof(peers ? "qk_norm_rope_append_kernel<peers>" : "qk_norm_rope_append_kernel",
                        static_cast<cudaStream_t>(stream));
-        if (peers)
-            qk_norm_rope_append_kernel<true><<<static_cast<unsigned>(rows), row_threads(C), 0, static_cast<cudaStream_t>(stream)>>>(p);
-        else
-            qk_norm_rope_append_kernel<false><<<static_cast<unsigned>(rows), row_threads(C), 0, static_cast<cudaStream_t>(stream)>>>(p);
+        const RowLaunch rl = row_launch(rows, C);
+        p.rows = rows;
+        p.warp_rows = rl.warp_rows;
+        IFX_CUDA_OK(launch_kernel(peers ? qk_norm_rope_append_kernel<true> : qk_norm_rope_append_kernel<false>,
+                                  dim3(rl.grid), dim3(rl.block), 0, static_cast<cudaStream_t>(stream), true, p));
     }
     IFX_LAUNCH_OK("qk_norm_rope_append_kernel");
     return IFX_OK;
@@ -791,7 +860,7 @@ extern "C" ifx_status ifx_peer_push(ifx_kv* kv_, const ifx_kv_plan* plan, const 
     p.done_counter = g_done_push;
     {
         ProfScope prof("peer_push_kernel", static_cast<cudaStream_t>(stream));
-        peer_push_kernel<<<ctas, 1024, 0, static_cast<cudaStream_t>(stream)>>>(p);
+        IFX_CUDA_OK(launch_kernel(peer_push_kernel, dim3(ctas), dim3(1024), 0, static_cast<cudaStream_t>(stream), true, p));
     }
     IFX_LAUNCH_OK("peer_push_kernel");
     return IFX_OK;
@@ -801,8 +870,9 @@ extern "C" ifx_status ifx_peer_wait(const int64_t* flags, int32_t world, int64_t
     IFX_CHECK_ARG(flags && world >= 1 && world <= IFX_MAX_PEERS && epoch > 0 && timeout_ms > 0, "ifx_peer_wait: bad argument");
     {
         ProfScope prof("peer_wait_kernel", static_cast<cudaStream_t>(stream));
-        peer_wait_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const long long*>(flags), world,
-                                                                         epoch, static_cast<unsigned long long>(timeout_ms) * 1000000ull);
+        IFX_CUDA_OK(launch_kernel(peer_wait_kernel, dim3(1), dim3(32), 0, static_cast<cudaStream_t>(stream), true,
+                                  reinterpret_cast<const long long*>(flags), world, static_cast<long long>(epoch),
+                                  static_cast<unsigned long long>(timeout_ms) * 1000000ull));
     }
     IFX_LAUNCH_OK("peer_wait_kernel");
     return IFX_OK;

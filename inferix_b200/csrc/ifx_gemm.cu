@@ -74,6 +74,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // programmatic dependent launch: everything above overlapped the previous kernel's tail; no global memory has
+    // been touched yet
+    griddep_launch();
+    griddep_wait();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -171,11 +175,13 @@ template <int kEpi, int kBN, bool kFp8>
 static ifx_status launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p,
                               cudaStream_t stream) {
     constexpr int kGemmSmem = GemmCfg<kBN>::kSmem;
-    static bool configured = false;
-    if (!configured) {
+    static uint64_t configured = 0;     // per-device bit: the opt-in shared-memory size is a per-device attribute
+    int dev = 0;
+    IFX_CUDA_OK(cudaGetDevice(&dev));
+    if (dev >= 64 || !(configured & (1ull << dev))) {
         IFX_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tn_kernel<kEpi, kBN, kFp8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          kGemmSmem));
-        configured = true;
+        if (dev < 64) configured |= 1ull << dev;
     }
     const int tiles = p.num_m_tiles * p.num_n_tiles;
     const int grid = tiles < sm_count() ? tiles : sm_count();
@@ -184,7 +190,8 @@ static ifx_status launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, co
         snprintf(label, sizeof(label), "gemm_%s_tn_kernel<%d,%d>[M=%lld,N=%d,K=%d]", kFp8 ? "fp8" : "bf16", kEpi, kBN,
                  (long long)p.M, p.N, p.K);
         ProfScope prof(label, stream);
-        gemm_bf16_tn_kernel<kEpi, kBN, kFp8><<<grid, kGemmThreads, kGemmSmem, stream>>>(tmA, tmB, p);
+        IFX_CUDA_OK(launch_kernel(gemm_bf16_tn_kernel<kEpi, kBN, kFp8>, dim3(grid), dim3(kGemmThreads), kGemmSmem, stream,
+                                  true, tmA, tmB, p));
     }
     IFX_LAUNCH_OK("gemm_bf16_tn_kernel");
     return IFX_OK;

@@ -140,6 +140,10 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // programmatic dependent launch: the prologue above overlapped the previous kernel's tail; nothing has touched
+    // global memory yet
+    griddep_launch();
+    griddep_wait();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -209,8 +213,8 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             mbar_wait(&tmem_full[as], aphase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * k2BN;
-#pragma unroll 1
             constexpr int kChunksPerHalf = k2BN / 64;   // 32-column chunks each epilogue half owns
+#pragma unroll 1
             for (int c = chalf * kChunksPerHalf; c < (chalf + 1) * kChunksPerHalf; ++c) {
                 const int col0 = n_blk * k2BN + c * 32;
                 if (col0 >= p.N) break;  // warp-uniform
@@ -236,11 +240,13 @@ template <int kEpi, bool kFp8, int k2BN>
 static ifx_status launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p,
                                cudaStream_t stream) {
     constexpr int k2Smem = Gemm2Cfg<k2BN>::kSmem;
-    static bool configured = false;
-    if (!configured) {
+    static uint64_t configured = 0;     // per-device bit
+    int dev = 0;
+    IFX_CUDA_OK(cudaGetDevice(&dev));
+    if (dev >= 64 || !(configured & (1ull << dev))) {
         IFX_CUDA_OK(cudaFuncSetAttribute(gemm2_tn_kernel<kEpi, kFp8, k2BN>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, k2Smem));
-        configured = true;
+        if (dev < 64) configured |= 1ull << dev;
     }
     const int tiles = p.num_m_tiles * p.num_n_tiles;
     int clusters = sm_count() / 2;
@@ -250,7 +256,8 @@ static ifx_status launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, c
         snprintf(label, sizeof(label), "gemm_%s_tn_kernel<%d,2cta,%d>[M=%lld,N=%d,K=%d]", kFp8 ? "fp8" : "bf16", kEpi,
                  k2BN, (long long)p.M, p.N, p.K);
         ProfScope prof(label, stream);
-        gemm2_tn_kernel<kEpi, kFp8, k2BN><<<2 * clusters, k2Threads, k2Smem, stream>>>(tmA, tmB, p);
+        IFX_CUDA_OK(launch_kernel(gemm2_tn_kernel<kEpi, kFp8, k2BN>, dim3(2 * clusters), dim3(k2Threads), k2Smem, stream,
+                                  true, tmA, tmB, p));
     }
     IFX_LAUNCH_OK("gemm2_tn_kernel");
     return IFX_OK;

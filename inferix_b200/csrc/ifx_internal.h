@@ -56,6 +56,29 @@ ifx_status make_tmap_u8_2d(CUtensorMap* out, const void* base, uint64_t inner_el
 
 int sm_count();
 
+// Programmatic dependent launch (PDL).  Kernels of the DiT layer are launched with the programmatic-stream-
+// serialization attribute: their CTAs may become resident while the previous kernel on the stream is still draining,
+// run their prologue (barrier init, TMEM allocation, descriptor prefetch) and block in griddepcontrol.wait — which
+// every such kernel executes before its first global-memory access — until the previous kernel has completed and
+// flushed.  IFX_PDL=0 turns the attribute off (plain stream order; griddepcontrol.wait is then a no-op).
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                 bool pdl, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (pdl && pdl_enabled()) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 struct KvImpl {
     uint32_t magic;
     void* k_base;

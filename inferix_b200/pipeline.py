@@ -268,7 +268,7 @@ class CausalInferencePipeline(torch.nn.Module):
         device = kv_cache_manager.device
         # all layers' end indices are views of one tensor
         idx = torch.zeros((self.num_transformer_blocks, 2), dtype=torch.long, device=device)
-        self.kv_cache_meta = [{"global_end_index": idx[i, 0:1], "local_end_index": idx[i, 1:2]}
+        self.kv_cache_meta = [{"global_end_index": idx[i, 0:1], "local_end_index": idx[i, 1:2], "_ifx_shared": idx}
                               for i in range(self.num_transformer_blocks)]
 
     def _reset_kv_cache(self, kv_cache_manager, kv_cache_requests):

@@ -235,9 +235,12 @@ class CausalWanAttentionBlock(nn.Module):
             else:
                 plan = self._forward_ops(xb, mod[bi], fs, frames, grid, freqs, store, cstore, current_start,
                                          sink_tokens, windowed, ws, qkv_w, qkv_b, pc, amax=self._amax)
-            # mirror of causal_model.py:328-329 (host ints -> device scalars, no sync)
-            kv_cache_meta["global_end_index"].fill_(plan.global_end)
-            kv_cache_meta["local_end_index"].fill_(plan.local_end)
+            # mirror of causal_model.py:328-329 (host ints -> device scalars, no sync).  When the pipeline keeps all
+            # layers' indices in one tensor (kv_cache_meta["_ifx_shared"]), the model writes them once per forward
+            # instead of two tiny launches per layer.
+            if "_ifx_shared" not in kv_cache_meta:
+                kv_cache_meta["global_end_index"].fill_(plan.global_end)
+                kv_cache_meta["local_end_index"].fill_(plan.local_end)
             kv_cache_meta["_ifx_plan"] = (plan.local_start, plan.local_end, plan.global_end, plan.num_evicted)
         if crossattn_cache_meta is not None:
             crossattn_cache_meta["is_init"] = True
@@ -609,6 +612,17 @@ class CausalWanModel(nn.Module):
                       crossattn_cache_meta=crossattn_cache_meta[i], current_start=current_start,
                       cache_start=cache_start, kv_cache_manager=kv_cache_manager,
                       kv_cache_requests=kv_cache_requests, workspace=ws, mod=mods[i])
+        shared = kv_cache_meta[0].get("_ifx_shared") if kv_cache_meta else None
+        if shared is not None:
+            # every layer appended the same block: one [layers, 2] = (global_end, local_end) write per forward
+            _ls, local_end, global_end, _ev = kv_cache_meta[0]["_ifx_plan"]
+            if all(m["_ifx_plan"][1:3] == (local_end, global_end) for m in kv_cache_meta):
+                shared[:, 0].fill_(global_end)
+                shared[:, 1].fill_(local_end)
+            else:                                     # layers diverged (not produced by the shipped pipelines)
+                for m in kv_cache_meta:
+                    m["global_end_index"].fill_(m["_ifx_plan"][2])
+                    m["local_end_index"].fill_(m["_ifx_plan"][1])
 
         x = self.head(x, e.unflatten(dim=0, sizes=t.shape).unsqueeze(2))             # [B, F, hw/P, 64]
         x = x.flatten(1, 2)

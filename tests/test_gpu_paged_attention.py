@@ -102,8 +102,15 @@ def test_attention_waits_for_fresh_pages_in_kernel(lq, pt, old_pages, split_hint
     store.append(plan, poison, poison)
     flags = torch.zeros(4, dtype=torch.int64, device=DEV)
     out = torch.empty_like(q)
-    torch.cuda.synchronize()
     side = torch.cuda.Stream(device=DEV)
+    with torch.cuda.stream(side):
+        # every kernel the side stream will use is launched once BEFORE the attention starts spinning: with CUDA's lazy
+        # module loading the first launch of a kernel may synchronise the context, which would wait for the spinning
+        # attention kernel (which waits for this stream) until its timeout traps
+        torch.cuda._sleep(1000)
+        store.append(plan, poison, poison)
+        flags.fill_(0)
+    torch.cuda.synchronize()
     store.attention(q, out, fresh=plan, flags=flags, epoch=7, timeout_ms=20000)      # main stream: starts, then spins
     with torch.cuda.stream(side):
         torch.cuda._sleep(int(2e6))                                                  # ~1 ms: the attention is running

@@ -223,8 +223,9 @@ def sp_exchange_name(pipe):
     from inferix_b200 import wan_model
     if getattr(pipe, "_peer_group", None) is None:
         return "nccl_all_gather"
-    return {"overlap": "peer_memory_overlap (push grid + attention launched programmatically behind it, flag wait "
-                       "inside the attention kernel before its first fresh-page tile; one C-ABI call per layer)",
+    return {"overlap": "peer_memory_fused (the attention kernel ships this rank's new K/V rows to every peer's cache over "
+                       "NVLink from an idle warp of each CTA while it attends the cached window, and acquires the peers' "
+                       "epoch flags in-kernel before its first fresh-page tile; one C-ABI call per layer)",
             "store": "peer_memory_store (K/V stored into every rank's cache by the norm+RoPE kernel, wait kernel; one "
                      "C-ABI call per layer)",
             "ops": "peer_memory_store, op by op from Python"}[wan_model._SP_MODE]
@@ -456,6 +457,10 @@ def main():
         L = window_frames * fs
         ms_total_prof = ms_prof
         attn_ms, attn_n = _lib.prof_read(f"attn_fwd_kernel[Lq={S_local},Lk={L},")
+        fused_exchange = False
+        if attn_n == 0:      # sequence parallel, fused exchange: the same kernel also ships the new K/V to the peers
+            attn_ms, attn_n = _lib.prof_read(f"attn_fwd_kernel<push>[Lq={S_local},Lk={L},")
+            fused_exchange = attn_n > 0
         all_ms, all_n = _lib.prof_read("")
         gemm_ms, gemm_n = _lib.prof_read("gemm_")
         # HBM-bound KV kernels (second half of the BASELINE metric): algorithmic bytes / device time
@@ -463,7 +468,7 @@ def main():
         kv_hbm = {}
         if app_n:
             app_bytes = 6.0 * S_local * C * 2          # read q|k|v rows, write q, roped-k and v (into the cache pages)
-            if world > 1 and getattr(pipe, "_peer_group", None) is not None:
+            if world > 1 and getattr(pipe, "_peer_group", None) is not None and not fused_exchange:
                 app_bytes = (4.0 + 2.0 * world) * S_local * C * 2   # k and v rows stored into every rank's cache
             kv_hbm["append_norm_rope"] = {"gbs": app_bytes / (app_ms / app_n * 1e-3) / 1e9, "bytes_per_launch": app_bytes,
                                           "avg_launch_us": 1e3 * app_ms / app_n, "launches_timed": app_n}
@@ -471,6 +476,10 @@ def main():
         if wait_n:
             kv_hbm["peer_wait"] = {"avg_launch_us": 1e3 * wait_ms / wait_n, "launches_timed": wait_n,
                                    "note": "stream-ordered wait for all ranks' K/V stores before attention"}
+        if fused_exchange:
+            kv_hbm["fused_exchange"] = {"nvlink_bytes_out_per_launch": 2.0 * (world - 1) * S_local * C * 2,
+                                        "where": "inside attn_fwd_kernel<push> (warp 2 of each CTA); no launch, no "
+                                                 "wait kernel: the roofline kernel's time includes it"}
         push_ms, push_n = _lib.prof_read("peer_push_kernel")
         if push_n:
             push_bytes = 2.0 * (world - 1) * S_local * C * 2     # this rank's K and V rows to every other rank
@@ -488,7 +497,8 @@ def main():
             tp = ROOT / "profiles" / "attn_traffic.json"
             if tp.exists():
                 traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
-            roofline = {"kernel": "attn_fwd_kernel (self-attention over the paged KV window)", "bound": "tensor",
+            roofline = {"kernel": "attn_fwd_kernel (self-attention over the paged KV window)"
+                                  + (" + fused K/V exchange over NVLink" if fused_exchange else ""), "bound": "tensor",
                         "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                         "peak_source": f"{src} bf16_tflops_sustained", "traffic": traffic,
                         "algorithmic_flops_per_launch": flops, "avg_launch_ms": attn_ms / attn_n,

@@ -397,11 +397,13 @@ ifx_status ifx_wan_block_forward(const ifx_wan_block_weights* w, const ifx_wan_b
  * frames * hw/P, io->tokens_per_frame = hw/P, io->grid.hw_offset / hw_count name the shard; the cache is replicated and
  * the plan covers rows * world tokens).  One call per layer, no collective:
  *   mode IFX_SP_STORE   : the norm + RoPE kernel stores K / V into every rank's cache, ifx_peer_wait, attention.
- *   mode IFX_SP_OVERLAP : the norm + RoPE kernel writes the local cache only; a `push_ctas`-CTA copy grid ships the rows
- *                         to the peers and publishes the epoch; the attention kernel is launched programmatically
- *                         behind it (it starts as soon as the push grid is resident), attends the cached pages while
- *                         the rows travel and acquires the epoch flags only before its first fresh-page tile
- *                         (ifx_attention_kv_wait).  The exchange costs no time on the critical path. */
+ *   mode IFX_SP_OVERLAP : the norm + RoPE kernel writes the local cache only; the ATTENTION KERNEL itself performs the
+ *                         exchange: an otherwise idle warp of each of its first CTAs (at most `push_ctas`, 0 = default
+ *                         7/8 of the SMs) copies a slice of this rank's new rows to the same cache rows of every peer
+ *                         over NVLink and the last one publishes the epoch, while the MMA / softmax warps attend the
+ *                         cached pages; every CTA acquires the peers' epoch flags only before its first fresh-page tile
+ *                         (ifx_attention_kv_wait).  Compute and collective are one kernel; the exchange costs no SM and
+ *                         no time on the critical path. */
 #define IFX_SP_STORE 0
 #define IFX_SP_OVERLAP 1
 ifx_status ifx_wan_block_forward_sp(const ifx_wan_block_weights* w, const ifx_wan_block_io* io,

@@ -198,7 +198,7 @@ static ifx_status wan_block_forward_impl(const ifx_wan_block_weights* w, const i
         IFX_CHECK_ARG(world >= 2 && world <= IFX_MAX_PEERS && peers->rank >= 0 && peers->rank < world && peers->epoch > 0,
                       "ifx_wan_block_forward_sp: bad world / rank / epoch");
         IFX_CHECK_ARG(sp_mode == IFX_SP_STORE || sp_mode == IFX_SP_OVERLAP, "ifx_wan_block_forward_sp: bad mode %d", sp_mode);
-        IFX_CHECK_ARG(timeout_ms > 0 && push_ctas > 0, "ifx_wan_block_forward_sp: timeout_ms / push_ctas must be positive");
+        IFX_CHECK_ARG(timeout_ms > 0 && push_ctas >= 0, "ifx_wan_block_forward_sp: timeout_ms must be positive");
         IFX_CHECK_ARG(peers->flags[peers->rank] != nullptr, "ifx_wan_block_forward_sp: null flag array");
     }
     const __nv_bfloat16* mod = static_cast<const __nv_bfloat16*>(io->mod);
@@ -227,15 +227,17 @@ static ifx_status wan_block_forward_impl(const ifx_wan_block_weights* w, const i
         IFX_TRY(ifx_peer_wait(peers->flags[peers->rank], world, peers->epoch, timeout_ms, stream));
         IFX_TRY(ifx_attention_kv(io->ws_q, C, io->kv, io->ws_attn, C, S, scale, stream));
     } else {
-        // exchange behind the attention over the cached window (see the header)
+        // exchange fused into the attention kernel, behind the attention over the cached window (see the header)
         ifx_peer_dst pd = *peers;
         pd.local_only = 1;
         IFX_TRY(ifx_qk_norm_rope_append_peers(io->ws_qkv, 3 * C, w->norm_q_w, w->norm_k_w, io->freqs, &io->grid,
                                               io->ws_q, C, io->kv, &plan, &pd, S, w->heads, w->head_dim, w->eps, stream));
-        IFX_TRY(ifx_peer_push(io->kv, &plan, peers, static_cast<int32_t>(S / fs), static_cast<int32_t>(fs), push_ctas,
-                              stream));
+        PeerPushParams push;
+        IFX_TRY(fill_peer_push(push, kv_cast(io->kv), &plan, peers, static_cast<int32_t>(S / fs),
+                               static_cast<int32_t>(fs)));
+        push.n_ctas = push_ctas;
         IFX_TRY(attention_kv_launch(io->ws_q, C, io->kv, io->ws_attn, C, S, scale, &plan, peers->flags[peers->rank], world,
-                                    peers->epoch, timeout_ms, /*pdl=*/true, cs));
+                                    peers->epoch, timeout_ms, /*pdl=*/false, cs, &push));
     }
     IFX_TRY(ifx_gemm_bf16(io->ws_attn, C, w->o_w, C, w->o_b, io->x, C, S, C, C, IFX_EPI_BIAS_GATE_RES, io->x, C,
                           mod + 2 * C, mstride, fs, stream));

@@ -77,6 +77,8 @@ struct AttnParams {
     long long wait_epoch;
     unsigned long long wait_timeout_ns;
     int32_t no_dep_wait;     // 1: do not griddepcontrol.wait (see the kernel prologue)
+    // ---- fused exchange: warp 2 of CTAs [0, push.n_ctas) ships this rank's rows of the fresh pages to the peers
+    PeerPushParams push;
 };
 
 // Monotone cursor over the extent list: key tile j (over the concatenated extents) -> first key row and number of
@@ -110,6 +112,58 @@ __device__ __forceinline__ TileRange make_tile_range(int n_all, int n_old_tiles,
     r.new_begin = n_old_tiles + static_cast<int>(static_cast<int64_t>(n_new_tiles) * sub / n);
     r.n_new = n_old_tiles + static_cast<int>(static_cast<int64_t>(n_new_tiles) * (sub + 1) / n) - r.new_begin;
     return r;
+}
+
+// One warp's share of the exchange (sequence parallel over peer memory): CTA `cta` of `p.n_ctas` copies a contiguous
+// slice of this rank's new K / V rows (16-byte vectors, 4 loads in flight per lane) from the local cache to the same
+// rows of every other rank's cache over NVLink, then arrives; the last CTA publishes the epoch on every rank.  The
+// NVLink stores need no SM resource the attention uses (the warp is otherwise idle after the TMEM allocation), and the
+// whole box-wide exchange is done long before any rank reaches its first fresh-page tile.
+__device__ __forceinline__ void push_slice(const PeerPushParams& p, int cta, int lane) {
+    const int nvec = p.C >> 3;
+    const int64_t rows = static_cast<int64_t>(p.frames) * p.chunk;
+    const int64_t fs_full = static_cast<int64_t>(p.world) * p.chunk;
+    const int64_t total = rows * nvec * 2;                               // K and V
+    const int64_t begin = total * cta / p.n_ctas, end = total * (cta + 1) / p.n_ctas;
+    constexpr int kUnroll = 4;
+    for (int64_t i0 = begin + lane; i0 < end; i0 += 32 * kUnroll) {
+        uint4 val[kUnroll];
+        int64_t off[kUnroll];
+        int which[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const int64_t i = i0 + u * 32;
+            off[u] = -1;
+            which[u] = 0;
+            if (i < end) {
+                which[u] = static_cast<int>(i / (rows * nvec));
+                const int64_t r = (i / nvec) % rows;
+                const int vi = static_cast<int>(i % nvec);
+                const int64_t tb = (r / p.chunk) * fs_full + static_cast<int64_t>(p.rank) * p.chunk + r % p.chunk;
+                const int64_t crow =
+                    static_cast<int64_t>(p.pl.pages[tb / p.page_tokens]) * p.page_tokens + tb % p.page_tokens;
+                off[u] = crow * p.C + vi * 8;
+                val[u] = *reinterpret_cast<const uint4*>((which[u] ? p.peer_v[p.rank] : p.peer_k[p.rank]) + off[u]);
+            }
+        }
+        for (int d = 1; d < p.world; ++d) {
+            const int dst = (p.rank + d) % p.world;                      // start at the neighbour: spread the links
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u)
+                if (off[u] >= 0)
+                    *reinterpret_cast<uint4*>((which[u] ? p.peer_v[dst] : p.peer_k[dst]) + off[u]) = val[u];
+        }
+    }
+    __threadfence_system();
+    __syncwarp();
+    if (lane == 0) {
+        const unsigned int prev = atomicAdd(p.done_counter, 1u);
+        if (prev == static_cast<unsigned int>(p.n_ctas) - 1) {
+            *p.done_counter = 0;                                         // next launch on this stream starts from zero
+            __threadfence_system();
+            for (int d = 0; d < p.world; ++d) st_relaxed_sys(p.peer_flags[d] + p.rank, p.epoch);
+        }
+    }
 }
 
 // Producer-side wait for the peers' K / V rows: acquire every rank's epoch flag at system scope, then order the TMA
@@ -214,7 +268,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // Sequence-parallel overlap (p.no_dep_wait): the preceding kernel on the stream is the peer-push grid, which this
     // kernel deliberately overlaps — it released us only after the kernel that wrote q and the local rows had
     // completed (peer_push_kernel), and the peers' rows are ordered by the epoch flags.
-    griddep_launch();
+    // The trigger for OUR dependents is issued at the very end of the kernel: this kernel runs for milliseconds and
+    // may spin on the peers' flags, so dependents that became resident early would only hold SM resources.
     if (!p.no_dep_wait) griddep_wait();
     // TMEM columns
     // TMEM columns: S0 | S1 | O0 | O1 (128 each)
@@ -281,6 +336,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             }
         }
       }
+      if (warp == 2 && p.push.n_ctas > 0 && static_cast<int>(blockIdx.x) < p.push.n_ctas)
+          push_slice(p.push, static_cast<int>(blockIdx.x), lane);
       if (warp == 1) {
         if (lane == 0) {
             const uint32_t tmem_base = tmem_base_of();
@@ -485,6 +542,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
     tc_fence_before();
     __syncthreads();
+    griddep_launch();
     if (warp == 2) {
         tc_fence_after();
         tmem_dealloc<512>(tmem_base_of());
@@ -536,8 +594,10 @@ struct KeySpec {
     int world = 0;
     long long epoch = 0;
     unsigned long long timeout_ns = 0;
-    bool pdl = false;              // launch with programmatic stream serialization (may start before the preceding
-                                   // kernel on the stream has finished; see ifx_wan_block_forward_sp)
+    bool pdl = false;              // run next to the preceding kernel on the stream instead of after it (only behind a
+                                   // kernel that releases this one explicitly, e.g. peer_push_kernel)
+    const PeerPushParams* push = nullptr;   // fused exchange: see AttnParams::push
+    int push_ctas = 0;                      // cap on the CTAs sharing the copy (0: default)
 };
 
 static void fill_defaults(AttnParams& p) {
@@ -553,6 +613,7 @@ static void fill_defaults(AttnParams& p) {
     p.wait_epoch = 0;
     p.wait_timeout_ns = 0;
     p.no_dep_wait = 0;
+    p.push = PeerPushParams{};
 }
 
 // returns the total number of key tiles
@@ -686,9 +747,27 @@ static ifx_status attention_launch(const void* q, int64_t ldq, const void* k, co
         p.part_ml = sc.ptr + static_cast<size_t>(pieces) * (2 * kQT) * kHD;
     }
     const int grid = p.n_whole + pieces;
+    if (keys != nullptr && keys->push != nullptr) {
+        // The CTAs that carry a slice of the exchange must all be resident before any CTA can be blocked on the peers'
+        // flags: keep them inside the first wave (lowest block indices are dispatched first) with some margin.
+        static unsigned int* g_done[64] = {nullptr};
+        int dev = 0;
+        IFX_CUDA_OK(cudaGetDevice(&dev));
+        IFX_CHECK_ARG(dev < 64, "ifx_attention: device ordinal %d not supported", dev);
+        if (!g_done[dev]) {
+            IFX_CUDA_OK(cudaMalloc(&g_done[dev], sizeof(unsigned int)));
+            IFX_CUDA_OK(cudaMemset(g_done[dev], 0, sizeof(unsigned int)));
+        }
+        p.push = *keys->push;
+        int cap = keys->push_ctas > 0 ? keys->push_ctas : (sms * 7) / 8;
+        if (cap > (sms * 7) / 8) cap = (sms * 7) / 8;
+        p.push.n_ctas = grid < cap ? grid : cap;
+        p.push.done_counter = g_done[dev];
+    }
     {
         char label[96];
-        snprintf(label, sizeof(label), "attn_fwd_kernel[Lq=%d,Lk=%lld,H=%d]", p.q_rows, (long long)key_rows, heads);
+        snprintf(label, sizeof(label), "attn_fwd_kernel%s[Lq=%d,Lk=%lld,H=%d]", p.push.n_ctas ? "<push>" : "", p.q_rows,
+                 (long long)key_rows, heads);
         ProfScope prof(label, stream);
         st = launch_attn_kernel(grid, tmQ, tmK, tmV, p, keys != nullptr && keys->pdl, stream);
         if (st != IFX_OK) return st;
@@ -875,7 +954,8 @@ extern "C" ifx_status ifx_attention_extents(const void* q, int64_t ldq, const vo
 namespace ifx {
 ifx_status attention_kv_launch(const void* q, int64_t ldq, const ifx_kv* kv_, void* out, int64_t ldo, int64_t q_rows,
                                float softmax_scale, const ifx_kv_plan* fresh, const int64_t* flags, int32_t world,
-                               int64_t epoch, int32_t timeout_ms, bool pdl, cudaStream_t stream) {
+                               int64_t epoch, int32_t timeout_ms, bool pdl, cudaStream_t stream,
+                               const PeerPushParams* push) {
     const KvImpl* kv = kv_cast(kv_);
     if (!kv) return set_error(IFX_ERR_HANDLE, "ifx_attention_kv: bad kv handle");
     IFX_CHECK_ARG(kv->local_end > 0, "ifx_attention_kv: cache is empty");
@@ -894,6 +974,9 @@ ifx_status attention_kv_launch(const void* q, int64_t ldq, const ifx_kv* kv_, vo
         ks.timeout_ns = static_cast<unsigned long long>(timeout_ms) * 1000000ull;
     }
     ks.pdl = pdl;
+    IFX_CHECK_ARG(push == nullptr || fresh != nullptr, "attention: the fused exchange needs the plan of the fresh pages");
+    ks.push = push;
+    ks.push_ctas = push ? push->n_ctas : 0;
     const int64_t width = static_cast<int64_t>(kv->heads) * kv->head_dim;
     // dense: the tensor map ends at local_end; extents: it covers the whole buffer
     const int64_t map_rows = ks.n_ext == 0 ? kv->local_end : static_cast<int64_t>(kv->num_pages) * kv->page_tokens;

@@ -22,7 +22,7 @@ static inline RowLaunch row_launch(int64_t rows, int cols) {
     RowLaunch r;
     if ((cols >> 3) <= 32 * 8) {                 // one warp per row
         const int64_t ctas = (rows + 7) / 8;
-        const int64_t cap = static_cast<int64_t>(sm_count()) * 6;
+        const int64_t cap = static_cast<int64_t>(sm_count()) * 4;   // 4 resident CTAs (32 warps) per SM
         r.grid = static_cast<unsigned>(ctas < cap ? ctas : cap);
         r.block = 256;
         r.warp_rows = 1;
@@ -438,6 +438,296 @@ qk_norm_rope_append_kernel(const NormRopeParams p) {
     }
 }
 
+
+// ================================================================== warp-per-row kernels (rows <= 2048 columns)
+// The Wan / MAGI widths fit one warp per row.  A CTA is 8 independent warps walking rows with a grid-wide stride; the
+// row stays PACKED in registers (kVec 16-byte vectors per lane) and is unpacked on use, which keeps the kernels at
+// <= 64 registers = 4 CTAs (32 warps, ~100 KB of loads in flight) per SM.  Per-lane accumulation order and the shuffle
+// tree are those of the generic kernels above, so results are bit-identical to them.
+constexpr int kWarpRowCtaThreads = 256;
+
+template <int kVec, bool kOutFp8>
+__global__ void __launch_bounds__(kWarpRowCtaThreads, 3)
+ln_modulate_warp_kernel(const __nv_bfloat16* __restrict__ x, void* __restrict__ out_,
+                        const __nv_bfloat16* __restrict__ ln_w, const __nv_bfloat16* __restrict__ ln_b,
+                        const __nv_bfloat16* __restrict__ shift, const __nv_bfloat16* __restrict__ scale,
+                        int64_t mod_frame_stride, int64_t rows, int cols, int64_t tokens_per_frame, float eps,
+                        float out_scale) {
+    griddep_launch();
+    griddep_wait();
+    const int lane = threadIdx.x & 31;
+    const int nvec = cols >> 3;
+    const int64_t step = static_cast<int64_t>(gridDim.x) * (kWarpRowCtaThreads / 32);
+    for (int64_t row = static_cast<int64_t>(blockIdx.x) * (kWarpRowCtaThreads / 32) + (threadIdx.x >> 5); row < rows;
+         row += step) {
+        const uint4* xr = reinterpret_cast<const uint4*>(x + row * cols);
+        uint4 raw[kVec];
+#pragma unroll
+        for (int i = 0; i < kVec; ++i) {
+            const int vi = lane + i * 32;
+            raw[i] = vi < nvec ? xr[vi] : make_uint4(0, 0, 0, 0);
+        }
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < kVec; ++i)
+            if (lane + i * 32 < nvec) {
+                float v[8];
+                unpack8(raw[i], v);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acc += v[e];
+            }
+        const float mean = warp_sum(acc) / cols;
+        acc = 0.f;   // two-pass variance (matches at::native RowwiseMoments to fp32 rounding)
+#pragma unroll
+        for (int i = 0; i < kVec; ++i)
+            if (lane + i * 32 < nvec) {
+                float v[8];
+                unpack8(raw[i], v);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const float d = v[e] - mean;
+                    acc += d * d;
+                }
+            }
+        const float rstd = rsqrtf(warp_sum(acc) / cols + eps);
+
+        const int64_t frame = row / tokens_per_frame;
+        const uint4* sh = shift ? reinterpret_cast<const uint4*>(shift + frame * mod_frame_stride) : nullptr;
+        const uint4* sc = scale ? reinterpret_cast<const uint4*>(scale + frame * mod_frame_stride) : nullptr;
+        uint4* orow = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(out_) + row * cols);
+        uint2* orow8 = reinterpret_cast<uint2*>(static_cast<uint8_t*>(out_) + row * cols);
+#pragma unroll
+        for (int i = 0; i < kVec; ++i) {
+            const int vi = lane + i * 32;
+            if (vi < nvec) {
+                float v[8], y[8];
+                unpack8(raw[i], v);
+                if (ln_w) {
+                    float w[8], b[8];
+                    unpack8(__ldg(reinterpret_cast<const uint4*>(ln_w) + vi), w);
+                    unpack8(__ldg(reinterpret_cast<const uint4*>(ln_b) + vi), b);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) y[e] = bf16_round((v[e] - mean) * rstd * w[e] + b[e]);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) y[e] = bf16_round((v[e] - mean) * rstd);
+                }
+                if (sc) {
+                    float a[8], b[8];
+                    unpack8(__ldg(sc + vi), a);
+                    unpack8(__ldg(sh + vi), b);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const float one_plus = bf16_round(1.0f + a[e]);
+                        y[e] = bf16_round(y[e] * one_plus) + b[e];  // final rounding happens in pack8
+                    }
+                }
+                if (kOutFp8) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) y[e] = bf16_round(y[e]);
+                    orow8[vi] = quant8_e4m3(y, out_scale);
+                } else {
+                    orow[vi] = pack8(y);
+                }
+            }
+        }
+    }
+}
+
+template <int kVec>
+__global__ void __launch_bounds__(kWarpRowCtaThreads, 4)
+rmsnorm_warp_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const __nv_bfloat16* __restrict__ w,
+                    __nv_bfloat16* __restrict__ out, int64_t ldo, int64_t rows, int cols, float eps) {
+    griddep_launch();
+    griddep_wait();
+    const int lane = threadIdx.x & 31;
+    const int nvec = cols >> 3;
+    const int64_t step = static_cast<int64_t>(gridDim.x) * (kWarpRowCtaThreads / 32);
+    for (int64_t row = static_cast<int64_t>(blockIdx.x) * (kWarpRowCtaThreads / 32) + (threadIdx.x >> 5); row < rows;
+         row += step) {
+        const uint4* xr = reinterpret_cast<const uint4*>(x + row * ldx);
+        uint4 raw[kVec];
+#pragma unroll
+        for (int i = 0; i < kVec; ++i) {
+            const int vi = lane + i * 32;
+            raw[i] = vi < nvec ? xr[vi] : make_uint4(0, 0, 0, 0);
+        }
+        float ss = 0.f;
+#pragma unroll
+        for (int i = 0; i < kVec; ++i)
+            if (lane + i * 32 < nvec) {
+                float v[8];
+                unpack8(raw[i], v);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) ss += v[e] * v[e];
+            }
+        const float r = rsqrtf(warp_sum(ss) / cols + eps);
+        uint4* orow = reinterpret_cast<uint4*>(out + row * ldo);
+#pragma unroll
+        for (int i = 0; i < kVec; ++i) {
+            const int vi = lane + i * 32;
+            if (vi < nvec) {
+                float v[8], wv[8], y[8];
+                unpack8(raw[i], v);
+                unpack8(__ldg(reinterpret_cast<const uint4*>(w) + vi), wv);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) y[e] = bf16_round(v[e] * r) * wv[e];
+                orow[vi] = pack8(y);
+            }
+        }
+    }
+}
+
+template <int kVec, bool kPeers>
+__global__ void __launch_bounds__(kWarpRowCtaThreads, 2)
+qk_norm_rope_append_warp_kernel(const NormRopeParams p) {
+    __shared__ double2 cs_all[(kWarpRowCtaThreads / 32) * 128];   // per warp: this token's rotation factors (<= 128 pairs)
+    griddep_launch();
+    griddep_wait();
+    const int lane = threadIdx.x & 31;
+    const int C = p.C;
+    const int nvec = C >> 3;
+    const int half = p.head_dim >> 1;
+    double2* cs_s = cs_all + (threadIdx.x >> 5) * 128;
+    const int64_t step = static_cast<int64_t>(gridDim.x) * (kWarpRowCtaThreads / 32);
+    for (int64_t t = static_cast<int64_t>(blockIdx.x) * (kWarpRowCtaThreads / 32) + (threadIdx.x >> 5); t < p.rows;
+         t += step) {
+        const uint4* qr = reinterpret_cast<const uint4*>(p.qkv + t * p.ld_qkv);
+        const uint4* kr = reinterpret_cast<const uint4*>(p.qkv + t * p.ld_qkv + C);
+        const uint4* vr = reinterpret_cast<const uint4*>(p.qkv + t * p.ld_qkv + 2 * C);
+        uint4 qraw[kVec], kraw[kVec];
+#pragma unroll
+        for (int i = 0; i < kVec; ++i) {
+            const int vi = lane + i * 32;
+            qraw[i] = vi < nvec ? qr[vi] : make_uint4(0, 0, 0, 0);
+            kraw[i] = vi < nvec ? kr[vi] : make_uint4(0, 0, 0, 0);
+        }
+        // destination row in the cache
+        int64_t drow;
+        if (p.paged == 1) {
+            const int pg = static_cast<int>(t / p.page_tokens);
+            drow = static_cast<int64_t>(p.pl.pages[pg]) * p.page_tokens + (t % p.page_tokens);
+        } else if (kPeers && p.paged == 2) {
+            // token index inside the block in single-process order: (frame, rank, hw)  (causal_model.py:1016-1021)
+            const int64_t fs_full = static_cast<int64_t>(p.sp_world) * p.grid.hw_count;
+            const int64_t tb = (t / p.grid.hw_count) * fs_full + p.grid.hw_offset + (t % p.grid.hw_count);
+            drow = static_cast<int64_t>(p.pl.pages[tb / p.page_tokens]) * p.page_tokens + (tb % p.page_tokens);
+        } else {
+            drow = t;
+        }
+        // V is appended untouched
+#pragma unroll
+        for (int i = 0; i < kVec; ++i) {
+            const int vi = lane + i * 32;
+            if (vi < nvec) {
+                const uint4 vv = vr[vi];
+                if (kPeers && p.paged == 2) {
+                    if (p.local_only) {
+                        reinterpret_cast<uint4*>(p.peer_v[p.sp_rank] + drow * C)[vi] = vv;
+                    } else {
+                        for (int d = 0; d < p.sp_world; ++d) {
+                            const int dst = (p.sp_rank + 1 + d) % p.sp_world;  // start at the neighbour: spread the links
+                            reinterpret_cast<uint4*>(p.peer_v[dst] + drow * C)[vi] = vv;
+                        }
+                    }
+                } else {
+                    reinterpret_cast<uint4*>(p.v_dst + drow * C)[vi] = vv;
+                }
+            }
+        }
+        // (frame, h, w) of this token; under sequence parallelism the rank owns hw indices [hw_offset, +hw_count)
+        const int f = static_cast<int>(t / p.grid.hw_count);
+        const int hw = p.grid.hw_offset + static_cast<int>(t % p.grid.hw_count);
+        const int t_pos = p.grid.start_frame + f;
+        const int h_pos = hw / p.grid.width;
+        const int w_pos = hw % p.grid.width;
+        __syncwarp();                                  // previous row's readers are done with cs_s
+        for (int pr = lane; pr < half; pr += 32)
+            cs_s[pr] = __ldg(&p.freqs[rope_pos(pr, half, t_pos, h_pos, w_pos) * half + pr]);
+        __syncwarp();
+
+        float sq = 0.f, sk = 0.f;
+#pragma unroll
+        for (int i = 0; i < kVec; ++i)
+            if (lane + i * 32 < nvec) {
+                float a[8], b[8];
+                unpack8(qraw[i], a);
+                unpack8(kraw[i], b);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    sq += a[e] * a[e];
+                    sk += b[e] * b[e];
+                }
+            }
+        const float rq = rsqrtf(warp_sum(sq) / C + p.eps);
+        const float rk = rsqrtf(warp_sum(sk) / C + p.eps);
+#pragma unroll
+        for (int i = 0; i < kVec; ++i) {
+            const int vi = lane + i * 32;
+            if (vi < nvec) {
+                float q[8], k[8], wq[8], wk[8], qo[8], ko[8];
+                unpack8(qraw[i], q);
+                unpack8(kraw[i], k);
+                unpack8(__ldg(reinterpret_cast<const uint4*>(p.wq) + vi), wq);
+                unpack8(__ldg(reinterpret_cast<const uint4*>(p.wk) + vi), wk);
+                const int pair0 = ((vi * 8) % p.head_dim) >> 1;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const double2 cs = cs_s[pair0 + e];
+                    // RMSNorm: bf16(x * rsqrt) then bf16(.. * weight)  (components.py:118-126)
+                    const double qa = bf16_round(bf16_round(q[2 * e] * rq) * wq[2 * e]);
+                    const double qb = bf16_round(bf16_round(q[2 * e + 1] * rq) * wq[2 * e + 1]);
+                    const double ka = bf16_round(bf16_round(k[2 * e] * rk) * wk[2 * e]);
+                    const double kb = bf16_round(bf16_round(k[2 * e + 1] * rk) * wk[2 * e + 1]);
+                    // complex multiply in fp64 (causal_model.py:46-56), rounded once to bf16
+                    qo[2 * e] = static_cast<float>(qa * cs.x - qb * cs.y);
+                    qo[2 * e + 1] = static_cast<float>(qa * cs.y + qb * cs.x);
+                    ko[2 * e] = static_cast<float>(ka * cs.x - kb * cs.y);
+                    ko[2 * e + 1] = static_cast<float>(ka * cs.y + kb * cs.x);
+                }
+                reinterpret_cast<uint4*>(p.q_out + t * p.ld_q)[vi] = pack8(qo);
+                const uint4 kk = pack8(ko);
+                if (kPeers && p.paged == 2) {
+                    if (p.local_only) {
+                        reinterpret_cast<uint4*>(p.peer_k[p.sp_rank] + drow * C)[vi] = kk;
+                    } else {
+                        for (int d = 0; d < p.sp_world; ++d) {
+                            const int dst = (p.sp_rank + 1 + d) % p.sp_world;
+                            reinterpret_cast<uint4*>(p.peer_k[dst] + drow * C)[vi] = kk;
+                        }
+                    }
+                } else {
+                    reinterpret_cast<uint4*>(p.k_dst + drow * C)[vi] = kk;
+                }
+            }
+        }
+    }
+    if (kPeers && p.paged == 2 && !p.local_only) {
+        // every thread's peer stores are ordered before the CTA's arrival; the last CTA to arrive publishes the epoch
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned int prev = atomicAdd(p.done_counter, 1u);
+            if (prev == gridDim.x - 1) {
+                *p.done_counter = 0;                       // next launch on this stream starts from zero
+                __threadfence_system();
+                for (int d = 0; d < p.sp_world; ++d) st_relaxed_sys(p.peer_flags[d] + p.sp_rank, p.epoch);
+            }
+        }
+    }
+}
+
+// kVec dispatch: smallest instantiated vector count per lane that covers the row
+#define IFX_WARP_ROW_DISPATCH(nvec, CALL)            \
+    do {                                             \
+        const int _k = ((nvec) + 31) / 32;           \
+        if (_k <= 1) { CALL(1); }                    \
+        else if (_k <= 2) { CALL(2); }               \
+        else if (_k <= 4) { CALL(4); }               \
+        else if (_k <= 6) { CALL(6); }               \
+        else { CALL(8); }                            \
+    } while (0)
+
 // Spin until every rank has published `epoch` in this rank's flag array (one lane per source rank).  Bounded: a rank
 // that never arrives traps the kernel after timeout_ns instead of hanging the GPU.
 __global__ void peer_wait_kernel(const long long* flags, int world, long long epoch, unsigned long long timeout_ns) {
@@ -497,16 +787,6 @@ paged_copy_kernel(const PagedCopyParams p) {
 // Copy this rank's rows of the block's new pages from its own cache to the same rows of every other rank's cache and
 // publish the epoch: the exchange half of qk_norm_rope_append_kernel<true>, as a separate small grid that runs on a
 // side stream next to the attention over the already-cached pages (which leaves a few SMs free at 4-8 ranks).
-struct PeerPushParams {
-    int32_t world, rank, frames, chunk, page_tokens, C;
-    PageList pl;
-    __nv_bfloat16* peer_k[IFX_MAX_PEERS];
-    __nv_bfloat16* peer_v[IFX_MAX_PEERS];
-    long long* peer_flags[IFX_MAX_PEERS];
-    long long epoch;
-    unsigned int* done_counter;
-};
-
 __global__ void __launch_bounds__(1024)
 peer_push_kernel(const PeerPushParams p) {
     // This grid is itself launched programmatically behind the norm + RoPE kernel that wrote the rows it ships: wait
@@ -649,11 +929,23 @@ static ifx_status ln_modulate_entry(const void* x, void* out, const void* ln_wei
     {
         ProfScope prof(fp8 ? "ln_modulate_kernel<fp8>" : "ln_modulate_kernel", st);
         const RowLaunch rl = row_launch(rows, cols);
-        IFX_CUDA_OK(launch_kernel(fp8 ? ln_modulate_kernel<true> : ln_modulate_kernel<false>, dim3(rl.grid), dim3(rl.block),
-                                  0, st, true, static_cast<const __nv_bfloat16*>(x), out,
-                                  static_cast<const __nv_bfloat16*>(ln_weight), static_cast<const __nv_bfloat16*>(ln_bias),
-                                  static_cast<const __nv_bfloat16*>(shift), static_cast<const __nv_bfloat16*>(scale),
-                                  mod_frame_stride, rows, cols, tpf, eps, fp8 ? out_scale : 1.0f, rl.warp_rows));
+        if (rl.warp_rows) {
+#define IFX_LN_CALL(K)                                                                                                \
+    IFX_CUDA_OK(launch_kernel(fp8 ? ln_modulate_warp_kernel<K, true> : ln_modulate_warp_kernel<K, false>, dim3(rl.grid),  \
+                              dim3(rl.block), 0, st, true, static_cast<const __nv_bfloat16*>(x), out,                 \
+                              static_cast<const __nv_bfloat16*>(ln_weight), static_cast<const __nv_bfloat16*>(ln_bias), \
+                              static_cast<const __nv_bfloat16*>(shift), static_cast<const __nv_bfloat16*>(scale),     \
+                              mod_frame_stride, rows, cols, tpf, eps, fp8 ? out_scale : 1.0f))
+            IFX_WARP_ROW_DISPATCH(cols >> 3, IFX_LN_CALL);
+#undef IFX_LN_CALL
+        } else {
+            IFX_CUDA_OK(launch_kernel(fp8 ? ln_modulate_kernel<true> : ln_modulate_kernel<false>, dim3(rl.grid),
+                                      dim3(rl.block), 0, st, true, static_cast<const __nv_bfloat16*>(x), out,
+                                      static_cast<const __nv_bfloat16*>(ln_weight),
+                                      static_cast<const __nv_bfloat16*>(ln_bias), static_cast<const __nv_bfloat16*>(shift),
+                                      static_cast<const __nv_bfloat16*>(scale), mod_frame_stride, rows, cols, tpf, eps,
+                                      fp8 ? out_scale : 1.0f, 0));
+        }
     }
     IFX_LAUNCH_OK("ln_modulate_kernel");
     return IFX_OK;
@@ -703,9 +995,19 @@ extern "C" ifx_status ifx_rmsnorm(const void* x, int64_t ldx, const void* weight
     {
         ProfScope prof("rmsnorm_kernel", static_cast<cudaStream_t>(stream));
         const RowLaunch rl = row_launch(rows, cols);
-        IFX_CUDA_OK(launch_kernel(rmsnorm_kernel, dim3(rl.grid), dim3(rl.block), 0, static_cast<cudaStream_t>(stream), true,
-                                  static_cast<const __nv_bfloat16*>(x), ldx, static_cast<const __nv_bfloat16*>(weight),
-                                  static_cast<__nv_bfloat16*>(out), ldo, rows, cols, eps, rl.warp_rows));
+        if (rl.warp_rows) {
+#define IFX_RMS_CALL(K)                                                                                               \
+    IFX_CUDA_OK(launch_kernel(rmsnorm_warp_kernel<K>, dim3(rl.grid), dim3(rl.block), 0, static_cast<cudaStream_t>(stream), \
+                              true, static_cast<const __nv_bfloat16*>(x), ldx, static_cast<const __nv_bfloat16*>(weight), \
+                              static_cast<__nv_bfloat16*>(out), ldo, rows, cols, eps))
+            IFX_WARP_ROW_DISPATCH(cols >> 3, IFX_RMS_CALL);
+#undef IFX_RMS_CALL
+        } else {
+            IFX_CUDA_OK(launch_kernel(rmsnorm_kernel, dim3(rl.grid), dim3(rl.block), 0, static_cast<cudaStream_t>(stream),
+                                      true, static_cast<const __nv_bfloat16*>(x), ldx,
+                                      static_cast<const __nv_bfloat16*>(weight), static_cast<__nv_bfloat16*>(out), ldo, rows,
+                                      cols, eps, 0));
+        }
     }
     IFX_LAUNCH_OK("rmsnorm_kernel");
     return IFX_OK;
@@ -796,9 +1098,17 @@ static ifx_status norm_rope_append_entry(const void* qkv, int64_t ld_qkv, const 
                        static_cast<cudaStream_t>(stream));
         const RowLaunch rl = row_launch(rows, C);
         p.rows = rows;
-        p.warp_rows = rl.warp_rows;
-        IFX_CUDA_OK(launch_kernel(peers ? qk_norm_rope_append_kernel<true> : qk_norm_rope_append_kernel<false>,
-                                  dim3(rl.grid), dim3(rl.block), 0, static_cast<cudaStream_t>(stream), true, p));
+        p.warp_rows = 0;
+        if (rl.warp_rows) {
+#define IFX_QK_CALL(K)                                                                                               \
+    IFX_CUDA_OK(launch_kernel(peers ? qk_norm_rope_append_warp_kernel<K, true> : qk_norm_rope_append_warp_kernel<K, false>, \
+                              dim3(rl.grid), dim3(rl.block), 0, static_cast<cudaStream_t>(stream), true, p))
+            IFX_WARP_ROW_DISPATCH(C >> 3, IFX_QK_CALL);
+#undef IFX_QK_CALL
+        } else {
+            IFX_CUDA_OK(launch_kernel(peers ? qk_norm_rope_append_kernel<true> : qk_norm_rope_append_kernel<false>,
+                                      dim3(rl.grid), dim3(rl.block), 0, static_cast<cudaStream_t>(stream), true, p));
+        }
     }
     IFX_LAUNCH_OK("qk_norm_rope_append_kernel");
     return IFX_OK;
@@ -823,23 +1133,17 @@ extern "C" ifx_status ifx_qk_norm_rope_append_peers(const void* qkv, int64_t ld_
                                   nullptr, peers, rows, heads, head_dim, eps, stream);
 }
 
-extern "C" ifx_status ifx_peer_push(ifx_kv* kv_, const ifx_kv_plan* plan, const ifx_peer_dst* peers, int32_t frames,
-                                    int32_t chunk, int32_t ctas, void* stream) {
-    KvImpl* kv = kv_cast(kv_);
-    if (!kv) return set_error(IFX_ERR_HANDLE, "ifx_peer_push: bad kv handle");
-    IFX_CHECK_ARG(plan && peers, "ifx_peer_push: null pointer");
+namespace ifx {
+ifx_status fill_peer_push(PeerPushParams& p, const KvImpl* kv, const ifx_kv_plan* plan, const ifx_peer_dst* peers,
+                          int32_t frames, int32_t chunk) {
+    IFX_CHECK_ARG(kv && plan && peers, "peer push: null pointer");
     IFX_CHECK_ARG(peers->world >= 2 && peers->world <= IFX_MAX_PEERS && peers->rank >= 0 && peers->rank < peers->world &&
-                      peers->epoch > 0, "ifx_peer_push: bad world / rank / epoch");
-    IFX_CHECK_ARG(frames > 0 && chunk > 0 && ctas > 0 && ctas <= 1024, "ifx_peer_push: bad geometry");
+                      peers->epoch > 0, "peer push: bad world / rank / epoch");
+    IFX_CHECK_ARG(frames > 0 && chunk > 0, "peer push: bad geometry");
     const int64_t rows = static_cast<int64_t>(peers->world) * frames * chunk;
     IFX_CHECK_ARG(rows == plan->local_end - plan->local_start && rows == (int64_t)plan->num_pages * kv->page_tokens,
-                  "ifx_peer_push: world*frames*chunk (%lld) does not match the plan", (long long)rows);
-    static unsigned int* g_done_push = nullptr;    // separate from the append kernel's counter: the two may overlap
-    if (!g_done_push) {
-        IFX_CUDA_OK(cudaMalloc(&g_done_push, sizeof(unsigned int)));
-        IFX_CUDA_OK(cudaMemset(g_done_push, 0, sizeof(unsigned int)));
-    }
-    PeerPushParams p = {};
+                  "peer push: world*frames*chunk (%lld) does not match the plan", (long long)rows);
+    p = PeerPushParams{};
     p.world = peers->world;
     p.rank = peers->rank;
     p.frames = frames;
@@ -849,14 +1153,31 @@ extern "C" ifx_status ifx_peer_push(ifx_kv* kv_, const ifx_kv_plan* plan, const 
     p.pl.n = plan->num_pages;
     for (int i = 0; i < plan->num_pages; ++i) p.pl.pages[i] = plan->pages[i];
     for (int d = 0; d < peers->world; ++d) {
-        IFX_CHECK_ARG(peers->k[d] && peers->v[d] && peers->flags[d], "ifx_peer_push: null peer %d", d);
+        IFX_CHECK_ARG(peers->k[d] && peers->v[d] && peers->flags[d], "peer push: null peer %d", d);
         p.peer_k[d] = static_cast<__nv_bfloat16*>(peers->k[d]);
         p.peer_v[d] = static_cast<__nv_bfloat16*>(peers->v[d]);
         p.peer_flags[d] = reinterpret_cast<long long*>(peers->flags[d]);
     }
     IFX_CHECK_ARG(peers->k[peers->rank] == kv->k_base && peers->v[peers->rank] == kv->v_base,
-                  "ifx_peer_push: own entry must be this rank's cache");
+                  "peer push: own entry must be this rank's cache");
     p.epoch = peers->epoch;
+    return IFX_OK;
+}
+}  // namespace ifx
+
+extern "C" ifx_status ifx_peer_push(ifx_kv* kv_, const ifx_kv_plan* plan, const ifx_peer_dst* peers, int32_t frames,
+                                    int32_t chunk, int32_t ctas, void* stream) {
+    KvImpl* kv = kv_cast(kv_);
+    if (!kv) return set_error(IFX_ERR_HANDLE, "ifx_peer_push: bad kv handle");
+    IFX_CHECK_ARG(ctas > 0 && ctas <= 1024, "ifx_peer_push: bad CTA count");
+    static unsigned int* g_done_push = nullptr;    // separate from the append kernel's counter: the two may overlap
+    if (!g_done_push) {
+        IFX_CUDA_OK(cudaMalloc(&g_done_push, sizeof(unsigned int)));
+        IFX_CUDA_OK(cudaMemset(g_done_push, 0, sizeof(unsigned int)));
+    }
+    PeerPushParams p;
+    ifx_status st = fill_peer_push(p, kv, plan, peers, frames, chunk);
+    if (st != IFX_OK) return st;
     p.done_counter = g_done_push;
     {
         ProfScope prof("peer_push_kernel", static_cast<cudaStream_t>(stream));

@@ -99,6 +99,24 @@ struct PageList {
     int32_t n;
     int32_t pages[IFX_KV_MAX_PLAN_PAGES];
 };
+// Exchange of the block's new K / V rows over peer memory: rank `rank` owns hw indices [rank*chunk, (rank+1)*chunk) of
+// each of the `frames` new frames; its rows are copied from its own cache to the same rows of every other rank's
+// cache, then `epoch` is published in every rank's flag array.  Run either as its own grid (peer_push_kernel) or as a
+// side job of the attention kernel (one otherwise idle warp of each of the first n_ctas CTAs).
+struct PeerPushParams {
+    int32_t world, rank, frames, chunk, page_tokens, C;
+    int32_t n_ctas;          // CTAs sharing the copy (in-attention mode); 0 = disabled
+    PageList pl;
+    __nv_bfloat16* peer_k[IFX_MAX_PEERS];
+    __nv_bfloat16* peer_v[IFX_MAX_PEERS];
+    long long* peer_flags[IFX_MAX_PEERS];
+    long long epoch;
+    unsigned int* done_counter;
+};
+// fills PeerPushParams from the ABI structs (validates geometry); done_counter is left to the caller
+ifx_status fill_peer_push(PeerPushParams& p, const KvImpl* kv, const ifx_kv_plan* plan, const ifx_peer_dst* peers,
+                          int32_t frames, int32_t chunk);
+
 // mode 0: contiguous rows -> cache pages (append / import); mode 1: cache pages -> contiguous rows (export)
 struct PagedCopyParams {
     __nv_bfloat16* cache_k;
@@ -117,10 +135,12 @@ struct PagedCopyParams {
 ifx_status launch_paged_copy(const PagedCopyParams& p, cudaStream_t stream);
 
 // attention over a paged cache; fresh != nullptr: the plan's pages sit behind the flag wait (ifx_attention_kv_wait);
-// pdl: programmatic stream serialization (the kernel may start before its predecessor on the stream has finished)
+// pdl: the kernel may run NEXT TO its predecessor on the stream (only for a predecessor that releases it explicitly);
+// push != nullptr: the kernel also ships this rank's rows of the fresh pages to the peers (fused exchange)
 ifx_status attention_kv_launch(const void* q, int64_t ldq, const ifx_kv* kv, void* out, int64_t ldo, int64_t q_rows,
                                float softmax_scale, const ifx_kv_plan* fresh, const int64_t* flags, int32_t world,
-                               int64_t epoch, int32_t timeout_ms, bool pdl, cudaStream_t stream);
+                               int64_t epoch, int32_t timeout_ms, bool pdl, cudaStream_t stream,
+                               const PeerPushParams* push = nullptr);
 
 constexpr uint32_t kKvMagic = 0x4B564958u;  // "XIVK"
 KvImpl* kv_cast(ifx_kv* kv);

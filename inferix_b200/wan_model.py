@@ -401,8 +401,8 @@ class CausalWanAttentionBlock(nn.Module):
 
 
 # IFX_SP_MODE selects how the sequence-parallel layer exchanges the block's new K / V over peer memory:
-#   overlap (default) one C-ABI call per layer; the rows travel behind the attention over the cached window
-#                     (push grid + programmatically launched attention with an in-kernel flag wait)
+#   overlap (default) one C-ABI call per layer; the attention kernel itself ships the rows to the peers (an idle warp
+#                     of each CTA) while it attends the cached window, and waits for the peers' flags in-kernel
 #   store             one C-ABI call per layer; the norm+RoPE kernel stores into every rank's cache, then a wait kernel
 #   ops               the round-1 op-by-op path below (also what FP8 / calibration / the NCCL fallback use)
 _SP_MODE = __import__("os").environ.get("IFX_SP_MODE", "overlap")
@@ -411,11 +411,8 @@ if _SP_MODE not in ("overlap", "store", "ops"):
 
 
 def _sp_push_ctas(world: int) -> int:
-    """CTAs of the push grid: the attention grid leaves these SMs free at 4-8 ranks (132 / 144 of 148 CTAs)."""
-    env = __import__("os").environ.get("IFX_SP_PUSH_CTAS")
-    if env:
-        return max(1, int(env))
-    return {2: 8, 4: 16}.get(world, 4)
+    """Cap on the attention CTAs that share the fused K/V exchange (0 = the library default, 7/8 of the SMs)."""
+    return max(0, int(__import__("os").environ.get("IFX_SP_PUSH_CTAS", "0")))
 
 
 # IFX_SP_OVERLAP=1 turns on the exchange/compute overlap of the sequence-parallel path: local queries attend the pages

@@ -274,18 +274,6 @@ ifx_status ifx_attention_partial(const void* q, int64_t ldq, const void* k, cons
                                  int32_t piece_first, int32_t piece_count, void* stream);
 ifx_status ifx_attention_combine(const void* workspace, int32_t pieces_per_item, void* out, int64_t ldo,
                                  int64_t q_rows, int32_t heads, int32_t head_dim, void* stream);
-/* Introspection (host only, no GPU needed): the work schedule ifx_attention* would use for q_rows x heads queries over
- * n_tiles 128-key tiles on `sms` SMs.  Work items are (head, 256-row pair); when they fill the SMs badly (the sequence-
- * parallel shards: 1350 or 2700 rows per rank) the key tiles of all items are laid end to end and cut into one
- * equal-cost share per SM ("planned" schedule: a CTA runs up to 6 segments, cut items are merged by a combine pass);
- * otherwise whole waves + a key-split tail ("analytic").  Efficiency = total cost / (sms * busiest CTA).  The planned
- * schedule is used when the analytic one is below 0.95 and the plan beats it by 0.02.  `segments` (optional) receives
- * rows of 7 int32 (cta, item, r0_begin, r0_count, r1_begin, r1_count, partial slot or -1), terminated by cta = -1.
- * grid = 0: no plan within the limits. */
-ifx_status ifx_attention_plan_info(int32_t q_rows, int32_t heads, int32_t n_tiles, int32_t n_old_tiles, int32_t sms,
-                                   int32_t* grid, double* planned_efficiency, double* analytic_efficiency,
-                                   int32_t* segments, int32_t segments_cap);
-
 /* Attention over a LIST of key-row extents of k/v[0:kv_rows_total): up to IFX_ATTN_MAX_EXTENTS [row0, rows) pairs
  * (runs of physically consecutive cache pages).  Rows that follow an extent in memory are never attended: their
  * scores are masked and their V rows are zeroed in shared memory before the P V product, so unmapped pages may hold

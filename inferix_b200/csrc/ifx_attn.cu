@@ -22,7 +22,6 @@
 // cross-attention (wan_base/model.py:94-95).  Numerics follow FlashAttention-2: fp32 scores and running
 // sum (of the un-rounded probabilities), bf16 P for the PV product, one division by l at the end.
 #include <algorithm>
-#include <cstdlib>
 #include <vector>
 
 #include "ifx_internal.h"
@@ -45,20 +44,6 @@ constexpr int kMaxExt = IFX_ATTN_MAX_EXTENTS;  // key-row extents (runs of physi
 #define IFX_ATTN_POLY_EVERY 0
 #endif
 constexpr int kPolyEvery = IFX_ATTN_POLY_EVERY;  // 0: all exponentials on MUFU; n: one pair in n on the FMA pipe
-
-// One unit of work of a CTA: key tiles [r0_begin, +r0_count) then [r1_begin, +r1_count) of one (head, 256-row pair)
-// item.  Tile ids index the ORDERED tile sequence (resident tiles first, in-flight tiles last).
-struct AttnSeg {
-    int32_t item;
-    int32_t r0_begin, r0_count, r1_begin, r1_count;
-    int32_t slot;    // -1: the segment covers every key of the item -> normalise and write the output;
-                     // >= 0: un-normalised partial (O, max, sum) into this slot, merged by attn_combine_kernel
-};
-constexpr int kMaxSeg = 6;
-// an item whose keys were cut into several segments (planned schedule): its partial slots are consecutive
-struct CombineItem {
-    int32_t item, slot0, nslots;
-};
 
 struct AttnParams {
     int32_t q_rows;
@@ -94,12 +79,6 @@ struct AttnParams {
     int32_t no_dep_wait;     // 1: do not griddepcontrol.wait (see the kernel prologue)
     // ---- fused exchange: warp 2 of CTAs [0, push.n_ctas) ships this rank's rows of the fresh pages to the peers
     PeerPushParams push;
-    // ---- planned schedule (host-built, see plan_schedule): CTA b runs seg_table[b * kMaxSeg .. + seg_count[b]);
-    // nullptr: one analytically derived segment per CTA (n_whole / split above)
-    const AttnSeg* seg_table;
-    const int32_t* seg_count;
-    const CombineItem* comb_items;   // items cut into several partial slots (planned schedule)
-    int32_t n_comb;
 };
 
 // Monotone cursor over the extent list: key tile j (over the concatenated extents) -> first key row and number of
@@ -204,15 +183,6 @@ __device__ __forceinline__ void wait_peer_flags(const AttnParams& p) {
     asm volatile("fence.proxy.async;" ::: "memory");
 }
 
-__device__ __forceinline__ TileRange seg_tiles(const AttnSeg& sg) {
-    TileRange r;
-    r.old_begin = sg.r0_begin;
-    r.n_old = sg.r0_count;
-    r.new_begin = sg.r1_begin;
-    r.n_new = sg.r1_count;
-    return r;
-}
-
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -228,55 +198,37 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     uint64_t* p_full = s_full + 2;         // [2]
     uint64_t* o_full = p_full + 2;         // [1]
     uint64_t* v_fixed = o_full + 1;        // [kSlots]  warp 3 -> MMA (extent mode): V tile checked, stale rows zeroed
-    uint64_t* q_empty = v_fixed + kSlots;  // [1]  MMA -> producer: every MMA of the segment is done, sQ may be reloaded
-    uint64_t* o_empty = q_empty + 1;       // [2]  softmax -> MMA: the segment's O has been read out of TMEM
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 2);
-    // valid keys of the CTA's t-th tile at [t & 7], written by the producer before it arms the tile's K slot (release
-    // through the mbarrier chain kv_full -> s_full); the softmax warps read it after s_full.  The producer runs < 4
-    // tiles ahead.
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(v_fixed + kSlots);
+    // valid keys of tile i at [i & 7], written by the producer before it arms the tile's K slot (release through the
+    // mbarrier chain kv_full -> s_full); the softmax warps read it after s_full.  The producer runs < 4 tiles ahead.
     volatile int32_t* tile_valid = reinterpret_cast<volatile int32_t*>(tmem_slot + 1);
-    __shared__ AttnSeg segs[kMaxSeg];
-    __shared__ int nseg_s;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
-    // ---- the CTA's work list: planned schedule (table) or one analytically derived segment
+    // ---- which (item, key tiles) does this CTA own
     const int n_kv_all = p.n_ext ? p.ext_tile0[p.n_ext] : (p.kv_rows + kKT - 1) / kKT;
     const int n_old_all = p.wait_flags ? p.n_old_tiles : n_kv_all;
-    if (threadIdx.x == 0) {
-        if (p.seg_table != nullptr) {
-            const int n = p.seg_count[blockIdx.x];
-            for (int i = 0; i < n; ++i) segs[i] = p.seg_table[blockIdx.x * kMaxSeg + i];
-            nseg_s = n;
-        } else {
-            int item, piece = -1, sub = 0, nsub = 1;
-            if (p.partial) {
-                item = blockIdx.x / p.piece_count;
-                sub = blockIdx.x % p.piece_count;
-                nsub = p.piece_count;
-                piece = item * p.pieces_per_item + p.piece_first + sub;
-            } else if (static_cast<int>(blockIdx.x) < p.n_whole) {
-                item = blockIdx.x;
-            } else {
-                const int idx = blockIdx.x - p.n_whole;
-                item = p.n_whole + idx / p.split;
-                sub = idx % p.split;
-                nsub = p.split;
-                piece = idx;
-            }
-            const TileRange t = make_tile_range(n_kv_all, n_old_all, sub, nsub);
-            AttnSeg sg;
-            sg.item = item;
-            sg.r0_begin = t.old_begin;
-            sg.r0_count = t.n_old;
-            sg.r1_begin = t.new_begin;
-            sg.r1_count = t.n_new;
-            sg.slot = piece;
-            segs[0] = sg;
-            nseg_s = 1;
-        }
+    int item, piece = -1, sub = 0, nsub = 1;
+    if (p.partial) {
+        item = blockIdx.x / p.piece_count;
+        sub = blockIdx.x % p.piece_count;
+        nsub = p.piece_count;
+        piece = item * p.pieces_per_item + p.piece_first + sub;
+    } else if (static_cast<int>(blockIdx.x) < p.n_whole) {
+        item = blockIdx.x;
+    } else {
+        const int idx = blockIdx.x - p.n_whole;
+        item = p.n_whole + idx / p.split;
+        sub = idx % p.split;
+        nsub = p.split;
+        piece = idx;
     }
+    const TileRange tiles = make_tile_range(n_kv_all, n_old_all, sub, nsub);
+    const int head = item / p.num_q_pairs;
+    const int q0 = (item % p.num_q_pairs) * (2 * kQT);
+    const int n_kv = tiles.count();
+    const bool two = q0 + kQT < p.q_rows;  // second tile has at least one real row
     // extent mode: a tile at the end of an extent is followed in memory by rows of OTHER pages (unmapped, or being
     // written by a peer).  Their scores are masked, but 0 x NaN would still poison P V, so warp 3 zeroes those V rows
     // in shared memory before the MMA warp may consume the tile (v_fixed barrier).  The dense mode needs none of
@@ -292,115 +244,92 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         for (int i = 0; i < kSlots; ++i) {
             mbar_init(&kv_full[i], 1);
             mbar_init(&kv_empty[i], 1);
-            mbar_init(&v_fixed[i], 1);
         }
         mbar_init(q_full, 1);
-        mbar_init(q_empty, 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(&s_full[i], 1);
             mbar_init(&p_full[i], 128);
-            mbar_init(&o_empty[i], 128);
         }
         mbar_init(o_full, 1);
+        for (int i = 0; i < kSlots; ++i) mbar_init(&v_fixed[i], 1);
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc<512>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const int nseg = nseg_s;
     // each role re-reads the TMEM base from shared memory into its own registers (a single kernel-wide value gets
     // spilled to local memory by ptxas and reloaded in front of every MMA)
     auto tmem_base_of = [tmem_slot]() { return *reinterpret_cast<volatile uint32_t*>(tmem_slot); };
     // Programmatic dependent launch.  Normal case: wait for the producer of q / K / V before the first global access.
-    // p.no_dep_wait: the preceding kernel on the stream is a peer-push grid this kernel deliberately overlaps (it
-    // released us only after the kernel that wrote q and the local rows had completed, see peer_push_kernel).
+    // Sequence-parallel overlap (p.no_dep_wait): the preceding kernel on the stream is the peer-push grid, which this
+    // kernel deliberately overlaps — it released us only after the kernel that wrote q and the local rows had
+    // completed (peer_push_kernel), and the peers' rows are ordered by the epoch flags.
     // The trigger for OUR dependents is issued at the very end of the kernel: this kernel runs for milliseconds and
     // may spin on the peers' flags, so dependents that became resident early would only hold SM resources.
     if (!p.no_dep_wait) griddep_wait();
+    // TMEM columns
     // TMEM columns: S0 | S1 | O0 | O1 (128 each)
 
     // register re-balancing: the producer / MMA warpgroup needs few registers, the softmax warps hold a whole
-    // 128-wide score row per thread (the CTA owns 384 x 168 = 64512 registers = 128 x 88 + 256 x 208; asking for more deadlocks the inc)
+    // 128-wide score row per thread (the CTA owns 384 x 168 = 64512 registers = 128 x 72 + 256 x 216; asking for more deadlocks the inc)
     if (warp < 4) {
-      setmaxnreg_dec<88>();
+      setmaxnreg_dec<72>();
       if (warp == 0) {
         if (lane == 0) {
-            int idx = 0;        // K / V ring counter over all segments
-            int t_run = 0;      // tiles issued so far (tile_valid ring)
-            bool waited = false;
-            for (int si = 0; si < nseg; ++si) {
-                const AttnSeg sg = segs[si];
-                const TileRange tiles = seg_tiles(sg);
-                const int head = sg.item / p.num_q_pairs;
-                const int q0 = (sg.item % p.num_q_pairs) * (2 * kQT);
-                const bool two = q0 + kQT < p.q_rows;  // second tile has at least one real row
-                if (si > 0) mbar_wait(q_empty, static_cast<uint32_t>((si - 1) & 1));
-                // Q: one or two tiles x two 64-wide halves
-                const int nq = two ? 2 : 1;
-                mbar_expect_tx(q_full, nq * kTileBytes);
-                for (int w = 0; w < nq; ++w)
+            // Q: one or two tiles x two 64-wide halves
+            const int nq = two ? 2 : 1;
+            mbar_expect_tx(q_full, nq * kTileBytes);
+            for (int w = 0; w < nq; ++w)
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+                    tma_load_2d_hint(sQ + w * kTileBytes + h * kHalfBytes, &tmQ, q_full, head * kHD + h * 64,
+                                     q0 + w * kQT, kEvictFirst);
+            int idx = 0;
+            TileCursor cur;
+            for (int i = 0; i < n_kv; ++i) {
+                if (i == tiles.n_old && p.wait_flags != nullptr) wait_peer_flags(p);
+                int krow0, kvalid;
+                cur.locate(p, tiles.tile(i), krow0, kvalid);
+                tile_valid[i & 7] = kvalid;
+#pragma unroll
+                for (int kv = 0; kv < 2; ++kv, ++idx) {
+                    const int s = idx % kSlots;
+                    const uint32_t ph = (idx / kSlots) & 1;
+                    mbar_wait(&kv_empty[s], ph ^ 1);
+                    mbar_expect_tx(&kv_full[s], kTileBytes);
+                    const CUtensorMap* tm = kv == 0 ? &tmK : &tmV;
 #pragma unroll
                     for (int h = 0; h < 2; ++h)
-                        tma_load_2d_hint(sQ + w * kTileBytes + h * kHalfBytes, &tmQ, q_full, head * kHD + h * 64,
-                                         q0 + w * kQT, kEvictFirst);
-                TileCursor cur;
-                const int n_kv = tiles.count();
-                for (int i = 0; i < n_kv; ++i) {
-                    const int j = tiles.tile(i);
-                    if (!waited && p.wait_flags != nullptr && j >= n_old_all) {
-                        wait_peer_flags(p);
-                        waited = true;
-                    }
-                    int krow0, kvalid;
-                    cur.locate(p, j, krow0, kvalid);
-                    tile_valid[(t_run + i) & 7] = kvalid;
-#pragma unroll
-                    for (int kv = 0; kv < 2; ++kv, ++idx) {
-                        const int s = idx % kSlots;
-                        const uint32_t ph = (idx / kSlots) & 1;
-                        mbar_wait(&kv_empty[s], ph ^ 1);
-                        mbar_expect_tx(&kv_full[s], kTileBytes);
-                        const CUtensorMap* tm = kv == 0 ? &tmK : &tmV;
-#pragma unroll
-                        for (int h = 0; h < 2; ++h)
-                            tma_load_2d_hint(sKV + s * kTileBytes + h * kHalfBytes, tm, &kv_full[s],
-                                             (head / p.kv_group) * kHD + h * 64, krow0, kEvictLast);
-                    }
+                        tma_load_2d_hint(sKV + s * kTileBytes + h * kHalfBytes, tm, &kv_full[s],
+                                         (head / p.kv_group) * kHD + h * 64, krow0, kEvictLast);
                 }
-                t_run += n_kv;
             }
         }
       } else if (warp == 3) {
         if (fix_tails) {
             // every V tile passes through this warp on its way to the MMA warp (v_fixed instead of kv_full); tiles
             // that end an extent get their rows past the extent zeroed first.  Same tile walk as the producer.
-            int t_run = 0;
-            for (int si = 0; si < nseg; ++si) {
-                const TileRange tiles = seg_tiles(segs[si]);
-                TileCursor cur;
-                const int n_kv = tiles.count();
-                for (int i = 0; i < n_kv; ++i) {
-                    int krow0, kvalid;
-                    cur.locate(p, tiles.tile(i), krow0, kvalid);
-                    const int vi = 2 * (t_run + i) + 1;
-                    const int slot = vi % kSlots;
-                    mbar_wait(&kv_full[slot], static_cast<uint32_t>((vi / kSlots) & 1));
-                    if (kvalid < kKT) {
-                        uint8_t* vt = sKV + slot * kTileBytes;
-                        // row r of the tile = 128 bytes at r * 128 in each 64-dim half (the swizzle permutes 16-byte
-                        // chunks inside the row only)
-                        const int n16 = (kKT - kvalid) * 8;   // 16-byte chunks per half
-                        for (int c = lane; c < 2 * n16; c += 32) {
-                            const int h = c / n16, o = c % n16;
-                            *reinterpret_cast<uint4*>(vt + h * kHalfBytes + kvalid * 128 + o * 16) = make_uint4(0, 0, 0, 0);
-                        }
-                        fence_proxy_async();
+            TileCursor cur;
+            for (int i = 0; i < n_kv; ++i) {
+                int krow0, kvalid;
+                cur.locate(p, tiles.tile(i), krow0, kvalid);
+                const int vi = 2 * i + 1;
+                const int slot = vi % kSlots;
+                mbar_wait(&kv_full[slot], static_cast<uint32_t>((vi / kSlots) & 1));
+                if (kvalid < kKT) {
+                    uint8_t* vt = sKV + slot * kTileBytes;
+                    // row r of the tile = 128 bytes at r * 128 in each 64-dim half (the swizzle permutes 16-byte
+                    // chunks inside the row only)
+                    const int n16 = (kKT - kvalid) * 8;   // 16-byte chunks per half
+                    for (int c = lane; c < 2 * n16; c += 32) {
+                        const int h = c / n16, o = c % n16;
+                        *reinterpret_cast<uint4*>(vt + h * kHalfBytes + kvalid * 128 + o * 16) = make_uint4(0, 0, 0, 0);
                     }
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&v_fixed[slot]);
+                    fence_proxy_async();
                 }
-                t_run += n_kv;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&v_fixed[slot]);
             }
         }
       }
@@ -438,209 +367,173 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             auto slot_of = [](int idx) { return idx % kSlots; };
             auto phase_of = [](int idx) { return static_cast<uint32_t>((idx / kSlots) & 1); };
 
-            int t_run = 0;              // tiles of all segments so far (K / V ring position)
-            int cnt0 = 0, cnt1 = 0;     // tiles processed per query tile (s_full / p_full phases)
-            int sg0 = 0, sg1 = 0;       // segments per query tile (o_empty phase)
-            for (int si = 0; si < nseg; ++si) {
-                const AttnSeg sg = segs[si];
-                const int q0 = (sg.item % p.num_q_pairs) * (2 * kQT);
-                const bool two = q0 + kQT < p.q_rows;
-                const int n_kv = sg.r0_count + sg.r1_count;
-                const int k0 = 2 * t_run;
-                mbar_wait(q_full, static_cast<uint32_t>(si & 1));
-                mbar_wait(&kv_full[slot_of(k0)], phase_of(k0));
+            mbar_wait(q_full, 0);
+            mbar_wait(&kv_full[slot_of(0)], phase_of(0));
+            tc_fence_after();
+            issue_qk(0, slot_of(0));
+            umma_commit(&s_full[0]);
+            if (two) {
+                issue_qk(1, slot_of(0));
+                umma_commit(&s_full[1]);
+            }
+            umma_commit(&kv_empty[slot_of(0)]);
+            for (int j = 0; j < n_kv; ++j) {
+                const int vi = 2 * j + 1;
+                const int kn = 2 * j + 2;
+                const bool more = (j + 1 < n_kv);
+                mbar_wait(fix_tails ? &v_fixed[slot_of(vi)] : &kv_full[slot_of(vi)], phase_of(vi));
+                mbar_wait(&p_full[0], j & 1);
                 tc_fence_after();
-                issue_qk(0, slot_of(k0));
-                umma_commit(&s_full[0]);
-                if (two) {
-                    issue_qk(1, slot_of(k0));
-                    umma_commit(&s_full[1]);
-                }
-                umma_commit(&kv_empty[slot_of(k0)]);
-                for (int j = 0; j < n_kv; ++j) {
-                    const int vi = 2 * (t_run + j) + 1;
-                    const int kn = 2 * (t_run + j) + 2;
-                    const bool more = (j + 1 < n_kv);
-                    mbar_wait(fix_tails ? &v_fixed[slot_of(vi)] : &kv_full[slot_of(vi)], phase_of(vi));
-                    mbar_wait(&p_full[0], static_cast<uint32_t>((cnt0 + j) & 1));
-                    // the first P V of a segment overwrites O: the previous segment's epilogue must have read it
-                    if (j == 0 && sg0 > 0) mbar_wait(&o_empty[0], static_cast<uint32_t>((sg0 - 1) & 1));
+                issue_pv(0, slot_of(vi), j > 0);
+                if (more) {
+                    mbar_wait(&kv_full[slot_of(kn)], phase_of(kn));
                     tc_fence_after();
-                    issue_pv(0, slot_of(vi), j > 0);
-                    if (more) {
-                        mbar_wait(&kv_full[slot_of(kn)], phase_of(kn));
-                        tc_fence_after();
-                        issue_qk(0, slot_of(kn));
-                        umma_commit(&s_full[0]);
-                    }
-                    if (two) {
-                        mbar_wait(&p_full[1], static_cast<uint32_t>((cnt1 + j) & 1));
-                        if (j == 0 && sg1 > 0) mbar_wait(&o_empty[1], static_cast<uint32_t>((sg1 - 1) & 1));
-                        tc_fence_after();
-                        issue_pv(1, slot_of(vi), j > 0);
-                    }
-                    umma_commit(&kv_empty[slot_of(vi)]);
-                    if (more) {
-                        if (two) {
-                            issue_qk(1, slot_of(kn));
-                            umma_commit(&s_full[1]);
-                        }
-                        umma_commit(&kv_empty[slot_of(kn)]);
-                    }
+                    issue_qk(0, slot_of(kn));
+                    umma_commit(&s_full[0]);
                 }
-                umma_commit(o_full);
-                umma_commit(q_empty);
-                t_run += n_kv;
-                cnt0 += n_kv;
-                ++sg0;
                 if (two) {
-                    cnt1 += n_kv;
-                    ++sg1;
+                    mbar_wait(&p_full[1], j & 1);
+                    tc_fence_after();
+                    issue_pv(1, slot_of(vi), j > 0);
+                }
+                umma_commit(&kv_empty[slot_of(vi)]);
+                if (more) {
+                    if (two) {
+                        issue_qk(1, slot_of(kn));
+                        umma_commit(&s_full[1]);
+                    }
+                    umma_commit(&kv_empty[slot_of(kn)]);
                 }
             }
+            umma_commit(o_full);
         }
       }
     } else {
-        setmaxnreg_inc<208>();
+        setmaxnreg_inc<216>();
         const int w = (warp - 4) >> 2;  // which query tile
-        const int quad = warp & 3;      // TMEM lane quadrant
-        const uint32_t lane_sel = static_cast<uint32_t>(quad * 32) << 16;
-        const uint32_t tmem_base = tmem_base_of();
-        const uint32_t tS_row = tmem_base + static_cast<uint32_t>(w) * 128u + lane_sel;
-        const uint32_t tO_row = tmem_base + 256u + static_cast<uint32_t>(w) * 128u + lane_sel;
-        const float sl2 = p.scale_log2;
-        int t_run = 0;   // tiles of all segments so far (tile_valid ring)
-        int cnt = 0;     // tiles this query tile has processed (s_full / p_full phases)
-        for (int si = 0; si < nseg; ++si) {
-            const int item = segs[si].item;
-            const int n_kv = segs[si].r0_count + segs[si].r1_count;
-            const int piece = segs[si].slot;
-            const int head = item / p.num_q_pairs;
-            const int q0 = (item % p.num_q_pairs) * (2 * kQT);
-            const bool two = q0 + kQT < p.q_rows;
-            if (w == 0 || two) {
-                const int row_in_pair = w * kQT + quad * 32 + lane;
-                const int row = q0 + row_in_pair;
+        if (w == 0 || two) {
+            const int quad = warp & 3;      // TMEM lane quadrant
+            const uint32_t lane_sel = static_cast<uint32_t>(quad * 32) << 16;
+            const uint32_t tmem_base = tmem_base_of();
+            const uint32_t tS_row = tmem_base + static_cast<uint32_t>(w) * 128u + lane_sel;
+            const uint32_t tO_row = tmem_base + 256u + static_cast<uint32_t>(w) * 128u + lane_sel;
+            const int row_in_pair = w * kQT + quad * 32 + lane;
+            const int row = q0 + row_in_pair;
+            const float sl2 = p.scale_log2;
 
-                float m_used = -INFINITY;  // max (raw score units) the probabilities are currently referenced to
-                float l = 0.f;
-                for (int j = 0; j < n_kv; ++j) {
-                    mbar_wait(&s_full[w], static_cast<uint32_t>((cnt + j) & 1));
-                    tc_fence_after();
-                    uint32_t s[4][32];
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) tmem_ld32(tS_row + c * 32, s[c]);
-                    tmem_wait_ld();
-                    const int valid = tile_valid[(t_run + j) & 7];
-                    if (valid < kKT) {
-#pragma unroll
-                        for (int c = 0; c < 4; ++c)
-#pragma unroll
-                            for (int i = 0; i < 32; ++i)
-                                if (c * 32 + i >= valid) s[c][i] = __float_as_uint(-INFINITY);
-                    }
-                    float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll
-                    for (int c = 0; c < 4; ++c)
-#pragma unroll
-                        for (int i = 0; i < 32; i += 4) {
-                            mx0 = fmaxf(mx0, __uint_as_float(s[c][i]));
-                            mx1 = fmaxf(mx1, __uint_as_float(s[c][i + 1]));
-                            mx2 = fmaxf(mx2, __uint_as_float(s[c][i + 2]));
-                            mx3 = fmaxf(mx3, __uint_as_float(s[c][i + 3]));
-                        }
-                    const float m_new = fmaxf(fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)), m_used);
-                    if (j == 0) {
-                        m_used = m_new;
-                    } else {
-                        const bool need = (m_new - m_used) * sl2 > kRescaleThreshold;
-                        if (__any_sync(0xffffffffu, need)) {
-                            // whole warp rescales (tcgen05.ld/st are warp-collective); rows that did not need it use
-                            // their exact (possibly tiny) correction as well, which keeps every row consistent.
-                            const float alpha = ex2_approx((m_used - m_new) * sl2);
-                            m_used = m_new;
-                            l *= alpha;
-#pragma unroll
-                            for (int c = 0; c < 4; ++c) {
-                                uint32_t o[32];
-                                tmem_ld32(tO_row + c * 32, o);
-                                tmem_wait_ld();
-#pragma unroll
-                                for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                                tmem_st32(tO_row + c * 32, o);
-                            }
-                        }
-                    }
-                    const float ms = m_used * sl2;
-                    float l0 = 0.f, l1 = 0.f;
-                    uint32_t pk[2][32];
-#pragma unroll
-                    for (int c = 0; c < 4; ++c)
-#pragma unroll
-                        for (int i = 0; i < 32; i += 2) {
-                            const float x0 = fmaf(__uint_as_float(s[c][i]), sl2, -ms);
-                            const float x1 = fmaf(__uint_as_float(s[c][i + 1]), sl2, -ms);
-                            // every kPolyEvery-th pair takes the FMA-pipe polynomial instead of MUFU.EX2
-                            const bool poly = kPolyEvery > 0 && ((i >> 1) % (kPolyEvery > 0 ? kPolyEvery : 1)) == kPolyEvery - 1;
-                            const float p0 = poly ? ex2_poly(x0) : ex2_approx(x0);
-                            const float p1 = poly ? ex2_poly(x1) : ex2_approx(x1);
-                            l0 += p0;
-                            l1 += p1;
-                            pk[c >> 1][(c & 1) * 16 + (i >> 1)] = pack_bf16x2(p0, p1);
-                        }
-                    l += l0 + l1;
-                    tmem_st32(tS_row, pk[0]);
-                    tmem_st32(tS_row + 32, pk[1]);
-                    tmem_wait_st();
-                    tc_fence_before();
-                    mbar_arrive(&p_full[w]);
-                }
-
-                mbar_wait(o_full, static_cast<uint32_t>(si & 1));
+            float m_used = -INFINITY;  // max (raw score units) the probabilities are currently referenced to
+            float l = 0.f;
+            for (int j = 0; j < n_kv; ++j) {
+                mbar_wait(&s_full[w], j & 1);
                 tc_fence_after();
-                if (piece < 0) {
-                    // epilogue: O / l -> bf16 -> global
-                    const float inv_l = 1.0f / l;
-                    __nv_bfloat16* optr = p.out + static_cast<int64_t>(row) * p.ldo + head * kHD;
+                uint32_t s[4][32];
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        uint32_t o[32];
-                        tmem_ld32(tO_row + c * 32, o);
-                        tmem_wait_ld();
-                        if (row < p.q_rows) {
+                for (int c = 0; c < 4; ++c) tmem_ld32(tS_row + c * 32, s[c]);
+                tmem_wait_ld();
+                const int valid = tile_valid[j & 7];
+                if (valid < kKT) {
 #pragma unroll
-                            for (int v = 0; v < 4; ++v) {
-                                uint4 pkt;
-                                pkt.x = pack_bf16x2(__uint_as_float(o[v * 8 + 0]) * inv_l, __uint_as_float(o[v * 8 + 1]) * inv_l);
-                                pkt.y = pack_bf16x2(__uint_as_float(o[v * 8 + 2]) * inv_l, __uint_as_float(o[v * 8 + 3]) * inv_l);
-                                pkt.z = pack_bf16x2(__uint_as_float(o[v * 8 + 4]) * inv_l, __uint_as_float(o[v * 8 + 5]) * inv_l);
-                                pkt.w = pack_bf16x2(__uint_as_float(o[v * 8 + 6]) * inv_l, __uint_as_float(o[v * 8 + 7]) * inv_l);
-                                *reinterpret_cast<uint4*>(optr + c * 32 + v * 8) = pkt;
-                            }
+                    for (int c = 0; c < 4; ++c)
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (c * 32 + i >= valid) s[c][i] = __float_as_uint(-INFINITY);
+                }
+                float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        mx0 = fmaxf(mx0, __uint_as_float(s[c][i]));
+                        mx1 = fmaxf(mx1, __uint_as_float(s[c][i + 1]));
+                        mx2 = fmaxf(mx2, __uint_as_float(s[c][i + 2]));
+                        mx3 = fmaxf(mx3, __uint_as_float(s[c][i + 3]));
+                    }
+                const float m_new = fmaxf(fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)), m_used);
+                if (j == 0) {
+                    m_used = m_new;
+                } else {
+                    const bool need = (m_new - m_used) * sl2 > kRescaleThreshold;
+                    if (__any_sync(0xffffffffu, need)) {
+                        // whole warp rescales (tcgen05.ld/st are warp-collective); rows that did not need it use
+                        // their exact (possibly tiny) correction as well, which keeps every row consistent.
+                        const float alpha = ex2_approx((m_used - m_new) * sl2);
+                        m_used = m_new;
+                        l *= alpha;
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            uint32_t o[32];
+                            tmem_ld32(tO_row + c * 32, o);
+                            tmem_wait_ld();
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                            tmem_st32(tO_row + c * 32, o);
                         }
                     }
-                } else {
-                    // partial: un-normalised O, reference max (log2 units) and sum
-                    float* po = p.part_o + (static_cast<int64_t>(piece) * (2 * kQT) + row_in_pair) * kHD;
-                    float* pml = p.part_ml + (static_cast<int64_t>(piece) * (2 * kQT) + row_in_pair) * 2;
-                    pml[0] = m_used * sl2;
-                    pml[1] = l;
+                }
+                const float ms = m_used * sl2;
+                float l0 = 0.f, l1 = 0.f;
+                uint32_t pk[2][32];
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        uint32_t o[32];
-                        tmem_ld32(tO_row + c * 32, o);
-                        tmem_wait_ld();
+                for (int c = 0; c < 4; ++c)
 #pragma unroll
-                        for (int v = 0; v < 8; ++v)
-                            *reinterpret_cast<uint4*>(po + c * 32 + v * 4) = make_uint4(o[v * 4], o[v * 4 + 1], o[v * 4 + 2], o[v * 4 + 3]);
+                    for (int i = 0; i < 32; i += 2) {
+                        const float x0 = fmaf(__uint_as_float(s[c][i]), sl2, -ms);
+                        const float x1 = fmaf(__uint_as_float(s[c][i + 1]), sl2, -ms);
+                        // every kPolyEvery-th pair takes the FMA-pipe polynomial instead of MUFU.EX2
+                        const bool poly = kPolyEvery > 0 && ((i >> 1) % (kPolyEvery > 0 ? kPolyEvery : 1)) == kPolyEvery - 1;
+                        const float p0 = poly ? ex2_poly(x0) : ex2_approx(x0);
+                        const float p1 = poly ? ex2_poly(x1) : ex2_approx(x1);
+                        l0 += p0;
+                        l1 += p1;
+                        pk[c >> 1][(c & 1) * 16 + (i >> 1)] = pack_bf16x2(p0, p1);
+                    }
+                l += l0 + l1;
+                tmem_st32(tS_row, pk[0]);
+                tmem_st32(tS_row + 32, pk[1]);
+                tmem_wait_st();
+                tc_fence_before();
+                mbar_arrive(&p_full[w]);
+            }
+
+            mbar_wait(o_full, 0);
+            tc_fence_after();
+            if (piece < 0) {
+                // epilogue: O / l -> bf16 -> global
+                const float inv_l = 1.0f / l;
+                __nv_bfloat16* optr = p.out + static_cast<int64_t>(row) * p.ldo + head * kHD;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t o[32];
+                    tmem_ld32(tO_row + c * 32, o);
+                    tmem_wait_ld();
+                    if (row < p.q_rows) {
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) {
+                            uint4 pkt;
+                            pkt.x = pack_bf16x2(__uint_as_float(o[v * 8 + 0]) * inv_l, __uint_as_float(o[v * 8 + 1]) * inv_l);
+                            pkt.y = pack_bf16x2(__uint_as_float(o[v * 8 + 2]) * inv_l, __uint_as_float(o[v * 8 + 3]) * inv_l);
+                            pkt.z = pack_bf16x2(__uint_as_float(o[v * 8 + 4]) * inv_l, __uint_as_float(o[v * 8 + 5]) * inv_l);
+                            pkt.w = pack_bf16x2(__uint_as_float(o[v * 8 + 6]) * inv_l, __uint_as_float(o[v * 8 + 7]) * inv_l);
+                            *reinterpret_cast<uint4*>(optr + c * 32 + v * 8) = pkt;
+                        }
                     }
                 }
-                // O has been read: the next segment's first P V may overwrite it
-                tc_fence_before();
-                mbar_arrive(&o_empty[w]);
-                cnt += n_kv;
+            } else {
+                // partial: un-normalised O, reference max (log2 units) and sum
+                float* po = p.part_o + (static_cast<int64_t>(piece) * (2 * kQT) + row_in_pair) * kHD;
+                float* pml = p.part_ml + (static_cast<int64_t>(piece) * (2 * kQT) + row_in_pair) * 2;
+                pml[0] = m_used * sl2;
+                pml[1] = l;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t o[32];
+                    tmem_ld32(tO_row + c * 32, o);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int v = 0; v < 8; ++v)
+                        *reinterpret_cast<uint4*>(po + c * 32 + v * 4) = make_uint4(o[v * 4], o[v * 4 + 1], o[v * 4 + 2], o[v * 4 + 3]);
+                }
             }
-            t_run += n_kv;
         }
     }
 
@@ -662,26 +555,17 @@ attn_combine_kernel(const AttnParams p) {
     const int gw = blockIdx.x * 8 + warp;  // (split item, row in pair)
     const int sitem = gw / (2 * kQT);
     const int r = gw % (2 * kQT);
-    int item, slot0, nslots;
-    if (p.comb_items != nullptr) {         // planned schedule: the item's partial slots are listed
-        item = p.comb_items[sitem].item;
-        slot0 = p.comb_items[sitem].slot0;
-        nslots = p.comb_items[sitem].nslots;
-    } else {                               // analytic schedule: `split` pieces per item of the tail wave
-        item = p.n_whole + sitem;
-        slot0 = sitem * p.split;
-        nslots = p.split;
-    }
+    const int item = p.n_whole + sitem;
     const int head = item / p.num_q_pairs;
     const int row = (item % p.num_q_pairs) * (2 * kQT) + r;
     if (row >= p.q_rows) return;
     float m = -INFINITY;
-    for (int s = 0; s < nslots; ++s)
-        m = fmaxf(m, p.part_ml[(static_cast<int64_t>(slot0 + s) * (2 * kQT) + r) * 2]);
+    for (int s = 0; s < p.split; ++s)
+        m = fmaxf(m, p.part_ml[((static_cast<int64_t>(sitem) * p.split + s) * (2 * kQT) + r) * 2]);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     float l = 0.f;
-    for (int s = 0; s < nslots; ++s) {
-        const int64_t base = static_cast<int64_t>(slot0 + s) * (2 * kQT) + r;
+    for (int s = 0; s < p.split; ++s) {
+        const int64_t base = (static_cast<int64_t>(sitem) * p.split + s) * (2 * kQT) + r;
         const float a = ex2_approx(p.part_ml[base * 2] - m);
         l += p.part_ml[base * 2 + 1] * a;
         const float4 o = *reinterpret_cast<const float4*>(p.part_o + base * kHD + lane * 4);
@@ -695,173 +579,6 @@ attn_combine_kernel(const AttnParams p) {
     pkt.x = pack_bf16x2(acc.x * inv, acc.y * inv);
     pkt.y = pack_bf16x2(acc.z * inv, acc.w * inv);
     *reinterpret_cast<uint2*>(p.out + static_cast<int64_t>(row) * p.ldo + head * kHD + lane * 4) = pkt;
-}
-
-// ---------------------------------------------------------------------------------------------- planned schedule
-// When the (head, 256-row pair) items do not fill whole waves of SMs well — the sequence-parallel shards: 72 items of
-// which 12 are half-empty at 8 ranks, 132 items at 4 ranks — the key tiles of all items are laid end to end and cut
-// into one equal-COST share per SM.  A CTA then runs up to kMaxSeg segments (the tail of one item, whole items, the
-// head of the next); items cut across CTAs are merged by attn_combine_kernel.  Built on the host once per shape.
-struct PlanKey {
-    int q_rows, heads, n_tiles, n_old_tiles, sms;
-    bool operator==(const PlanKey& o) const {
-        return q_rows == o.q_rows && heads == o.heads && n_tiles == o.n_tiles && n_old_tiles == o.n_old_tiles && sms == o.sms;
-    }
-};
-struct HostPlan {
-    int grid = 0, n_comb = 0, n_slots = 0;
-    std::vector<AttnSeg> segs;          // [grid][kMaxSeg]
-    std::vector<int32_t> counts;        // [grid]
-    std::vector<CombineItem> comb;
-    double efficiency = 0.0;            // planned: total cost / (grid * largest CTA cost)
-};
-// cost of one key tile of a single-tile item relative to a two-tile (ping-pong) item
-constexpr double kSingleTileCost = 0.62;
-
-// Returns false when no schedule within the limits exists (caller keeps the analytic one).
-bool plan_schedule(int q_rows, int heads, int n_tiles, int n_old_tiles, int sms, HostPlan& out) {
-    const int pairs = (q_rows + 2 * kQT - 1) / (2 * kQT);
-    const int items = pairs * heads;
-    auto cost_of = [&](int item) { return ((item % pairs) * 2 * kQT + kQT < q_rows) ? 1.0 : kSingleTileCost; };
-    double total = 0.0;
-    for (int i = 0; i < items; ++i) total += cost_of(i) * n_tiles;
-    const int min_seg = n_tiles < 64 ? 1 : 8;      // do not cut segments shorter than this many tiles
-    for (int attempt = 0; attempt < 24; ++attempt) {
-        const double cap = total / sms * (1.0 + 0.005 * attempt);
-        std::vector<std::vector<AttnSeg>> cta(1);
-        std::vector<CombineItem> comb;
-        double room = cap, worst = 0.0, used = 0.0;
-        int next_slot = 0;
-        bool ok = true;
-        for (int it = 0; it < items && ok; ++it) {
-            const double c = cost_of(it);
-            int pos = 0, first_slot = -1, nslots = 0;
-            while (pos < n_tiles) {
-                const int rem = n_tiles - pos;
-                const int can = static_cast<int>(room / c + 1e-9);
-                const bool empty_cta = cta.back().empty();
-                int take;
-                if (can >= rem) {
-                    take = rem;                                   // the rest of the item fits
-                } else if (can >= min_seg && rem - can >= min_seg) {
-                    take = can;                                   // cut here, both sides long enough
-                } else if (can >= 2 * min_seg) {
-                    take = rem - min_seg;                         // leave a leftover of exactly min_seg for the next CTA
-                    if (take > can) take = can;
-                } else if (!empty_cta) {
-                    worst = std::max(worst, used);                // too little room left: next CTA
-                    cta.emplace_back();
-                    room = cap;
-                    used = 0.0;
-                    continue;
-                } else {
-                    take = rem < min_seg ? rem : std::max(can, 1);   // cannot happen with cap >= min_seg tiles; progress anyway
-                }
-                AttnSeg sg;
-                sg.item = it;
-                sg.r0_begin = pos;
-                sg.r0_count = take;
-                sg.r1_begin = pos + take;
-                sg.r1_count = 0;
-                sg.slot = -1;
-                if (!(pos == 0 && take == n_tiles)) {
-                    sg.slot = next_slot++;
-                    if (first_slot < 0) first_slot = sg.slot;
-                    ++nslots;
-                }
-                cta.back().push_back(sg);
-                if (cta.back().size() > static_cast<size_t>(kMaxSeg)) ok = false;
-                pos += take;
-                room -= take * c;
-                used += take * c;
-                if (room < min_seg * c && (pos < n_tiles || it + 1 < items)) {
-                    worst = std::max(worst, used);
-                    cta.emplace_back();
-                    room = cap;
-                    used = 0.0;
-                }
-            }
-            if (nslots > 0) comb.push_back(CombineItem{it, first_slot, nslots});
-        }
-        worst = std::max(worst, used);
-        if (!cta.empty() && cta.back().empty()) cta.pop_back();
-        if (!ok || static_cast<int>(cta.size()) > sms) continue;
-        out = HostPlan{};
-        out.grid = static_cast<int>(cta.size());
-        out.segs.assign(static_cast<size_t>(out.grid) * kMaxSeg, AttnSeg{0, 0, 0, 0, 0, -1});
-        out.counts.assign(out.grid, 0);
-        for (int b = 0; b < out.grid; ++b) {
-            // segments that touch in-flight tiles (ids >= n_old_tiles) go last: the flag wait comes as late as possible
-            std::stable_sort(cta[b].begin(), cta[b].end(), [&](const AttnSeg& x, const AttnSeg& y) {
-                const bool nx = x.r0_begin + x.r0_count > n_old_tiles, ny = y.r0_begin + y.r0_count > n_old_tiles;
-                return !nx && ny;
-            });
-            out.counts[b] = static_cast<int32_t>(cta[b].size());
-            for (size_t i = 0; i < cta[b].size(); ++i) out.segs[static_cast<size_t>(b) * kMaxSeg + i] = cta[b][i];
-        }
-        out.comb = comb;
-        out.n_comb = static_cast<int>(comb.size());
-        out.n_slots = next_slot;
-        out.efficiency = total / (static_cast<double>(sms) * worst);
-        return true;
-    }
-    return false;
-}
-
-// efficiency of the analytic schedule (whole waves + split tail) under the same cost model
-static double analytic_efficiency(int q_rows, int heads, int sms, int n_whole, int rem, int split) {
-    const int pairs = (q_rows + 2 * kQT - 1) / (2 * kQT);
-    const int items = pairs * heads;
-    double total = 0.0;
-    for (int i = 0; i < items; ++i) total += ((i % pairs) * 2 * kQT + kQT < q_rows) ? 1.0 : kSingleTileCost;
-    const double waves = static_cast<double>((n_whole + sms - 1) / sms) +
-                         (rem ? static_cast<double>((rem * split + sms - 1) / sms) / split : 0.0);
-    return total / (sms * waves);
-}
-
-struct DevicePlan {
-    PlanKey key;
-    int dev;
-    int grid, n_comb, n_slots;
-    AttnSeg* segs;
-    int32_t* counts;
-    CombineItem* comb;
-};
-static std::vector<DevicePlan> g_plans;
-
-// Looks the shape up in the per-process plan cache; builds + uploads it on first use.  nullptr: use the analytic one.
-static const DevicePlan* get_plan(int q_rows, int heads, int n_tiles, int n_old_tiles, int sms, double analytic_eff) {
-    static const bool enabled = [] {
-        const char* e = getenv("IFX_ATTN_PLAN");
-        return e == nullptr || e[0] != '0';
-    }();
-    if (!enabled || analytic_eff >= 0.95) return nullptr;
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
-    const PlanKey key{q_rows, heads, n_tiles, n_old_tiles, sms};
-    for (const DevicePlan& d : g_plans)
-        if (d.dev == dev && d.key == key) return d.grid > 0 ? &d : nullptr;
-    DevicePlan d{};
-    d.key = key;
-    d.dev = dev;
-    HostPlan hp;
-    if (g_plans.size() < 256 && plan_schedule(q_rows, heads, n_tiles, n_old_tiles, sms, hp) &&
-        hp.efficiency > analytic_eff + 0.02) {
-        bool ok = cudaMalloc(&d.segs, hp.segs.size() * sizeof(AttnSeg)) == cudaSuccess &&
-                  cudaMalloc(&d.counts, hp.counts.size() * sizeof(int32_t)) == cudaSuccess &&
-                  cudaMalloc(&d.comb, std::max<size_t>(1, hp.comb.size()) * sizeof(CombineItem)) == cudaSuccess;
-        ok = ok && cudaMemcpy(d.segs, hp.segs.data(), hp.segs.size() * sizeof(AttnSeg), cudaMemcpyHostToDevice) == cudaSuccess &&
-             cudaMemcpy(d.counts, hp.counts.data(), hp.counts.size() * sizeof(int32_t), cudaMemcpyHostToDevice) == cudaSuccess &&
-             (hp.comb.empty() || cudaMemcpy(d.comb, hp.comb.data(), hp.comb.size() * sizeof(CombineItem),
-                                            cudaMemcpyHostToDevice) == cudaSuccess);
-        if (ok) {
-            d.grid = hp.grid;
-            d.n_comb = hp.n_comb;
-            d.n_slots = hp.n_slots;
-        }
-    }
-    g_plans.push_back(d);       // grid == 0 records "no better plan for this shape"
-    return g_plans.back().grid > 0 ? &g_plans.back() : nullptr;
 }
 
 // Which key rows a launch attends, and (sequence parallel) which of them are still in flight from the peers.
@@ -894,10 +611,6 @@ static void fill_defaults(AttnParams& p) {
     p.wait_timeout_ns = 0;
     p.no_dep_wait = 0;
     p.push = PeerPushParams{};
-    p.seg_table = nullptr;
-    p.seg_count = nullptr;
-    p.comb_items = nullptr;
-    p.n_comb = 0;
 }
 
 // returns the total number of key tiles
@@ -1013,20 +726,7 @@ static ifx_status attention_launch(const void* q, int64_t ldq, const void* k, co
     if (split == 1) rem = 0;
     p.n_whole = items - rem;
     p.split = split;
-    int pieces = rem * split;
-    int n_comb = rem;                       // items merged by the combine kernel
-    int planned_grid = 0;
-    const DevicePlan* plan = get_plan(p.q_rows, heads, n_kv, p.wait_flags ? p.n_old_tiles : n_kv, sms,
-                                      analytic_efficiency(p.q_rows, heads, sms, p.n_whole, rem, split));
-    if (plan != nullptr) {
-        p.seg_table = plan->segs;
-        p.seg_count = plan->counts;
-        p.comb_items = plan->comb;
-        p.n_comb = plan->n_comb;
-        pieces = plan->n_slots;
-        n_comb = plan->n_comb;
-        planned_grid = plan->grid;
-    }
+    const int pieces = rem * split;
     if (pieces > 0) {
         int dev = 0;
         IFX_CUDA_OK(cudaGetDevice(&dev));
@@ -1043,7 +743,7 @@ static ifx_status attention_launch(const void* q, int64_t ldq, const void* k, co
         p.part_o = sc.ptr;
         p.part_ml = sc.ptr + static_cast<size_t>(pieces) * (2 * kQT) * kHD;
     }
-    const int grid = planned_grid > 0 ? planned_grid : p.n_whole + pieces;
+    const int grid = p.n_whole + pieces;
     if (keys != nullptr && keys->push != nullptr) {
         // The CTAs that carry a slice of the exchange must all be resident before any CTA can be blocked on the peers'
         // flags: keep them inside the first wave (lowest block indices are dispatched first) with some margin.
@@ -1071,11 +771,11 @@ static ifx_status attention_launch(const void* q, int64_t ldq, const void* k, co
         ProfScope prof(label, stream);
         st = launch_attn_kernel(grid, tmQ, tmK, tmV, p, keys != nullptr && keys->pdl, stream);
         if (st != IFX_OK) return st;
-        if (n_comb > 0)
-            IFX_CUDA_OK(launch_kernel(attn_combine_kernel, dim3(n_comb * (2 * kQT) / 8), dim3(256), 0, stream, true, p));
+        if (pieces > 0)
+            IFX_CUDA_OK(launch_kernel(attn_combine_kernel, dim3(rem * (2 * kQT) / 8), dim3(256), 0, stream, true, p));
     }
     IFX_LAUNCH_OK("attn_fwd_kernel");
-    if (n_comb > 0) count_launch();
+    if (pieces > 0) count_launch();
     return IFX_OK;
 }
 
@@ -1189,52 +889,6 @@ extern "C" ifx_status ifx_attention_partial(const void* q, int64_t ldq, const vo
         if (st != IFX_OK) return st;
     }
     IFX_LAUNCH_OK("attn_fwd_kernel<partial>");
-    return IFX_OK;
-}
-
-extern "C" ifx_status ifx_attention_plan_info(int32_t q_rows, int32_t heads, int32_t n_tiles, int32_t n_old_tiles,
-                                              int32_t sms, int32_t* grid, double* planned_efficiency,
-                                              double* analytic_efficiency_out, int32_t* segments, int32_t segments_cap) {
-    IFX_CHECK_ARG(q_rows > 0 && heads > 0 && n_tiles > 0 && n_old_tiles >= 0 && n_old_tiles <= n_tiles && sms > 0,
-                  "ifx_attention_plan_info: bad shape");
-    IFX_CHECK_ARG(grid && planned_efficiency && analytic_efficiency_out, "ifx_attention_plan_info: null pointer");
-    // the analytic schedule, as attention_launch derives it
-    const int pairs = (q_rows + 2 * kQT - 1) / (2 * kQT);
-    const int items = pairs * heads;
-    int rem = items % sms, split = 1;
-    if (rem != 0 && n_tiles >= 2 * kMaxSplit) {
-        double best = 1.0;
-        for (int s = 2; s <= kMaxSplit; ++s) {
-            const double cost = static_cast<double>((rem * s + sms - 1) / sms) / s;
-            if (cost < best - 1e-9) {
-                best = cost;
-                split = s;
-            }
-        }
-    }
-    if (split == 1) rem = 0;
-    *analytic_efficiency_out = analytic_efficiency(q_rows, heads, sms, items - rem, rem, split);
-    HostPlan hp;
-    if (!plan_schedule(q_rows, heads, n_tiles, n_old_tiles, sms, hp)) {
-        *grid = 0;
-        *planned_efficiency = 0.0;
-        return IFX_OK;
-    }
-    *grid = hp.grid;
-    *planned_efficiency = hp.efficiency;
-    if (segments != nullptr) {
-        // rows of 7 int32: cta, item, r0_begin, r0_count, r1_begin, r1_count, slot
-        int n = 0;
-        for (int b = 0; b < hp.grid; ++b)
-            for (int i = 0; i < hp.counts[b]; ++i) {
-                IFX_CHECK_ARG(n < segments_cap, "ifx_attention_plan_info: segments_cap too small");
-                const AttnSeg& sg = hp.segs[static_cast<size_t>(b) * kMaxSeg + i];
-                int32_t* o = segments + 7 * n++;
-                o[0] = b; o[1] = sg.item; o[2] = sg.r0_begin; o[3] = sg.r0_count; o[4] = sg.r1_begin; o[5] = sg.r1_count;
-                o[6] = sg.slot;
-            }
-        if (n < segments_cap) segments[7 * n] = -1;   // terminator
-    }
     return IFX_OK;
 }
 

@@ -274,6 +274,13 @@ ifx_status ifx_attention_partial(const void* q, int64_t ldq, const void* k, cons
                                  int32_t piece_first, int32_t piece_count, void* stream);
 ifx_status ifx_attention_combine(const void* workspace, int32_t pieces_per_item, void* out, int64_t ldo,
                                  int64_t q_rows, int32_t heads, int32_t head_dim, void* stream);
+/* Same as ifx_attention_gqa, also returning the log-sum-exp of the scaled scores, lse[h * q_rows + r] (fp32, natural
+ * log) — the (out, lse) pair the reference's attention backends return for LSE merging
+ * (models/attention/backends.py:58-72 flash_attn_forward; distributed.py:27-46 update_out_and_lse). */
+ifx_status ifx_attention_lse(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, void* out,
+                             int64_t ldo, float* lse, int64_t q_rows, int64_t kv_rows, int32_t heads, int32_t kv_heads,
+                             int32_t head_dim, float softmax_scale, void* stream);
+
 /* Attention over a LIST of key-row extents of k/v[0:kv_rows_total): up to IFX_ATTN_MAX_EXTENTS [row0, rows) pairs
  * (runs of physically consecutive cache pages).  Rows that follow an extent in memory are never attended: their
  * scores are masked and their V rows are zeroed in shared memory before the P V product, so unmapped pages may hold

@@ -135,6 +135,7 @@ SIGNATURES = {
                                         _f32, _vp, _i64, _i32, _i32, _i32, _vp]),
     "ifx_attention_combine": (C.c_int, [_vp, _i32, _vp, _i64, _i64, _i32, _i32, _vp]),
     "ifx_attention_kv": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _i64, _f32, _vp]),
+    "ifx_attention_lse": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _f32, _vp]),
     "ifx_attention_extents": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _i64, C.POINTER(_i64), _i32, _vp, _i64, _i64, _i32,
                                         _i32, _i32, _f32, _vp]),
     "ifx_attention_kv_wait": (C.c_int, [_vp, _i64, _vp, C.POINTER(KvPlan), _vp, _i32, _i64, _i32, _vp, _i64, _i64, _f32,

@@ -58,6 +58,7 @@ struct AttnParams {
     int64_t ldo;
     float* part_o;       // [pieces][256][128] un-normalised O
     float* part_ml;      // [pieces][256][2]   (max * scale_log2, sum)
+    float* lse;          // optional [heads][q_rows] natural-log softmax denominators (log-sum-exp of the scaled scores)
     // ---- partial mode (ifx_attention_partial): every CTA emits a partial; keys are a list of row extents
     int32_t partial;         // 1: blockIdx = item * piece_count + sub, slot = item * pieces_per_item + piece_first + sub
     int32_t pieces_per_item;
@@ -500,6 +501,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             if (piece < 0) {
                 // epilogue: O / l -> bf16 -> global
                 const float inv_l = 1.0f / l;
+                if (p.lse != nullptr && row < p.q_rows)
+                    p.lse[static_cast<int64_t>(head) * p.q_rows + row] = (m_used * sl2 + log2f(l)) * 0.6931471805599453f;
                 __nv_bfloat16* optr = p.out + static_cast<int64_t>(row) * p.ldo + head * kHD;
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
@@ -575,6 +578,8 @@ attn_combine_kernel(const AttnParams p) {
         acc.w += o.w * a;
     }
     const float inv = 1.0f / l;
+    if (p.lse != nullptr && lane == 0)
+        p.lse[static_cast<int64_t>(head) * p.q_rows + row] = (m + log2f(l)) * 0.6931471805599453f;
     uint2 pkt;
     pkt.x = pack_bf16x2(acc.x * inv, acc.y * inv);
     pkt.y = pack_bf16x2(acc.z * inv, acc.w * inv);
@@ -593,11 +598,13 @@ struct KeySpec {
     unsigned long long timeout_ns = 0;
     bool pdl = false;              // run next to the preceding kernel on the stream instead of after it (only behind a
                                    // kernel that releases this one explicitly, e.g. peer_push_kernel)
+    float* lse = nullptr;                   // optional log-sum-exp output [heads][q_rows]
     const PeerPushParams* push = nullptr;   // fused exchange: see AttnParams::push
     int push_ctas = 0;                      // cap on the CTAs sharing the copy (0: default)
 };
 
 static void fill_defaults(AttnParams& p) {
+    p.lse = nullptr;
     p.partial = 0;
     p.pieces_per_item = p.piece_count = 1;
     p.piece_first = 0;
@@ -700,6 +707,7 @@ static ifx_status attention_launch(const void* q, int64_t ldq, const void* k, co
     p.ldo = ldo;
     p.part_o = nullptr;
     p.part_ml = nullptr;
+    p.lse = keys != nullptr ? keys->lse : nullptr;
     const int n_kv = fill_keys(p, keys, kv_rows);
     int64_t key_rows = kv_rows;
     if (p.n_ext) {
@@ -930,6 +938,16 @@ extern "C" ifx_status ifx_attention_gqa(const void* q, int64_t ldq, const void* 
                                         int32_t kv_heads, int32_t head_dim, float softmax_scale, void* stream) {
     return attention_launch(q, ldq, k, v, ldkv, out, ldo, q_rows, kv_rows, heads, head_dim, softmax_scale,
                             static_cast<cudaStream_t>(stream), kv_heads);
+}
+
+extern "C" ifx_status ifx_attention_lse(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, void* out,
+                                        int64_t ldo, float* lse, int64_t q_rows, int64_t kv_rows, int32_t heads,
+                                        int32_t kv_heads, int32_t head_dim, float softmax_scale, void* stream) {
+    IFX_CHECK_ARG(lse != nullptr, "ifx_attention_lse: null lse");
+    KeySpec ks;
+    ks.lse = lse;
+    return attention_launch(q, ldq, k, v, ldkv, out, ldo, q_rows, kv_rows, heads, head_dim, softmax_scale,
+                            static_cast<cudaStream_t>(stream), kv_heads, &ks);
 }
 
 extern "C" ifx_status ifx_attention_extents(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv,

@@ -15,7 +15,7 @@ from ._lib import EPI_BIAS, EPI_BIAS_F32, EPI_BIAS_GATE_RES, EPI_BIAS_GELU, EPI_
 
 __all__ = [
     "ln_modulate", "gemm", "rmsnorm", "quantize_fp8", "ln_modulate_fp8", "gemm_fp8", "attention", "attention_gqa", "attention_ranges", "attention_partial", "attention_combine",
-    "attention_workspace_bytes", "attention_extents", "qk_norm_rope_append", "PagedKV", "rope_table",
+    "attention_workspace_bytes", "attention_extents", "attention_lse", "qk_norm_rope_append", "PagedKV", "rope_table",
     "EPI_BIAS", "EPI_BIAS_GELU", "EPI_BIAS_GATE_RES", "EPI_BIAS_GELU_ERF", "EPI_BIAS_F32",
     "qk_norm_rope_append_peers", "peer_push", "magi_qkv_post", "head_layernorm", "gate_norm_residual", "silu_mul",
 ]
@@ -211,6 +211,24 @@ def attention_gqa(q, k, v, heads, kv_heads, out=None, *, softmax_scale=None):
                                              out.data_ptr(), out.stride(0), q.shape[0], k.shape[0], heads, kv_heads,
                                              head_dim, scale, _stream()))
     return out
+
+
+def attention_lse(q, k, v, heads, kv_heads=None, out=None, *, softmax_scale=None):
+    """(out [Lq, heads*D] bf16, lse [heads, Lq] fp32): attention plus the log-sum-exp of the scaled scores, the pair the
+    reference's attention backends return (backends.py:58-72)."""
+    q, k, v = _bf16_2d(q, "q"), _bf16_2d(k, "k"), _bf16_2d(v, "v")
+    kv_heads = kv_heads or heads
+    head_dim = q.shape[1] // heads
+    if k.shape != v.shape or k.shape[1] != kv_heads * head_dim or k.stride(0) != v.stride(0):
+        raise ValueError("attention_lse: k / v must be [Lk, kv_heads*D] with identical strides")
+    if out is None:
+        out = torch.empty((q.shape[0], q.shape[1]), dtype=torch.bfloat16, device=q.device)
+    lse = torch.empty((heads, q.shape[0]), dtype=torch.float32, device=q.device)
+    scale = softmax_scale if softmax_scale is not None else head_dim ** -0.5
+    _lib.check(_lib.load().ifx_attention_lse(q.data_ptr(), q.stride(0), k.data_ptr(), v.data_ptr(), k.stride(0),
+                                             out.data_ptr(), out.stride(0), lse.data_ptr(), q.shape[0], k.shape[0], heads,
+                                             kv_heads, head_dim, scale, _stream()))
+    return out, lse
 
 
 def attention_ranges(q, k, v, q_ranges, k_ranges, heads, kv_heads, *, softmax_scale=None):

@@ -95,6 +95,59 @@ class CausalWanSelfAttention(_Attn):
         super().__init__(dim, num_heads, eps)
         self.local_attn_size, self.sink_size, self.qk_norm = local_attn_size, sink_size, qk_norm
         self.parallel_config = parallel_config
+        self._qkv = None
+
+    def forward(self, x, seq_lens, grid_sizes, freqs, block_mask, kv_cache_meta=None, current_start=0,
+                cache_start=None):
+        """The reference's stand-alone call (causal_model.py:147-334, KV-cached branch, single process): x [B, L, C]
+        (already normed / modulated), kv_cache_meta = {"k", "v": [B, N, H, D] cache tensors, "global_end_index",
+        "local_end_index": 1-element int64 tensors}, freqs = ops.rope_table(model.freqs) -> (y [B, L, C], k_view,
+        v_view).  Same arithmetic on the native kernels: fused q|k|v GEMM, QK-RMSNorm + fp64 RoPE, the reference's own
+        evict / roll / write on its tensor layout, tcgen05 attention over the cache prefix, output projection.
+        The hot path does NOT go through here (the block calls ifx_wan_block_forward on the paged cache); this method
+        exists so that code written against the reference's module surface keeps working."""
+        if kv_cache_meta is None:
+            raise NotImplementedError("only the KV-cached inference branch is built")
+        pc = self.parallel_config
+        if pc is not None and pc.world_size > 1:
+            raise NotImplementedError("the stand-alone self-attention call is single-process; the sequence-parallel "
+                                      "path is CausalWanAttentionBlock.forward")
+        b, s, c = x.shape
+        n, d = self.num_heads, self.head_dim
+        if self._qkv is None or self._qkv[0].device != x.device:
+            self._qkv = (torch.cat([self.q.weight, self.k.weight, self.v.weight]).detach().contiguous(),
+                         torch.cat([self.q.bias, self.k.bias, self.v.bias]).detach().contiguous())
+        f_, h_, w_ = (int(v) for v in grid_sizes[0])
+        frame_seqlen = h_ * w_
+        grid = RopeGrid(f_, h_, w_, current_start // frame_seqlen, 0, frame_seqlen)
+        kc, vc = kv_cache_meta["k"], kv_cache_meta["v"]
+        cache_size = kc.shape[1]
+        outs = []
+        for bi in range(b):
+            qkv = ops.gemm(x[bi].contiguous(), self._qkv[0], self._qkv[1])
+            q, k_new, v_new = ops.qk_norm_rope_append(qkv, self.norm_q.weight, self.norm_k.weight, freqs, grid, n, d,
+                                                      eps=self.eps)
+            # causal_model.py:277-304 on the reference's tensor layout
+            current_end = current_start + s
+            global_end = int(kv_cache_meta["global_end_index"].item())
+            local_end = int(kv_cache_meta["local_end_index"].item())
+            sink_tokens = self.sink_size * frame_seqlen
+            if self.local_attn_size != -1 and current_end > global_end and s + local_end > cache_size:
+                evicted = s + local_end - cache_size
+                rolled = local_end - evicted - sink_tokens
+                kc[bi, sink_tokens:sink_tokens + rolled] = kc[bi, sink_tokens + evicted:sink_tokens + evicted + rolled].clone()
+                vc[bi, sink_tokens:sink_tokens + rolled] = vc[bi, sink_tokens + evicted:sink_tokens + evicted + rolled].clone()
+                local_end_new = local_end + current_end - global_end - evicted
+            else:
+                local_end_new = local_end + current_end - global_end
+            local_start = local_end_new - s
+            kc[bi, local_start:local_end_new] = k_new.view(s, n, d)
+            vc[bi, local_start:local_end_new] = v_new.view(s, n, d)
+            o = ops.attention(q, kc[bi, :local_end_new].reshape(local_end_new, c), vc[bi, :local_end_new].reshape(local_end_new, c), n)
+            outs.append(ops.gemm(o, self.o.weight, self.o.bias))
+        kv_cache_meta["global_end_index"].fill_(current_end)
+        kv_cache_meta["local_end_index"].fill_(local_end_new)
+        return torch.stack(outs), kc[:, :local_end_new], vc[:, :local_end_new]
 
 
 class WanT2VCrossAttention(_Attn):
@@ -470,7 +523,8 @@ class _Workspace:
 
 
 class CausalHead(nn.Module):
-    """causal_model.py:487-515.  [S, C] -> [S, 64]: 0.03 % of the layer FLOPs; stays on torch ops."""
+    """causal_model.py:487-515.  [S, C] -> [S, 64] on the native kernels: LayerNorm + per-frame modulation
+    (ifx_ln_modulate) and the projection with its bias (ifx_gemm_bf16), two launches."""
 
     def __init__(self, dim, out_dim, patch_size, eps=1e-6):
         super().__init__()
@@ -482,9 +536,15 @@ class CausalHead(nn.Module):
     def forward(self, x, e):
         """x [B, L1, C]; e [B, F, 1, C]."""
         num_frames, frame_seqlen = e.shape[1], x.shape[1] // e.shape[1]
-        e = (self.modulation.unsqueeze(1) + e).chunk(2, dim=2)
-        h = F.layer_norm(x, (self.dim,), None, None, self.eps).unflatten(dim=1, sizes=(num_frames, frame_seqlen))
-        return self.head(h * (1 + e[1]) + e[0])
+        m = (self.modulation.unsqueeze(1) + e).contiguous()          # [B, F, 2, C]: shift, scale  (:510)
+        if not (x.is_cuda and x.dtype == torch.bfloat16):
+            raise ValueError("inferix_b200 head runs in bfloat16 on CUDA")
+        outs = []
+        for bi in range(x.shape[0]):
+            h = ops.ln_modulate(x[bi].contiguous(), shift=m[bi, :, 0], scale=m[bi, :, 1], tokens_per_frame=frame_seqlen,
+                                eps=self.eps)
+            outs.append(ops.gemm(h, self.head.weight, self.head.bias))
+        return torch.stack(outs).unflatten(dim=1, sizes=(num_frames, frame_seqlen))
 
 
 class CausalWanModel(nn.Module):

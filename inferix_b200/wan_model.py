@@ -461,6 +461,7 @@ class CausalWanAttentionBlock(nn.Module):
 _SP_MODE = __import__("os").environ.get("IFX_SP_MODE", "overlap")
 if _SP_MODE not in ("overlap", "store", "ops"):
     raise ValueError(f"IFX_SP_MODE={_SP_MODE!r}: expected overlap, store or ops")
+# measured on B200 boxes (profiles/r02*_sp*): 8 ranks 988 ms / block fused vs 1028 ms store + wait; 2 ranks 3266 vs 3216
 
 
 def _sp_push_ctas(world: int) -> int:

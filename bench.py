@@ -51,6 +51,12 @@ WORKLOADS = {
     # BASELINE.json configs[2]: CausVid 540p (544x960 -> 68x120 latent), FP8 per-tensor linears, 3 steps, 7-block cache
     "causvid_540p_fp8": dict(latent_hw=(68, 120), frames_per_block=3, timesteps=3, window_blocks=7, model="WAN_1_3B",
                              fp8=True),
+    # same shape with the qconfig the reference's quantisation examples actually request (dynamic per-token activation
+    # x per-channel weight, run_causvid_quantized.py:32-37): e4m3 and int8
+    "causvid_540p_fp8_dynamic": dict(latent_hw=(68, 120), frames_per_block=3, timesteps=3, window_blocks=7,
+                                     model="WAN_1_3B", q8="fp8"),
+    "causvid_540p_int8_dynamic": dict(latent_hw=(68, 120), frames_per_block=3, timesteps=3, window_blocks=7,
+                                      model="WAN_1_3B", q8="int8"),
     # tiny shape for smoke runs
     "tiny": dict(latent_hw=(16, 16), frames_per_block=3, timesteps=4, window_blocks=2, model="TINY"),
 }
@@ -401,6 +407,8 @@ def main():
         model.begin_fp8_calibration()
         pipe.denoise_block(noise_dev[0], frame0, common)
         model.finish_fp8_calibration()
+    if wl.get("q8"):
+        model.quantize_dynamic(wl["q8"])
     for _ in range(args.warmup):
         pipe.denoise_block(noise_dev[step], frame0 + step * n, common)
         step += 1
@@ -532,7 +540,11 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args, wl),
+            "vs_baseline": None,
+            "dtype": ("bf16 (block linears: e4m3 x e4m3, static per-tensor scales)" if wl.get("fp8") else
+                      f"bf16 (block linears: {wl['q8']} x {wl['q8']}, dynamic per-token x per-channel scales)"
+                      if wl.get("q8") else "bf16"),
+            "data": "synthetic", "config": workload_config(args, wl),
             "clocks": clock_info,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": noise_host[0].numel() * 2,
                     "d2h_bytes_per_step": out_host.numel() * 2},

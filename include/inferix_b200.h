@@ -162,6 +162,31 @@ ifx_status ifx_gemm_fp8(const void* A, int64_t lda, const void* W, int64_t ldw, 
                         int64_t ldr, const void* gate, int64_t gate_frame_stride, int64_t tokens_per_frame,
                         void* stream);
 
+/* ---- Dynamic 8-bit linears: per-token activation scales x per-channel weight scales, FP8 (e4m3) or INT8.
+ * This is the qconfig the reference's quantisation examples request (example/quantization/run_causvid_quantized.py:32-37,
+ * run_self_forcing_quantized.py: get_dynamic_fp8_per_token_act_per_channel_weight_qconfig + quantize_dynamic from DAX).
+ * DAX is a dependency that is not vendored in the reference (git clone in its README): the published algorithm is
+ * restated — "DAX parity unpinned" (oracle/wan_oracle.py: dynamic_q8_linear):
+ *     s_a[m] = max(|x[m, :]|, 1e-12) / qmax        s_w[n] = max(|W[n, :]|, 1e-12) / qmax      qmax = 448 | 127
+ *     x_q = rne_sat(x / s_a)   W_q = rne_sat(W / s_w)   y = bf16( (x_q @ W_q^T) * s_a[m] * s_w[n] + bias )
+ * The activation scales never touch the host: they are produced by the kernel that produces the activation and consumed
+ * by the GEMM epilogue. */
+#define IFX_Q8_E4M3 0
+#define IFX_Q8_INT8 1
+/* x[rows, cols] bf16 -> out[rows, cols] 8-bit codes + scales[rows] (fp32). */
+ifx_status ifx_quantize_rows(const void* x, int64_t ldx, void* out, int64_t ldo, float* scales, int64_t rows,
+                             int32_t cols, int32_t kind, void* stream);
+/* ifx_ln_modulate whose result is quantised per token on the way out (the QKV / cross-q / FFN1 GEMM inputs). */
+ifx_status ifx_ln_modulate_quant(const void* x, void* out, float* scales, const void* ln_weight, const void* ln_bias,
+                                 const void* shift, const void* scale, int64_t mod_frame_stride, int64_t rows,
+                                 int32_t cols, int64_t tokens_per_frame, float eps, int32_t kind, void* stream);
+/* out[M,N] = epilogue((A_q[M,K] @ W_q[N,K]^T) * row_scale[m] * col_scale[n] + bias): tcgen05 kind::f8f6f4 (e4m3) or
+ * kind::i8 (S8 x S8 -> S32 accumulators in TMEM); dequantisation, bias and the ifx_gemm_bf16 epilogues fused. K % 16 == 0. */
+ifx_status ifx_gemm_q8(const void* A, int64_t lda, const void* W, int64_t ldw, const float* row_scale,
+                       const float* col_scale, int32_t kind, const void* bias, void* out, int64_t ldo, int64_t M,
+                       int32_t N, int32_t K, int32_t epilogue, const void* residual, int64_t ldr, const void* gate,
+                       int64_t gate_frame_stride, int64_t tokens_per_frame, void* stream);
+
 /* 3-D RoPE table: complex128 [1024, head_dim/2] exactly as CausalWanModel.freqs (causal_model.py:634-641,
  * rope_params components.py:34-52), uploaded once by the host as interleaved (cos, sin) doubles. */
 typedef struct ifx_rope_grid {

@@ -52,6 +52,7 @@ IFX_MAX_PEERS = 8
 IFX_PEER_HANDLE_BYTES = 64
 IFX_ATTN_MAX_EXTENTS = 32
 IFX_SP_STORE, IFX_SP_OVERLAP = 0, 1
+IFX_Q8_E4M3, IFX_Q8_INT8 = 0, 1
 
 
 class PeerDst(C.Structure):
@@ -115,6 +116,10 @@ SIGNATURES = {
     "ifx_ln_modulate_fp8": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _i64, _f32, _f32, _vp]),
     "ifx_gemm_fp8": (C.c_int, [_vp, _i64, _vp, _i64, _f32, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _vp, _i64, _vp,
                                _i64, _i64, _vp]),
+    "ifx_quantize_rows": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _vp]),
+    "ifx_ln_modulate_quant": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _i64, _f32, _i32, _vp]),
+    "ifx_gemm_q8": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _i32, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _vp, _i64, _vp,
+                              _i64, _i64, _vp]),
     "ifx_gemm_bf16": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _vp, _i64, _vp, _i64,
                                 _i64, _vp]),
     "ifx_qk_norm_rope_append": (C.c_int, [_vp, _i64, _vp, _vp, _vp, C.POINTER(RopeGrid), _vp, _i64, _vp,

@@ -728,6 +728,168 @@ qk_norm_rope_append_warp_kernel(const NormRopeParams p) {
         else { CALL(8); }                            \
     } while (0)
 
+// ================================================================== dynamic per-token quantisation (8-bit linears)
+// x[row, :] -> q[row, :] = round(x / s_row) with s_row = max(|x[row, :]|, 1e-12) / qmax  (qmax 448: e4m3 RNE with
+// saturation; 127: int8 RNE), scales[row] = s_row.  The activation half of "dynamic per-token activation x per-channel
+// weight" quantisation (the qconfig the reference's quantisation examples request from DAX,
+// example/quantization/run_causvid_quantized.py:32-37; DAX itself is not vendored — algorithm restated, unpinned).
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ uint2 quant8_dyn(const float (&v)[8], float inv_s, int int8) {
+    uint2 o;
+    if (int8) {
+        uint32_t b[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            int q;
+            asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(q) : "f"(v[e] * inv_s));
+            q = max(q, -127);
+            b[e] = static_cast<uint32_t>(q) & 0xffu;
+        }
+        o.x = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
+        o.y = b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24);
+    } else {
+        float q[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) q[e] = v[e] * inv_s;
+        o.x = static_cast<uint32_t>(pack_e4m3x2(q[0], q[1])) | (static_cast<uint32_t>(pack_e4m3x2(q[2], q[3])) << 16);
+        o.y = static_cast<uint32_t>(pack_e4m3x2(q[4], q[5])) | (static_cast<uint32_t>(pack_e4m3x2(q[6], q[7])) << 16);
+    }
+    return o;
+}
+
+// one warp per row, any width (two passes over the row; the second one hits L2)
+__global__ void __launch_bounds__(kWarpRowCtaThreads)
+quantize_rows_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, uint8_t* __restrict__ out, int64_t ldo,
+                     float* __restrict__ scales, int64_t rows, int cols, int int8) {
+    griddep_launch();
+    griddep_wait();
+    const int lane = threadIdx.x & 31;
+    const int nvec = cols >> 3;
+    const float qmax = int8 ? 127.0f : 448.0f;
+    const int64_t step = static_cast<int64_t>(gridDim.x) * (kWarpRowCtaThreads / 32);
+    for (int64_t row = static_cast<int64_t>(blockIdx.x) * (kWarpRowCtaThreads / 32) + (threadIdx.x >> 5); row < rows;
+         row += step) {
+        const uint4* xr = reinterpret_cast<const uint4*>(x + row * ldx);
+        float amax = 0.f;
+        for (int vi = lane; vi < nvec; vi += 32) {
+            float v[8];
+            unpack8(xr[vi], v);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) amax = fmaxf(amax, fabsf(v[e]));
+        }
+        amax = warp_max(amax);
+        const float s = fmaxf(amax, 1e-12f) / qmax;
+        const float inv_s = 1.0f / s;
+        if (lane == 0) scales[row] = s;
+        uint2* orow = reinterpret_cast<uint2*>(out + row * ldo);
+        for (int vi = lane; vi < nvec; vi += 32) {
+            float v[8];
+            unpack8(xr[vi], v);
+            orow[vi] = quant8_dyn(v, inv_s, int8);
+        }
+    }
+}
+
+// ln_modulate_warp_kernel whose bf16 result is quantised per token on the way out (the row never leaves registers)
+template <int kVec>
+__global__ void __launch_bounds__(kWarpRowCtaThreads, 3)
+ln_modulate_quant_warp_kernel(const __nv_bfloat16* __restrict__ x, uint8_t* __restrict__ out, float* __restrict__ scales,
+                              const __nv_bfloat16* __restrict__ ln_w, const __nv_bfloat16* __restrict__ ln_b,
+                              const __nv_bfloat16* __restrict__ shift, const __nv_bfloat16* __restrict__ scale,
+                              int64_t mod_frame_stride, int64_t rows, int cols, int64_t tokens_per_frame, float eps,
+                              int int8) {
+    griddep_launch();
+    griddep_wait();
+    const int lane = threadIdx.x & 31;
+    const int nvec = cols >> 3;
+    const float qmax = int8 ? 127.0f : 448.0f;
+    const int64_t step = static_cast<int64_t>(gridDim.x) * (kWarpRowCtaThreads / 32);
+    for (int64_t row = static_cast<int64_t>(blockIdx.x) * (kWarpRowCtaThreads / 32) + (threadIdx.x >> 5); row < rows;
+         row += step) {
+        const uint4* xr = reinterpret_cast<const uint4*>(x + row * cols);
+        uint4 raw[kVec];
+#pragma unroll
+        for (int i = 0; i < kVec; ++i) {
+            const int vi = lane + i * 32;
+            raw[i] = vi < nvec ? xr[vi] : make_uint4(0, 0, 0, 0);
+        }
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < kVec; ++i)
+            if (lane + i * 32 < nvec) {
+                float v[8];
+                unpack8(raw[i], v);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acc += v[e];
+            }
+        const float mean = warp_sum(acc) / cols;
+        acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < kVec; ++i)
+            if (lane + i * 32 < nvec) {
+                float v[8];
+                unpack8(raw[i], v);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const float d = v[e] - mean;
+                    acc += d * d;
+                }
+            }
+        const float rstd = rsqrtf(warp_sum(acc) / cols + eps);
+        const int64_t frame = row / tokens_per_frame;
+        const uint4* sh = shift ? reinterpret_cast<const uint4*>(shift + frame * mod_frame_stride) : nullptr;
+        const uint4* sc = scale ? reinterpret_cast<const uint4*>(scale + frame * mod_frame_stride) : nullptr;
+        // the bf16 tensor the reference would hand to the quantised linear, one vector at a time
+        auto result = [&](int i, float (&y)[8]) {
+            const int vi = lane + i * 32;
+            float v[8];
+            unpack8(raw[i], v);
+            if (ln_w) {
+                float w[8], b[8];
+                unpack8(__ldg(reinterpret_cast<const uint4*>(ln_w) + vi), w);
+                unpack8(__ldg(reinterpret_cast<const uint4*>(ln_b) + vi), b);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) y[e] = bf16_round((v[e] - mean) * rstd * w[e] + b[e]);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) y[e] = bf16_round((v[e] - mean) * rstd);
+            }
+            if (sc) {
+                float a[8], b[8];
+                unpack8(__ldg(sc + vi), a);
+                unpack8(__ldg(sh + vi), b);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) y[e] = bf16_round(bf16_round(y[e] * bf16_round(1.0f + a[e])) + b[e]);
+            }
+        };
+        float amax = 0.f;
+#pragma unroll
+        for (int i = 0; i < kVec; ++i)
+            if (lane + i * 32 < nvec) {
+                float y[8];
+                result(i, y);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) amax = fmaxf(amax, fabsf(y[e]));
+            }
+        amax = warp_max(amax);
+        const float s = fmaxf(amax, 1e-12f) / qmax;
+        const float inv_s = 1.0f / s;
+        if (lane == 0) scales[row] = s;
+        uint2* orow = reinterpret_cast<uint2*>(out + row * cols);
+#pragma unroll
+        for (int i = 0; i < kVec; ++i)
+            if (lane + i * 32 < nvec) {
+                float y[8];
+                result(i, y);
+                orow[lane + i * 32] = quant8_dyn(y, inv_s, int8);
+            }
+    }
+}
+
 // Spin until every rank has published `epoch` in this rank's flag array (one lane per source rank).  Bounded: a rank
 // that never arrives traps the kernel after timeout_ns instead of hanging the GPU.
 __global__ void peer_wait_kernel(const long long* flags, int world, long long epoch, unsigned long long timeout_ns) {
@@ -1238,4 +1400,53 @@ extern "C" ifx_status ifx_kv_append(ifx_kv* kv_, const ifx_kv_plan* plan, const 
     p.pl.n = plan->num_pages;
     for (int i = 0; i < plan->num_pages; ++i) p.pl.pages[i] = plan->pages[i];
     return launch_paged_copy(p, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" ifx_status ifx_quantize_rows(const void* x, int64_t ldx, void* out, int64_t ldo, float* scales, int64_t rows,
+                                        int32_t cols, int32_t kind, void* stream) {
+    IFX_CHECK_ARG(x && out && scales, "ifx_quantize_rows: null pointer");
+    IFX_CHECK_ARG(rows > 0 && cols > 0 && cols % 16 == 0, "ifx_quantize_rows: cols must be a multiple of 16");
+    IFX_CHECK_ARG(ldx >= cols && ldx % 8 == 0 && ldo >= cols && ldo % 16 == 0, "ifx_quantize_rows: bad strides");
+    IFX_CHECK_ARG(kind == IFX_Q8_E4M3 || kind == IFX_Q8_INT8, "ifx_quantize_rows: kind must be IFX_Q8_E4M3 or IFX_Q8_INT8");
+    int64_t ctas = (rows + 7) / 8;
+    const int64_t cap = static_cast<int64_t>(sm_count()) * 8;
+    if (ctas > cap) ctas = cap;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    {
+        ProfScope prof("quantize_rows_kernel", st);
+        IFX_CUDA_OK(launch_kernel(quantize_rows_kernel, dim3(static_cast<unsigned>(ctas)), dim3(kWarpRowCtaThreads), 0, st,
+                                  true, static_cast<const __nv_bfloat16*>(x), ldx, static_cast<uint8_t*>(out), ldo, scales,
+                                  rows, cols, kind == IFX_Q8_INT8 ? 1 : 0));
+    }
+    IFX_LAUNCH_OK("quantize_rows_kernel");
+    return IFX_OK;
+}
+
+extern "C" ifx_status ifx_ln_modulate_quant(const void* x, void* out, float* scales, const void* ln_weight,
+                                            const void* ln_bias, const void* shift, const void* scale,
+                                            int64_t mod_frame_stride, int64_t rows, int32_t cols,
+                                            int64_t tokens_per_frame, float eps, int32_t kind, void* stream) {
+    IFX_CHECK_ARG(x && out && scales, "ifx_ln_modulate_quant: null pointer");
+    IFX_CHECK_ARG(rows > 0 && cols > 0 && cols % 16 == 0 && (cols >> 3) <= 256,
+                  "ifx_ln_modulate_quant: cols must be a multiple of 16 and <= 2048 (got %d)", cols);
+    IFX_CHECK_ARG((ln_weight == nullptr) == (ln_bias == nullptr), "ifx_ln_modulate_quant: weight and bias go together");
+    IFX_CHECK_ARG((shift == nullptr) == (scale == nullptr), "ifx_ln_modulate_quant: shift and scale go together");
+    IFX_CHECK_ARG(!scale || (tokens_per_frame > 0 && mod_frame_stride % 8 == 0), "ifx_ln_modulate_quant: bad modulation layout");
+    IFX_CHECK_ARG(kind == IFX_Q8_E4M3 || kind == IFX_Q8_INT8, "ifx_ln_modulate_quant: bad kind");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int64_t tpf = tokens_per_frame > 0 ? tokens_per_frame : 1;
+    const RowLaunch rl = row_launch(rows, cols);
+    {
+        ProfScope prof("ln_modulate_quant_kernel", st);
+#define IFX_LNQ_CALL(K)                                                                                              \
+    IFX_CUDA_OK(launch_kernel(ln_modulate_quant_warp_kernel<K>, dim3(rl.grid), dim3(rl.block), 0, st, true,          \
+                              static_cast<const __nv_bfloat16*>(x), static_cast<uint8_t*>(out), scales,              \
+                              static_cast<const __nv_bfloat16*>(ln_weight), static_cast<const __nv_bfloat16*>(ln_bias), \
+                              static_cast<const __nv_bfloat16*>(shift), static_cast<const __nv_bfloat16*>(scale),    \
+                              mod_frame_stride, rows, cols, tpf, eps, kind == IFX_Q8_INT8 ? 1 : 0))
+        IFX_WARP_ROW_DISPATCH(cols >> 3, IFX_LNQ_CALL);
+#undef IFX_LNQ_CALL
+    }
+    IFX_LAUNCH_OK("ln_modulate_quant_kernel");
+    return IFX_OK;
 }

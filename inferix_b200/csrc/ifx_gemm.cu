@@ -100,7 +100,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc = kFp8 ? make_idesc_e4m3(kBM, kBN) : make_idesc_bf16(kBM, kBN, 0, 0);
+            const uint32_t idesc = kFp8 ? (p.int8 ? make_idesc_s8(kBM, kBN) : make_idesc_e4m3(kBM, kBN))
+                                        : make_idesc_bf16(kBM, kBN, 0, 0);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
@@ -118,7 +119,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
                     for (int k = 0; k < kBK / 16; ++k) {
                         // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the (addr >> 4) field
-                        if (kFp8)
+                        if (kFp8 && p.int8)
+                            umma_ss_i8(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                        else if (kFp8)
                             umma_ss_f8(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
                         else
                             umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
@@ -215,11 +218,18 @@ static bool use_2cta() {
 }
 }  // namespace ifx
 
+// dynamic quantisation extras of the 8-bit family (ifx_gemm_q8)
+struct Q8Scales {
+    const float* row_scale = nullptr;
+    const float* col_scale = nullptr;
+    int int8 = 0;
+};
+
 template <bool kFp8>
 static ifx_status gemm_entry(const void* A, int64_t lda, const void* W, int64_t ldw, float alpha, const void* bias,
                              void* out, int64_t ldo, int64_t M, int32_t N, int32_t K, int32_t epilogue,
                              const void* residual, int64_t ldr, const void* gate, int64_t gate_frame_stride,
-                             int64_t tokens_per_frame, void* stream) {
+                             int64_t tokens_per_frame, void* stream, Q8Scales q8 = Q8Scales()) {
     constexpr int kAlign = kFp8 ? 16 : 8;  // operand rows must be 16-byte multiples
     IFX_CHECK_ARG(A && W && out, "ifx_gemm_bf16: null pointer");
     IFX_CHECK_ARG(M > 0 && N > 0 && K > 0, "ifx_gemm_bf16: empty problem M=%lld N=%d K=%d", (long long)M, N, K);
@@ -271,6 +281,9 @@ static ifx_status gemm_entry(const void* A, int64_t lda, const void* W, int64_t 
     p.N = N;
     p.K = K;
     p.alpha = alpha;
+    p.row_scale = q8.row_scale;
+    p.col_scale = q8.col_scale;
+    p.int8 = q8.int8;
     p.bias = static_cast<const __nv_bfloat16*>(bias);
     p.out = static_cast<__nv_bfloat16*>(out);
     p.ldo = ldo;
@@ -316,4 +329,18 @@ extern "C" ifx_status ifx_gemm_fp8(const void* A, int64_t lda, const void* W, in
     IFX_CHECK_ARG(alpha > 0.f, "ifx_gemm_fp8: alpha (input_scale * weight_scale) must be positive");
     return gemm_entry<true>(A, lda, W, ldw, alpha, bias, out, ldo, M, N, K, epilogue, residual, ldr, gate,
                             gate_frame_stride, tokens_per_frame, stream);
+}
+
+extern "C" ifx_status ifx_gemm_q8(const void* A, int64_t lda, const void* W, int64_t ldw, const float* row_scale,
+                                  const float* col_scale, int32_t kind, const void* bias, void* out, int64_t ldo,
+                                  int64_t M, int32_t N, int32_t K, int32_t epilogue, const void* residual, int64_t ldr,
+                                  const void* gate, int64_t gate_frame_stride, int64_t tokens_per_frame, void* stream) {
+    IFX_CHECK_ARG(row_scale != nullptr && col_scale != nullptr, "ifx_gemm_q8: row_scale and col_scale are required");
+    IFX_CHECK_ARG(kind == IFX_Q8_E4M3 || kind == IFX_Q8_INT8, "ifx_gemm_q8: kind must be IFX_Q8_E4M3 or IFX_Q8_INT8");
+    Q8Scales q8;
+    q8.row_scale = row_scale;
+    q8.col_scale = col_scale;
+    q8.int8 = kind == IFX_Q8_INT8 ? 1 : 0;
+    return gemm_entry<true>(A, lda, W, ldw, 1.0f, bias, out, ldo, M, N, K, epilogue, residual, ldr, gate,
+                            gate_frame_stride, tokens_per_frame, stream, q8);
 }

@@ -53,8 +53,15 @@ __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorM
         : "memory");
 }
 __device__ __forceinline__ void umma_ss_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                             uint32_t accumulate, bool fp8) {
-    if (fp8) {
+                                             uint32_t accumulate, bool fp8, bool int8 = false) {
+    if (int8) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}\n"
+            :
+            : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    } else if (fp8) {
         asm volatile(
             "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
             "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}\n"
@@ -168,7 +175,9 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
     } else if (warp == 1) {
         if (leader && lane == 0) {
-            constexpr uint32_t idesc = kFp8 ? make_idesc_e4m3(2 * k2BM, k2BN) : make_idesc_bf16(2 * k2BM, k2BN, 0, 0);
+            const uint32_t idesc = kFp8 ? (p.int8 ? make_idesc_s8(2 * k2BM, k2BN) : make_idesc_e4m3(2 * k2BM, k2BN))
+                                        : make_idesc_bf16(2 * k2BM, k2BN, 0, 0);
+            const bool int8 = kFp8 && p.int8;
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
@@ -185,7 +194,7 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sB + stage * k2BBytes), 16, 1024);
 #pragma unroll
                     for (int k = 0; k < k2BK / 16; ++k)
-                        umma_ss_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0, kFp8);
+                        umma_ss_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0, kFp8, int8);
                     umma_commit_pair(&empty[stage]);
                     if (++stage == k2Stages) {
                         stage = 0;

@@ -9,6 +9,11 @@ struct GemmParams {
     int64_t M;
     int32_t N, K;
     float alpha;  // FP8 path: input_scale * weight_scale applied to the fp32 accumulator before the bias
+    // 8-bit operand family (the kFp8 instantiations), dynamic quantisation: per-row activation scales and per-column
+    // weight scales replace alpha when non-null; int8 = 1 selects kind::i8 (S8 x S8 -> S32 accumulators in TMEM)
+    const float* row_scale;   // [M]
+    const float* col_scale;   // [N]
+    int32_t int8;
     const __nv_bfloat16* bias;
     __nv_bfloat16* out;
     int64_t ldo;
@@ -30,12 +35,19 @@ __device__ __forceinline__ float gelu_tanh_f(float x) {
     return 0.5f * x * (1.0f + t);
 }
 
+// accumulator bits -> dequantised fp32 value (8-bit operand family)
+__device__ __forceinline__ float dequant8(const GemmParams& p, uint32_t bits, float row_s, int col) {
+    const float a = p.int8 ? __int2float_rn(static_cast<int>(bits)) : __uint_as_float(bits);
+    return a * row_s * (p.col_scale ? __ldg(p.col_scale + col) : p.alpha);
+}
+
 // Epilogue of 32 accumulator columns of one output row: (dequant) + bias -> bf16 -> GELU | gate + residual -> bf16,
 // one rounding per reference op (causal_model.py:378-379,444,455-456), four 16-byte stores.
 template <int kEpi, bool kFp8>
 __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, const uint32_t (&acc)[32], int64_t row, int col0,
                                                     const __nv_bfloat16* gate_row) {
     __nv_bfloat16* optr = p.out + row * p.ldo + col0;
+    const float row_s = (kFp8 && p.row_scale != nullptr) ? __ldg(p.row_scale + row) : 1.0f;
     if (kEpi == IFX_EPI_BIAS_F32) {
         // fp32 result, no bf16 rounding of the accumulator: MAGI's output projection runs under
         // torch.autocast(dtype=float32) (dit_module.py:1291-1293) and feeds the fp32 gate / post-norm directly
@@ -47,8 +59,8 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, const u
             float* oe = reinterpret_cast<float*>(&o);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const float a = __uint_as_float(acc[v * 4 + e]);
-                oe[e] = (kFp8 ? a * p.alpha : a) + (p.bias ? __bfloat162float(p.bias[col0 + v * 4 + e]) : 0.f);
+                const float a = kFp8 ? dequant8(p, acc[v * 4 + e], row_s, col0 + v * 4 + e) : __uint_as_float(acc[v * 4 + e]);
+                oe[e] = a + (p.bias ? __bfloat162float(p.bias[col0 + v * 4 + e]) : 0.f);
             }
             *reinterpret_cast<float4*>(fo + v * 4) = o;
         }
@@ -72,8 +84,8 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, const u
         float val[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-            const float a = __uint_as_float(acc[v * 8 + e]);
-            val[e] = bf16_round((kFp8 ? a * p.alpha : a) + bv[e]);
+            const float a = kFp8 ? dequant8(p, acc[v * 8 + e], row_s, col0 + v * 8 + e) : __uint_as_float(acc[v * 8 + e]);
+            val[e] = bf16_round(a + bv[e]);
         }
         if (kEpi == IFX_EPI_BIAS_GELU) {
 #pragma unroll

@@ -148,6 +148,19 @@ __device__ __forceinline__ void umma_ss_f8(uint32_t d_tmem, uint64_t a_desc, uin
         : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// Same with INT8 operands: kind::i8, K = 32 per instruction, S32 accumulators.
+__device__ __forceinline__ void umma_ss_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                           uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
+        "}\n"
+        :
+        : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // D[tmem] (+)= A[tmem] * B[smem]; issued by ONE thread.
 __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
                                         uint32_t accumulate) {
@@ -215,6 +228,11 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_ma
 // kind::f8f6f4 with E4M3 inputs (format code 0 for both operands) and FP32 accumulate.
 __host__ __device__ constexpr uint32_t make_idesc_e4m3(int M, int N) {
     return (1u << 4) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+// kind::i8 with signed 8-bit inputs (format code 1) and S32 accumulate (c_format 2).
+__host__ __device__ constexpr uint32_t make_idesc_s8(int M, int N) {
+    return (2u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
 
 // ---------------------------------------------------------------- small numeric helpers

@@ -14,7 +14,8 @@ from . import _lib
 from ._lib import EPI_BIAS, EPI_BIAS_F32, EPI_BIAS_GATE_RES, EPI_BIAS_GELU, EPI_BIAS_GELU_ERF, KvPlan, RopeGrid
 
 __all__ = [
-    "ln_modulate", "gemm", "rmsnorm", "quantize_fp8", "ln_modulate_fp8", "gemm_fp8", "attention", "attention_gqa", "attention_ranges", "attention_partial", "attention_combine",
+    "ln_modulate", "gemm", "rmsnorm", "quantize_fp8", "quantize_rows", "ln_modulate_quant", "gemm_q8",
+    "quantize_weight_per_channel", "Q8_E4M3", "Q8_INT8", "ln_modulate_fp8", "gemm_fp8", "attention", "attention_gqa", "attention_ranges", "attention_partial", "attention_combine",
     "attention_workspace_bytes", "attention_extents", "attention_lse", "qk_norm_rope_append", "PagedKV", "rope_table",
     "EPI_BIAS", "EPI_BIAS_GELU", "EPI_BIAS_GATE_RES", "EPI_BIAS_GELU_ERF", "EPI_BIAS_F32",
     "qk_norm_rope_append_peers", "peer_push", "magi_qkv_post", "head_layernorm", "gate_norm_residual", "silu_mul",
@@ -169,6 +170,93 @@ def gemm_fp8(a_q, w_q, alpha: float, bias=None, out=None, *, epilogue=EPI_BIAS, 
         out.data_ptr(), out.stride(0), M, N, K, epilogue, _ptr(residual),
         residual.stride(0) if residual is not None else 0, _ptr(gate), gstride, tokens_per_frame, _stream()))
     return out
+
+
+# ----------------------------------------------------------------------------- dynamic 8-bit linears
+Q8_E4M3, Q8_INT8 = _lib.IFX_Q8_E4M3, _lib.IFX_Q8_INT8
+_Q8_DTYPE = {Q8_E4M3: torch.float8_e4m3fn, Q8_INT8: torch.int8}
+
+
+def _q8_2d(t, kind, name):
+    if not t.is_cuda or t.dtype != _Q8_DTYPE[kind] or t.dim() != 2 or t.stride(1) != 1:
+        raise ValueError(f"{name}: expected a 2-D CUDA {_Q8_DTYPE[kind]} tensor with unit inner stride")
+    return t
+
+
+def quantize_rows(x, kind=Q8_E4M3, out=None, scales=None):
+    """Per-token dynamic quantisation: x [rows, cols] bf16 -> (codes [rows, cols] e4m3 | int8, scales [rows] fp32)."""
+    x = _bf16_2d(x, "x")
+    rows, cols = x.shape
+    out = torch.empty((rows, cols), dtype=_Q8_DTYPE[kind], device=x.device) if out is None else _q8_2d(out, kind, "out")
+    scales = torch.empty(rows, dtype=torch.float32, device=x.device) if scales is None else scales
+    _lib.check(_lib.load().ifx_quantize_rows(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), scales.data_ptr(),
+                                             rows, cols, kind, _stream()))
+    return out, scales
+
+
+def ln_modulate_quant(x, kind=Q8_E4M3, out=None, scales=None, *, weight=None, bias=None, shift=None, scale=None,
+                      tokens_per_frame=0, eps=1e-6):
+    """ln_modulate whose bf16 result is quantised per token on the way out -> (codes, scales)."""
+    x = _bf16_2d(x, "x")
+    if not x.is_contiguous():
+        raise ValueError("x must be contiguous")
+    rows, cols = x.shape
+    out = torch.empty((rows, cols), dtype=_Q8_DTYPE[kind], device=x.device) if out is None else _q8_2d(out, kind, "out")
+    if not out.is_contiguous():
+        raise ValueError("out must be contiguous")
+    scales = torch.empty(rows, dtype=torch.float32, device=x.device) if scales is None else scales
+    stride = 0
+    if scale is not None:
+        if shift is None or scale.shape != shift.shape or scale.stride(0) != shift.stride(0):
+            raise ValueError("shift/scale must both be [frames, C] with a common frame stride")
+        stride = scale.stride(0)
+    _lib.check(_lib.load().ifx_ln_modulate_quant(
+        x.data_ptr(), out.data_ptr(), scales.data_ptr(), _ptr(_bf16_vec(weight, cols, "weight")),
+        _ptr(_bf16_vec(bias, cols, "bias")), _ptr(shift), _ptr(scale), stride, rows, cols, tokens_per_frame, eps, kind,
+        _stream()))
+    return out, scales
+
+
+def gemm_q8(a_q, w_q, row_scale, col_scale, kind=Q8_E4M3, bias=None, out=None, *, epilogue=EPI_BIAS, residual=None,
+            gate=None, tokens_per_frame=0):
+    """out = epilogue((a_q @ w_q.T) * row_scale[:, None] * col_scale[None, :] + bias); 8-bit codes, fp32 scales."""
+    a_q, w_q = _q8_2d(a_q, kind, "a_q"), _q8_2d(w_q, kind, "w_q")
+    M, K = a_q.shape
+    N = w_q.shape[0]
+    if w_q.shape[1] != K:
+        raise ValueError(f"gemm_q8: a is [{M},{K}] but w is {tuple(w_q.shape)}")
+    for t, n, name in ((row_scale, M, "row_scale"), (col_scale, N, "col_scale")):
+        if not t.is_cuda or t.dtype != torch.float32 or t.numel() != n or not t.is_contiguous():
+            raise ValueError(f"{name}: expected a contiguous CUDA float32 vector of {n} elements")
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.bfloat16, device=a_q.device)
+    out = _bf16_2d(out, "out")
+    gstride = 0
+    if gate is not None:
+        if gate.dim() != 2 or gate.shape[1] != N or gate.stride(1) != 1:
+            raise ValueError("gate must be [frames, N] with unit inner stride")
+        gstride = gate.stride(0)
+    if residual is not None:
+        residual = _bf16_2d(residual, "residual")
+    _lib.check(_lib.load().ifx_gemm_q8(
+        a_q.data_ptr(), a_q.stride(0), w_q.data_ptr(), w_q.stride(0), row_scale.data_ptr(), col_scale.data_ptr(), kind,
+        _ptr(_bf16_vec(bias, N, "bias")), out.data_ptr(), out.stride(0), M, N, K, epilogue, _ptr(residual),
+        residual.stride(0) if residual is not None else 0, _ptr(gate), gstride, tokens_per_frame, _stream()))
+    return out
+
+
+def quantize_weight_per_channel(w: torch.Tensor, kind=Q8_E4M3):
+    """W [N, K] -> (codes [N, K], scales [N] fp32): s_w[n] = max(|W[n, :]|, 1e-12) / qmax, round-to-nearest-even with
+    saturation (host-side torch arithmetic, done once per checkpoint)."""
+    qmax = 448.0 if kind == Q8_E4M3 else 127.0
+    wf = w.detach().float()
+    s = wf.abs().amax(dim=1).clamp_min(1e-12) / qmax
+    q = wf / s[:, None]
+    if kind == Q8_E4M3:
+        codes = q.clamp(-448.0, 448.0).to(torch.float8_e4m3fn)
+    else:
+        codes = torch.round(q).clamp(-127, 127).to(torch.int8)
+    return codes.contiguous(), s.contiguous()
 
 
 def rmsnorm(x, weight, out=None, *, eps=1e-6):

@@ -191,6 +191,7 @@ class CausalWanAttentionBlock(nn.Module):
         self.modulation = nn.Parameter(torch.randn(1, 6, dim) / dim ** 0.5)
         self._packed = None
         self._fp8 = None      # site -> quantised weight / scales once quantize_fp8() ran
+        self._q8 = None       # site -> per-channel quantised weight once quantize_dynamic() ran
         self._amax = None     # dict while calibrating
 
     # ------------------------------------------------------------------ weight packing for the C ABI
@@ -226,6 +227,7 @@ class CausalWanAttentionBlock(nn.Module):
     def invalidate_packed(self):
         self._packed = None
         self._fp8 = None
+        self._q8 = None
 
     # ------------------------------------------------------------------ forward
     def forward(self, x, e, seq_lens, grid_sizes, freqs, context, context_lens, block_mask, kv_cache_meta=None,
@@ -265,7 +267,7 @@ class CausalWanAttentionBlock(nn.Module):
             if not xb.is_contiguous():
                 raise ValueError("x must be contiguous per sample")
             peer_dst = getattr(store, "peer", None) if world > 1 else None
-            native_block = getattr(self, "_fp8", None) is None and self._amax is None
+            native_block = getattr(self, "_fp8", None) is None and self._amax is None and self._q8 is None
             if native_block and (world == 1 or (peer_dst is not None and _SP_MODE in ("overlap", "store"))):
                 io = WanBlockIO()
                 io.x, io.rows, io.tokens_per_frame = xb.data_ptr(), rows, fs
@@ -317,6 +319,36 @@ class CausalWanAttentionBlock(nn.Module):
             q[site] = dict(w=wq, w_scale=ws_, in_scale=float(input_scales[site]), bias=bias.detach())
         self._fp8 = q
 
+    def quantize_dynamic(self, kind: str = "fp8"):
+        """Dynamic per-token-activation x per-channel-weight 8-bit linears for the six block GEMMs — the qconfig of the
+        reference's quantisation examples (example/quantization/run_causvid_quantized.py:32-37).  kind: "fp8" (e4m3) or
+        "int8".  Weights are quantised once per output channel; activation scales are computed per token inside the
+        kernel that produces the activation and consumed by the GEMM epilogue (no calibration, no host round trip)."""
+        k = {"fp8": ops.Q8_E4M3, "int8": ops.Q8_INT8}[kind]
+        _w, _keep, qkv_w, qkv_b = self._packed or self._pack()
+        sa, ca = self.self_attn, self.cross_attn
+        mats = {"qkv": (qkv_w, qkv_b), "o": (sa.o.weight, sa.o.bias), "cq": (ca.q.weight, ca.q.bias),
+                "co": (ca.o.weight, ca.o.bias), "ffn1": (self.ffn[0].weight, self.ffn[0].bias),
+                "ffn2": (self.ffn[2].weight, self.ffn[2].bias)}
+        q = {"kind": k, "kind_name": kind}
+        for site, (wt, bias) in mats.items():
+            codes, scales = ops.quantize_weight_per_channel(wt, k)
+            q[site] = dict(w=codes, w_scale=scales, bias=bias.detach())
+        self._fp8 = None
+        self._q8 = q
+
+    def q8_state(self):
+        """Reference-named view of the dynamically quantised weights for the oracle: name -> (codes, scales, kind)."""
+        c, q, p = self.dim, self._q8, f"blocks.{self.layer_idx}"
+        out = {}
+        for j, name in enumerate(("q", "k", "v")):
+            out[f"{p}.self_attn.{name}"] = (q["qkv"]["w"][j * c:(j + 1) * c], q["qkv"]["w_scale"][j * c:(j + 1) * c],
+                                            q["kind_name"])
+        for site, name in (("o", "self_attn.o"), ("cq", "cross_attn.q"), ("co", "cross_attn.o"), ("ffn1", "ffn.0"),
+                           ("ffn2", "ffn.2")):
+            out[f"{p}.{name}"] = (q[site]["w"], q[site]["w_scale"], q["kind_name"])
+        return out
+
     def fp8_state(self):
         """Reference-named view of the quantised weights for the oracle: name -> (weight_q, weight_scale, input_scale)."""
         c = self.dim
@@ -342,12 +374,19 @@ class CausalWanAttentionBlock(nn.Module):
         m = mod.view(frames, 6, c)
         world = pc.world_size if pc is not None else 1
         f8 = getattr(self, "_fp8", None) if amax is None else None
+        q8 = self._q8 if (amax is None and f8 is None) else None
 
         def note(site, t):
             if amax is not None:
                 amax[site] = max(amax.get(site, 0.0), float(t.abs().max().float()))
 
         def linear(site, a_bf16, a_fp8, w, b, out, **kw):
+            if q8 is not None:
+                # a_fp8 carries (codes, per-token scales) when the producer (LN) quantised on the way out
+                codes, scales = a_fp8 if a_fp8 is not None else ops.quantize_rows(
+                    a_bf16, q8["kind"], ws.q8(site, a_bf16.shape, q8["kind"]), ws.q8_scales(site, a_bf16.shape[0]))
+                s = q8[site]
+                return ops.gemm_q8(codes, s["w"], scales, s["w_scale"], q8["kind"], s["bias"], out, **kw)
             if f8 is None:
                 note(site, a_bf16)
                 return ops.gemm(a_bf16, w, b, out, **kw)
@@ -357,6 +396,9 @@ class CausalWanAttentionBlock(nn.Module):
             return ops.gemm_fp8(a_fp8, q["w"], q["in_scale"] * q["w_scale"], q["bias"], out, **kw)
 
         def ln(site, **kw):
+            if q8 is not None:
+                return None, ops.ln_modulate_quant(x, q8["kind"], ws.q8(site, x.shape, q8["kind"]),
+                                                   ws.q8_scales(site, x.shape[0]), eps=self.eps, **kw)
             if f8 is None:
                 ops.ln_modulate(x, ws.h, eps=self.eps, **kw)
                 return ws.h, None
@@ -514,12 +556,22 @@ class _Workspace:
             self._part = torch.empty(need, dtype=torch.float32, device=self.h.device)
         return self._part
 
-    def q8(self, site, shape):
-        """e4m3 staging buffer for a GEMM input (lazily allocated, keyed by shape)."""
-        key = tuple(shape)
+    def q8(self, site, shape, kind=None):
+        """8-bit staging buffer for a GEMM input (lazily allocated, keyed by shape and code type)."""
+        dtype = torch.int8 if kind == ops.Q8_INT8 else torch.float8_e4m3fn
+        key = (tuple(shape), dtype)
         t = self._q8.get(key)
         if t is None:
-            t = self._q8[key] = torch.empty(key, dtype=torch.float8_e4m3fn, device=self.h.device)
+            t = self._q8[key] = torch.empty(tuple(shape), dtype=dtype, device=self.h.device)
+        return t
+
+    def q8_scales(self, site, rows):
+        """per-token activation scales of one GEMM input (fp32 [rows]); one buffer per site: the scales of a producer
+        must survive until its GEMM has run"""
+        key = ("scales", site, rows)
+        t = self._q8.get(key)
+        if t is None:
+            t = self._q8[key] = torch.empty(rows, dtype=torch.float32, device=self.h.device)
         return t
 
 
@@ -621,7 +673,14 @@ class CausalWanModel(nn.Module):
 
     def disable_fp8(self):
         for blk in self.blocks:
-            blk._fp8 = blk._amax = None
+            blk._fp8 = blk._amax = blk._q8 = None
+
+    def quantize_dynamic(self, kind: str = "fp8"):
+        """reference: quantize_dynamic(transformer, {"": get_dynamic_fp8_per_token_act_per_channel_weight_qconfig(),
+        "condition_embedder": None, "proj_out": None}) — every block linear, embeddings and head left in bf16
+        (example/quantization/run_causvid_quantized.py:28-37).  kind "fp8" or "int8"."""
+        for blk in self.blocks:
+            blk.quantize_dynamic(kind)
 
     def _get_workspace(self, rows, device):
         ws = self._workspace

@@ -188,7 +188,39 @@ def fp8_linear(x: torch.Tensor, w_q: torch.Tensor, weight_scale: float, input_sc
     return y.to(torch.bfloat16)
 
 
+def dynamic_q8_quantize(x: torch.Tensor, kind: str):
+    """Per-row dynamic quantisation: s = max(|x|_row, 1e-12) / qmax; codes = RNE with saturation (e4m3: qmax 448,
+    int8: qmax 127).  Returns (codes as float32 values, scales [rows, 1] fp32).  PARITY UNPINNED: this is the published
+    "dynamic per-token activation x per-channel weight" scheme the reference's quantisation examples request from DAX
+    (example/quantization/run_causvid_quantized.py:32-37); DAX (RiseAI-Sys/DAX, cloned by the example's README, no
+    version pinned) is absent from /root/reference, so no reference output exists to check against."""
+    qmax = 448.0 if kind == "fp8" else 127.0
+    xf = x.float()
+    s = xf.abs().amax(dim=-1, keepdim=True).clamp_min(1e-12) / qmax
+    q = xf * (1.0 / s)                     # the kernels multiply by the reciprocal
+    if kind == "fp8":
+        codes = q.clamp(-448.0, 448.0).to(torch.float8_e4m3fn).float()
+    else:
+        codes = torch.round(q).clamp(-127, 127)
+    return codes, s
+
+
+def dynamic_q8_linear(x: torch.Tensor, w_codes: torch.Tensor, w_scale: torch.Tensor, kind: str, bias=None) -> torch.Tensor:
+    """y = bf16( (x_q @ W_q^T) * s_a[m] * s_w[n] + bias ), exact integer / fp8 products accumulated in fp32 (int8: the
+    products are exact in fp32 up to K * 127^2 < 2^24 for K <= 1040; beyond that fp64 keeps the sum exact)."""
+    xq, sa = dynamic_q8_quantize(x, kind)
+    acc = (xq.double() @ w_codes.double().t()).float() if kind == "int8" else xq @ w_codes.float().t()
+    y = acc * sa * w_scale.float().view(1, -1)
+    if bias is not None:
+        y = y + bias.float()
+    return y.to(torch.bfloat16)
+
+
 def _lin(sd: Dict[str, torch.Tensor], name: str, x: torch.Tensor) -> torch.Tensor:
+    q8 = sd.get("__q8__", {}).get(name)
+    if q8 is not None:     # (weight codes, weight scales [N], kind): dynamically quantised 8-bit linear
+        shp = x.shape
+        return dynamic_q8_linear(x.reshape(-1, shp[-1]), q8[0], q8[1], q8[2], sd.get(name + ".bias")).view(*shp[:-1], -1)
     q = sd.get("__fp8__", {}).get(name)
     if q is not None:      # (weight_q, weight_scale, input_scale): this linear is FP8-quantised
         return fp8_linear(x, q[0], q[1], q[2], sd.get(name + ".bias"))

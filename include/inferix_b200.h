@@ -149,6 +149,12 @@ ifx_status ifx_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw,
 /* Activation quantisation x[rows, cols] bf16 -> e4m3 with a static per-tensor scale. */
 ifx_status ifx_quantize_fp8(const void* x, int64_t ldx, void* out, int64_t ldo, int64_t rows, int32_t cols,
                             float scale, void* stream);
+/* Same with one scale per input channel: x_q[m, k] = e4m3( bf16( clamp(x[m, k] / col_scale[k], -448, 448) ) ).  MAGI's
+ * PerTensorQuantizedFp8Linear keeps input_scale as an [in_features] vector and PerChannelQuantizedFp8Linear divides by
+ * its smooth_scale [1, in_features] (dit_module.py:434-490); both then call bmm_fp8 with per-tensor scales
+ * (ifx_gemm_fp8).  col_scale: fp32 [cols], 16-byte aligned. */
+ifx_status ifx_quantize_fp8_cols(const void* x, int64_t ldx, void* out, int64_t ldo, int64_t rows, int32_t cols,
+                                 const float* col_scale, void* stream);
 /* ifx_ln_modulate whose result is quantised on the way out (out: e4m3 [rows, cols]) — the quantisation of the
  * QKV / cross-q / FFN1 GEMM inputs fused into the kernel that produces them. */
 ifx_status ifx_ln_modulate_fp8(const void* x, void* out, const void* ln_weight, const void* ln_bias, const void* shift,

@@ -113,6 +113,7 @@ SIGNATURES = {
     "ifx_kv_import": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp]),
     "ifx_ln_modulate": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _i64, _f32, _vp]),
     "ifx_quantize_fp8": (C.c_int, [_vp, _i64, _vp, _i64, _i64, _i32, _f32, _vp]),
+    "ifx_quantize_fp8_cols": (C.c_int, [_vp, _i64, _vp, _i64, _i64, _i32, _vp, _vp]),
     "ifx_ln_modulate_fp8": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _i64, _f32, _f32, _vp]),
     "ifx_gemm_fp8": (C.c_int, [_vp, _i64, _vp, _i64, _f32, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _vp, _i64, _vp,
                                _i64, _i64, _vp]),

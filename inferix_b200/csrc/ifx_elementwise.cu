@@ -212,7 +212,9 @@ ln_modulate_kernel(const __nv_bfloat16* __restrict__ x, void* __restrict__ out_,
 // ------------------------------------------------------------------ bf16 -> e4m3 quantisation
 __global__ void __launch_bounds__(256)
 quantize_fp8_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, uint8_t* __restrict__ out, int64_t ldo,
-                    int64_t rows, int cols, float scale) {
+                    int64_t rows, int cols, float scale, const float* __restrict__ col_scale) {
+    griddep_launch();
+    griddep_wait();
     const int nvec = cols >> 3;
     const int64_t total = rows * nvec;
     for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
@@ -221,7 +223,21 @@ quantize_fp8_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, uint8_t* _
         const int vi = static_cast<int>(i % nvec);
         float v[8];
         unpack8(reinterpret_cast<const uint4*>(x + r * ldx)[vi], v);
-        reinterpret_cast<uint2*>(out + r * ldo)[vi] = quant8_e4m3(v, scale);
+        if (col_scale != nullptr) {
+            // one scale per input channel (MAGI PerTensor input_scale vector / PerChannel smooth_scale)
+            const float4 s0 = __ldg(reinterpret_cast<const float4*>(col_scale) + 2 * vi);
+            const float4 s1 = __ldg(reinterpret_cast<const float4*>(col_scale) + 2 * vi + 1);
+            const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+            float q[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) q[e] = bf16_round(fminf(fmaxf(__fdiv_rn(v[e], sv[e]), -448.f), 448.f));
+            uint2 o;
+            o.x = static_cast<uint32_t>(pack_e4m3x2(q[0], q[1])) | (static_cast<uint32_t>(pack_e4m3x2(q[2], q[3])) << 16);
+            o.y = static_cast<uint32_t>(pack_e4m3x2(q[4], q[5])) | (static_cast<uint32_t>(pack_e4m3x2(q[6], q[7])) << 16);
+            reinterpret_cast<uint2*>(out + r * ldo)[vi] = o;
+        } else {
+            reinterpret_cast<uint2*>(out + r * ldo)[vi] = quant8_e4m3(v, scale);
+        }
     }
 }
 
@@ -1128,12 +1144,14 @@ extern "C" ifx_status ifx_ln_modulate_fp8(const void* x, void* out, const void* 
                              eps, true, out_scale, stream);
 }
 
-extern "C" ifx_status ifx_quantize_fp8(const void* x, int64_t ldx, void* out, int64_t ldo, int64_t rows, int32_t cols,
-                                       float scale, void* stream) {
+static ifx_status quantize_fp8_entry(const void* x, int64_t ldx, void* out, int64_t ldo, int64_t rows, int32_t cols,
+                                     float scale, const float* col_scale, void* stream) {
     IFX_CHECK_ARG(x && out, "ifx_quantize_fp8: null pointer");
     IFX_CHECK_ARG(rows > 0 && cols > 0 && cols % 8 == 0, "ifx_quantize_fp8: cols must be a multiple of 8");
     IFX_CHECK_ARG(ldx >= cols && ldx % 8 == 0 && ldo >= cols && ldo % 8 == 0, "ifx_quantize_fp8: bad strides");
-    IFX_CHECK_ARG(scale > 0.f, "ifx_quantize_fp8: scale must be positive");
+    IFX_CHECK_ARG(col_scale != nullptr || scale > 0.f, "ifx_quantize_fp8: scale must be positive");
+    IFX_CHECK_ARG(col_scale == nullptr || (reinterpret_cast<uintptr_t>(col_scale) & 15) == 0,
+                  "ifx_quantize_fp8_cols: col_scale must be 16-byte aligned");
     const int64_t total = rows * (cols >> 3);
     int64_t blocks = (total + 255) / 256;
     const int64_t cap = static_cast<int64_t>(sm_count()) * 16;
@@ -1141,11 +1159,23 @@ extern "C" ifx_status ifx_quantize_fp8(const void* x, int64_t ldx, void* out, in
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     {
         ProfScope prof("quantize_fp8_kernel", st);
-        quantize_fp8_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(
-            static_cast<const __nv_bfloat16*>(x), ldx, static_cast<uint8_t*>(out), ldo, rows, cols, scale);
+        IFX_CUDA_OK(launch_kernel(quantize_fp8_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, st, true,
+                                  static_cast<const __nv_bfloat16*>(x), ldx, static_cast<uint8_t*>(out), ldo, rows, cols,
+                                  scale, col_scale));
     }
     IFX_LAUNCH_OK("quantize_fp8_kernel");
     return IFX_OK;
+}
+
+extern "C" ifx_status ifx_quantize_fp8(const void* x, int64_t ldx, void* out, int64_t ldo, int64_t rows, int32_t cols,
+                                       float scale, void* stream) {
+    return quantize_fp8_entry(x, ldx, out, ldo, rows, cols, scale, nullptr, stream);
+}
+
+extern "C" ifx_status ifx_quantize_fp8_cols(const void* x, int64_t ldx, void* out, int64_t ldo, int64_t rows,
+                                            int32_t cols, const float* col_scale, void* stream) {
+    IFX_CHECK_ARG(col_scale != nullptr, "ifx_quantize_fp8_cols: null col_scale");
+    return quantize_fp8_entry(x, ldx, out, ldo, rows, cols, 1.0f, col_scale, stream);
 }
 
 extern "C" ifx_status ifx_rmsnorm(const void* x, int64_t ldx, const void* weight, void* out, int64_t ldo,

@@ -22,7 +22,7 @@ What stays on torch ops: the AdaModulate gate of `denoising_range_num` rows (SiL
 :1299-1303) and the final fp32 LayerNorm of the block (once per forward), both < 0.1 % of the layer's bytes.
 
 Context parallel: `engine_config.cp_strategy == "cp_ulysses"` (see inferix_b200/magi_cp.py).  Not built: batch > 1,
-fp8_quant (the per-tensor FP8 GEMM exists — `ops.gemm_fp8` — but is not wired into this layer), cp_shuffle_overlap,
+cp_shuffle_overlap,
 pipeline parallel offsets.  There is no CPU path: every op below needs libinferix_b200.so and CUDA tensors.
 """
 from __future__ import annotations
@@ -83,6 +83,74 @@ class AdaModulateLayer(nn.Module):
         return self.proj(self.act(c))
 
 
+def _fp8_layer(engine_config, model_config, layer_number: int) -> bool:
+    """Which layers carry FP8 linears: fp8_quant set and neither the first nor the last layer (dit_module.py:410)."""
+    return bool(getattr(engine_config, "fp8_quant", False)) and layer_number not in (0, model_config.num_layers - 1)
+
+
+class PerTensorQuantizedFp8Linear(nn.Module):
+    """dit_module.py:434-459 — parameter names / shapes of the reference (a quantised checkpoint loads as is):
+    weight e4m3 [1, out, in], weight_scale fp32 [1], input_scale fp32 [in].  forward = div_clamp_to(x, input_scale)
+    (one divisor per input channel) followed by bmm_fp8 with per-tensor scales, for which cuBLASLt reads ONE float per
+    operand: input_scale[0] and weight_scale[0]."""
+
+    def __init__(self, in_features, out_features, bias=False, dtype=torch.bfloat16, device=None):
+        super().__init__()
+        self.in_features, self.out_features, self.output_dtype = in_features, out_features, dtype
+        self.weight = nn.Parameter(torch.zeros((1, out_features, in_features), dtype=torch.float8_e4m3fn), requires_grad=False)
+        self.weight_scale = nn.Parameter(torch.ones(1, dtype=torch.float32), requires_grad=False)
+        self.input_scale = nn.Parameter(torch.ones(in_features, dtype=torch.float32), requires_grad=False)
+
+    def divisor(self):
+        return self.input_scale
+
+    def alpha(self) -> float:
+        return float(self.input_scale.reshape(-1)[0]) * float(self.weight_scale.reshape(-1)[0])
+
+    @torch.no_grad()
+    def quantize_from(self, weight: torch.Tensor, input_amax: float = 8.0):
+        """Test / tooling helper: fill the parameters from a bf16 weight (per-tensor amax scaling)."""
+        ws = float(weight.float().abs().max()) / 448.0
+        self.weight.copy_(torch.clamp(weight.float() / ws, -448.0, 448.0).bfloat16().to(torch.float8_e4m3fn).unsqueeze(0))
+        self.weight_scale.fill_(ws)
+        self.input_scale.fill_(input_amax / 448.0)
+
+    def forward(self, x):
+        shp = x.shape
+        x2 = x.reshape(-1, shp[-1]).contiguous()
+        a = _ops.quantize_fp8_cols(x2, self.divisor().reshape(-1).contiguous())
+        return _ops.gemm_fp8(a, self.weight[0], self.alpha()).view(*shp[:-1], self.out_features)
+
+
+class PerChannelQuantizedFp8Linear(PerTensorQuantizedFp8Linear):
+    """dit_module.py:465-490: x / smooth_scale [1, in] -> e4m3, bmm_fp8 with input_scale [1] and weight_scale [1]."""
+
+    def __init__(self, in_features, out_features, bias=False, dtype=torch.bfloat16, device=None):
+        super().__init__(in_features, out_features, bias, dtype, device)
+        self.input_scale = nn.Parameter(torch.ones(1, dtype=torch.float32), requires_grad=False)
+        self.smooth_scale = nn.Parameter(torch.ones((1, in_features), dtype=torch.float32), requires_grad=False)
+
+    def divisor(self):
+        return self.smooth_scale
+
+    @torch.no_grad()
+    def quantize_from(self, weight: torch.Tensor, input_amax: float = 8.0, smooth=None):
+        """Smooth-quant style split: activations are divided by smooth_scale[k] * 1, the weight absorbs smooth / input."""
+        k = weight.shape[1]
+        sm = torch.ones(k) if smooth is None else smooth.float().cpu()
+        in_s = input_amax / 448.0
+        self.smooth_scale.copy_((sm * in_s).view(1, k))          # x / (smooth * input_scale) lands in the e4m3 range
+        w_eff = weight.float().cpu() * sm.view(1, k)             # (x / smooth) @ (W * smooth)^T == x @ W^T
+        ws = float(w_eff.abs().max()) / 448.0
+        self.weight.copy_(torch.clamp(w_eff / ws, -448.0, 448.0).bfloat16().to(torch.float8_e4m3fn).unsqueeze(0))
+        self.weight_scale.fill_(ws)
+        self.input_scale.fill_(in_s)
+
+
+def _is_fp8(lin) -> bool:
+    return isinstance(lin, PerTensorQuantizedFp8Linear)
+
+
 class CustomLayerNormLinear(nn.Module):
     """dit_module.py:393-431 (parameter container: layer_norm + q / qx / k / v)."""
 
@@ -91,8 +159,10 @@ class CustomLayerNormLinear(nn.Module):
         dt = model_config.params_dtype
         self.layer_norm = nn.LayerNorm(input_size, eps=model_config.layernorm_epsilon, dtype=dt)
         self.layer_number = layer_number
+        fp8 = _fp8_layer(engine_config, model_config, layer_number)
         for name, out in {"q": output_size_q, "qx": output_size_q, "k": output_size_kv, "v": output_size_kv}.items():
-            setattr(self, name, nn.Linear(input_size, out, bias=False, dtype=dt))
+            setattr(self, name, PerTensorQuantizedFp8Linear(input_size, out) if fp8
+                    else nn.Linear(input_size, out, bias=False, dtype=dt))
 
 
 class CustomMLP(nn.Module):
@@ -104,8 +174,12 @@ class CustomMLP(nn.Module):
         self.input_size = input_size if input_size is not None else model_config.hidden_size
         self.layer_norm = nn.LayerNorm(self.input_size, eps=model_config.layernorm_epsilon, dtype=dt)
         f = model_config.ffn_hidden_size
-        self.linear_fc1 = nn.Linear(self.input_size, (2 if model_config.gated_linear_unit else 1) * f, bias=False, dtype=dt)
-        self.linear_fc2 = nn.Linear(f, model_config.hidden_size, bias=False, dtype=dt)
+        fp8 = _fp8_layer(engine_config, model_config, layer_number)
+        fc1_out = (2 if model_config.gated_linear_unit else 1) * f
+        self.linear_fc1 = (PerTensorQuantizedFp8Linear(self.input_size, fc1_out) if fp8                      # :525-536
+                           else nn.Linear(self.input_size, fc1_out, bias=False, dtype=dt))
+        self.linear_fc2 = (PerChannelQuantizedFp8Linear(f, model_config.hidden_size) if fp8                   # :538-543
+                           else nn.Linear(f, model_config.hidden_size, bias=False, dtype=dt))
 
 
 class FullyParallelAttention(nn.Module):
@@ -132,7 +206,10 @@ class FullyParallelAttention(nn.Module):
                                                 layer_number, mc, engine_config)
         self.linear_kv_xattn = nn.Linear(int(mc.hidden_size * mc.xattn_cond_hidden_ratio), 2 * self.kv_projection_size,
                                          dtype=dt, bias=False)
-        self.linear_proj = nn.Linear(2 * self.query_projection_size, mc.hidden_size, dtype=dt, bias=False)
+        self.adapt_linear_quant = _fp8_layer(engine_config, mc, layer_number)                               # :864-866
+        self.linear_proj = (PerChannelQuantizedFp8Linear(2 * self.query_projection_size, mc.hidden_size)
+                            if self.adapt_linear_quant
+                            else nn.Linear(2 * self.query_projection_size, mc.hidden_size, dtype=dt, bias=False))
         # dtypes as left by _high_precision_promoter (dit_model.py:620-637): self-attention q/k norms in fp32
         self.q_layernorm = FusedLayerNorm(mc, mc.kv_channels, dtype=torch.float32)
         self.q_layernorm_xattn = FusedLayerNorm(mc, mc.kv_channels)
@@ -185,8 +262,6 @@ class TransformerLayer(nn.Module):
 
     def __init__(self, model_config, engine_config, layer_number: int = 1):
         super().__init__()
-        if getattr(engine_config, "fp8_quant", False):
-            raise NotImplementedError("fp8_quant is not wired into the native MAGI layer yet")
         if getattr(engine_config, "cp_strategy", "none") not in ("none", "cp_ulysses"):
             raise NotImplementedError("cp_strategy must be 'none' or 'cp_ulysses'")
         if model_config.kv_channels != 128:
@@ -219,21 +294,43 @@ class TransformerLayer(nn.Module):
         sa, mc = self.self_attention, self.model_config
         lq = sa.linear_qkv
         d, g = mc.kv_channels, mc.num_query_groups
-        w_qkvx = torch.cat([lq.q.weight, lq.k.weight, lq.v.weight, lq.qx.weight], dim=0).detach().contiguous()
+        fp8 = _is_fp8(lq.q)
+
+        def proj_perm(wp):
+            """output-projection input columns: reference '(hn n hd)' order (dit_module.py:1287) -> '[core | cross]'"""
+            hd = wp.shape[1] // 16
+            return wp.view(wp.shape[0], 8, 2, hd).permute(0, 2, 1, 3).reshape(wp.shape[0], -1).contiguous()
+
+        def q8(lin, perm=None):
+            """(e4m3 weight [out, in], per-input-channel divisor fp32 [in], alpha) of a quantised linear"""
+            wq = lin.weight.detach()[0]
+            div = lin.divisor().detach().reshape(-1).float()
+            if perm is not None:                     # permute input channels of weight and divisor alike
+                wq = perm(wq.view(torch.uint8)).view(torch.float8_e4m3fn)
+                div = perm(div.view(1, -1)).reshape(-1)
+            return wq.contiguous(), div.contiguous(), lin.alpha()
+
         w_kvx = sa.linear_kv_xattn.weight.detach()
         w_kvx = w_kvx.view(g, 2, d, w_kvx.shape[1]).permute(1, 0, 2, 3).reshape(2 * g * d, -1).contiguous()
-        wp = sa.linear_proj.weight.detach()
-        hd = wp.shape[1] // 16
-        w_proj = wp.view(wp.shape[0], 8, 2, hd).permute(0, 2, 1, 3).reshape(wp.shape[0], -1).contiguous()
-        self._packed = dict(
-            w_qkvx=w_qkvx, w_kvx=w_kvx, w_proj=w_proj,
+        pk = dict(
+            w_kvx=w_kvx, fp8=fp8,
             ln1=(lq.layer_norm.weight.detach().contiguous(), lq.layer_norm.bias.detach().contiguous()),
             q_ln=sa.q_layernorm.affine(), k_ln=sa.k_layernorm.affine(),
             qx_ln=sa.q_layernorm_xattn.affine(), kx_ln=sa.k_layernorm_xattn.affine(),
             post1=self.self_attn_post_norm.affine(), post2=self.mlp_post_norm.affine(),
             ln2=(self.mlp.layer_norm.weight.detach().contiguous(), self.mlp.layer_norm.bias.detach().contiguous()),
-            fc1=self.mlp.linear_fc1.weight.detach().contiguous(), fc2=self.mlp.linear_fc2.weight.detach().contiguous(),
             ada_w=self.ada_modulate_layer.proj[0].weight.detach(), ada_b=self.ada_modulate_layer.proj[0].bias.detach())
+        if fp8:
+            # four PerTensor linears with their own divisors / scales (:410-413), PerChannel proj and fc2, PerTensor fc1
+            pk["qkvx8"] = [q8(getattr(lq, n)) for n in ("q", "k", "v", "qx")]
+            pk["proj8"] = q8(sa.linear_proj, proj_perm)
+            pk["fc1_8"], pk["fc2_8"] = q8(self.mlp.linear_fc1), q8(self.mlp.linear_fc2)
+        else:
+            pk["w_qkvx"] = torch.cat([lq.q.weight, lq.k.weight, lq.v.weight, lq.qx.weight], dim=0).detach().contiguous()
+            pk["w_proj"] = proj_perm(sa.linear_proj.weight.detach())
+            pk["fc1"] = self.mlp.linear_fc1.weight.detach().contiguous()
+            pk["fc2"] = self.mlp.linear_fc2.weight.detach().contiguous()
+        self._packed = pk
         return self._packed
 
     # ------------------------------------------------------------------ KV rows
@@ -295,7 +392,14 @@ class TransformerLayer(nn.Module):
         hbuf = sc.get("h", (s_loc, h), bf, dev)
         _ops.ln_modulate(x, hbuf, weight=pk["ln1"][0], bias=pk["ln1"][1], eps=eps)
         qkvx = sc.get("qkvx", (s_loc, (2 * hq + 2 * g) * d), bf, dev)
-        _ops.gemm(hbuf, pk["w_qkvx"], None, qkvx)
+        if pk["fp8"]:
+            off = 0
+            for wq, div, alpha in pk["qkvx8"]:                    # q | k | v | qx, each with its own divisor and scales
+                a8 = _ops.quantize_fp8_cols(hbuf, div, sc.get("a8_h", (s_loc, h), torch.float8_e4m3fn, dev))
+                _ops.gemm_fp8(a8, wq, alpha, None, qkvx[:, off:off + wq.shape[0]])
+                off += wq.shape[0]
+        else:
+            _ops.gemm(hbuf, pk["w_qkvx"], None, qkvx)
 
         # ---- head-LN + rotary + KV placement (:902-958; cache :76-151)
         qx = sc.get("qx", (s_loc, hq * d), bf, dev)
@@ -349,8 +453,14 @@ class TransformerLayer(nn.Module):
 
         # ---- output projection, gate, post-norm, residual (:1281-1311)
         # the reference runs this projection under autocast(float32) (:1291-1293): its result is consumed in fp32
-        proj32 = sc.get("proj32", (s_loc, h), torch.float32, dev)
-        _ops.gemm(attn_cat, pk["w_proj"], None, proj32, epilogue=_ops.EPI_BIAS_F32)
+        if pk["fp8"]:
+            # adapt_linear_quant (:1288-1289): PerChannelQuantizedFp8Linear, bf16 result (no fp32 autocast region)
+            wq, div, alpha = pk["proj8"]
+            a8 = _ops.quantize_fp8_cols(attn_cat, div, sc.get("a8_attn", (s_loc, 2 * hq * d), torch.float8_e4m3fn, dev))
+            proj32 = _ops.gemm_fp8(a8, wq, alpha, None, sc.get("proj_bf", (s_loc, h), bf, dev))
+        else:
+            proj32 = sc.get("proj32", (s_loc, h), torch.float32, dev)
+            _ops.gemm(attn_cat, pk["w_proj"], None, proj32, epilogue=_ops.EPI_BIAS_F32)
         gate = softcap(F.linear(F.silu(condition.reshape(-1, condition.shape[-1])), pk["ada_w"], pk["ada_b"]), 1.0)
         gate = gate.to(bf).contiguous()                                          # [ranges, 2h]: gate_msa | gate_mlp
         x1 = torch.empty_like(x)
@@ -360,14 +470,27 @@ class TransformerLayer(nn.Module):
         f = mc.ffn_hidden_size
         _ops.ln_modulate(x1, hbuf, weight=pk["ln2"][0], bias=pk["ln2"][1], eps=eps)
         act = sc.get("act", (s_loc, f), bf, dev)
-        if mc.gated_linear_unit:
+        proj = sc.get("proj", (s_loc, h), bf, dev)
+        if pk["fp8"]:
+            wq, div, alpha = pk["fc1_8"]
+            a8 = _ops.quantize_fp8_cols(hbuf, div, sc.get("a8_h", (s_loc, h), torch.float8_e4m3fn, dev))
+            if mc.gated_linear_unit:
+                ffn = sc.get("ffn", (s_loc, 2 * f), bf, dev)
+                _ops.gemm_fp8(a8, wq, alpha, None, ffn)
+                _ops.silu_mul(ffn, act)
+            else:
+                _ops.gemm_fp8(a8, wq, alpha, None, act, epilogue=_ops.EPI_BIAS_GELU_ERF)
+            wq, div, alpha = pk["fc2_8"]
+            a8 = _ops.quantize_fp8_cols(act, div, sc.get("a8_act", (s_loc, f), torch.float8_e4m3fn, dev))
+            _ops.gemm_fp8(a8, wq, alpha, None, proj)
+        elif mc.gated_linear_unit:
             ffn = sc.get("ffn", (s_loc, 2 * f), bf, dev)
             _ops.gemm(hbuf, pk["fc1"], None, ffn)
             _ops.silu_mul(ffn, act)
+            _ops.gemm(act, pk["fc2"], None, proj)
         else:
             _ops.gemm(hbuf, pk["fc1"], None, act, epilogue=_ops.EPI_BIAS_GELU_ERF)
-        proj = sc.get("proj", (s_loc, h), bf, dev)
-        _ops.gemm(act, pk["fc2"], None, proj)
+            _ops.gemm(act, pk["fc2"], None, proj)
         _ops.gate_norm_residual(proj, gate[:, h:], ctx.row_map, pk["post2"][0], pk["post2"][1], x1, x1, eps=eps)
         return x1.view(s_loc, 1, h)
 

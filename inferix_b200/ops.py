@@ -14,7 +14,7 @@ from . import _lib
 from ._lib import EPI_BIAS, EPI_BIAS_F32, EPI_BIAS_GATE_RES, EPI_BIAS_GELU, EPI_BIAS_GELU_ERF, KvPlan, RopeGrid
 
 __all__ = [
-    "ln_modulate", "gemm", "rmsnorm", "quantize_fp8", "quantize_rows", "ln_modulate_quant", "gemm_q8",
+    "ln_modulate", "gemm", "rmsnorm", "quantize_fp8", "quantize_fp8_cols", "quantize_rows", "ln_modulate_quant", "gemm_q8",
     "quantize_weight_per_channel", "Q8_E4M3", "Q8_INT8", "ln_modulate_fp8", "gemm_fp8", "attention", "attention_gqa", "attention_ranges", "attention_partial", "attention_combine",
     "attention_workspace_bytes", "attention_extents", "attention_lse", "qk_norm_rope_append", "PagedKV", "rope_table",
     "EPI_BIAS", "EPI_BIAS_GELU", "EPI_BIAS_GATE_RES", "EPI_BIAS_GELU_ERF", "EPI_BIAS_F32",
@@ -123,6 +123,20 @@ def quantize_fp8(x, scale: float, out=None):
     out = torch.empty((rows, cols), dtype=torch.float8_e4m3fn, device=x.device) if out is None else _fp8_2d(out, "out")
     _lib.check(_lib.load().ifx_quantize_fp8(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), rows, cols,
                                             float(scale), _stream()))
+    return out
+
+
+def quantize_fp8_cols(x, col_scale, out=None):
+    """e4m3(bf16(clamp(x[:, k] / col_scale[k], +-448))): MAGI's quantised linears divide by a per-input-channel vector
+    (PerTensor input_scale [in] / PerChannel smooth_scale [1, in], dit_module.py:434-490)."""
+    x = _bf16_2d(x, "x")
+    rows, cols = x.shape
+    col_scale = col_scale.reshape(-1)
+    if not col_scale.is_cuda or col_scale.dtype != torch.float32 or col_scale.numel() != cols or not col_scale.is_contiguous():
+        raise ValueError(f"col_scale: expected a contiguous CUDA float32 vector of {cols} elements")
+    out = torch.empty((rows, cols), dtype=torch.float8_e4m3fn, device=x.device) if out is None else _fp8_2d(out, "out")
+    _lib.check(_lib.load().ifx_quantize_fp8_cols(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), rows, cols,
+                                                 col_scale.data_ptr(), _stream()))
     return out
 
 

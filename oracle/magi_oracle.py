@@ -151,6 +151,36 @@ class OracleMagiCache:
         return full[0].contiguous(), full[1].contiguous()
 
 
+# ----------------------------------------------------------------------------- FP8 linears
+def div_clamp_to(x: torch.Tensor, scale: torch.Tensor) -> torch.Tensor:
+    """dit_module.py:367-387: clamp(x.float() / scale.float(), +-448) -> bf16 -> e4m3 (scale broadcasts over the last dim)."""
+    return torch.clamp(x.float() / scale.float(), -448.0, 448.0).bfloat16().to(torch.float8_e4m3fn)
+
+
+def bmm_fp8(a_q: torch.Tensor, w_q: torch.Tensor, a_scale: torch.Tensor, b_scale: torch.Tensor) -> torch.Tensor:
+    """flashinfer.bmm_fp8 (cuBLASLt FP8 matmul with per-tensor scaling): fp32 accumulation of the exact e4m3 products,
+    times ONE scale per operand (cuBLASLt reads a single float through each scale pointer: element 0 when the tensor
+    has more, as PerTensorQuantizedFp8Linear.input_scale does), rounded to bf16."""
+    return ((a_q.float() @ w_q.float().t()) * (float(a_scale.reshape(-1)[0]) * float(b_scale.reshape(-1)[0]))).to(torch.bfloat16)
+
+
+def qlinear(sd, name: str, x: torch.Tensor, fp32_autocast: bool = False) -> torch.Tensor:
+    """A MAGI linear by parameter prefix `name`: nn.Linear, PerTensorQuantizedFp8Linear (:434-459) or
+    PerChannelQuantizedFp8Linear (:465-490), told apart by the parameters present, as the reference's module types are."""
+    if name + ".weight_scale" not in sd:
+        if fp32_autocast:
+            return F.linear(x.float(), sd[name + ".weight"].float())
+        return F.linear(x, sd[name + ".weight"])
+    w_q = sd[name + ".weight"][0]
+    shp = x.shape
+    x2 = x.reshape(-1, shp[-1])
+    if name + ".smooth_scale" in sd:                                            # PerChannel
+        a = div_clamp_to(x2, sd[name + ".smooth_scale"].to(torch.float32))
+    else:                                                                       # PerTensor (input_scale is [in])
+        a = div_clamp_to(x2, sd[name + ".input_scale"])
+    return bmm_fp8(a, w_q, sd[name + ".input_scale"], sd[name + ".weight_scale"]).view(*shp[:-1], -1)
+
+
 # ----------------------------------------------------------------------------- the layer
 def attention_block(sd, p, cfg: MagiConfig, layer: int, hidden, y_xattn_flat, rope, cache: Optional[OracleMagiCache],
                     meta):
@@ -164,7 +194,7 @@ def attention_block(sd, p, cfg: MagiConfig, layer: int, hidden, y_xattn_flat, ro
                          sd[a + "linear_qkv.layer_norm.bias"], eps)                                 # :1103, :415
 
     def roped(name, ln):                                                                            # get_q / get_k :902-934
-        t = F.linear(mixed, sd[a + f"linear_qkv.{name}.weight"])
+        t = qlinear(sd, a + f"linear_qkv.{name}", mixed)
         t = t.reshape(t.size(0), t.size(1), -1, d)
         dt = t.dtype
         t = fused_layer_norm(t.float(), sd[a + ln + ".weight"], sd[a + ln + ".bias"], eps, g1p)
@@ -172,7 +202,7 @@ def attention_block(sd, p, cfg: MagiConfig, layer: int, hidden, y_xattn_flat, ro
         return t[0]                                                                                 # (sq b) hn hd, b = 1
 
     key = roped("k", "k_layernorm")
-    value = F.linear(mixed, sd[a + "linear_qkv.v.weight"]).reshape(-1, hk, d)                       # get_v :936-938
+    value = qlinear(sd, a + "linear_qkv.v", mixed).reshape(-1, hk, d)                               # get_v :936-938
     query = roped("q", "q_layernorm")
     key_and_value = torch.cat([key, value], dim=-1)                                                 # get_kv :940-945
     if cache is None:
@@ -187,7 +217,7 @@ def attention_block(sd, p, cfg: MagiConfig, layer: int, hidden, y_xattn_flat, ro
     core = torch.cat(outs, dim=0).reshape(-1, 1, hq * d)                                             # :1120
 
     # cross attention (get_xqkv :954-970, cross_attention :1047-1085)
-    qx = F.linear(mixed, sd[a + "linear_qkv.qx.weight"]).reshape(-1, hq, d)                          # (b sq) hn hd
+    qx = qlinear(sd, a + "linear_qkv.qx", mixed).reshape(-1, hq, d)                                  # (b sq) hn hd
     qx = fused_layer_norm(qx, sd[a + "q_layernorm_xattn.weight"], sd[a + "q_layernorm_xattn.bias"], eps, g1p)
     w = sd[a + "linear_kv_xattn.weight"]
     mixed_kv = torch.cat([torch.matmul(y_xattn_flat, wc.t()) for wc in torch.chunk(w, 8, dim=0)], dim=1)
@@ -213,7 +243,8 @@ def layer_forward(sd, layer: int, cfg: MagiConfig, hidden, condition, condition_
     # operands of `linear` to fp32, so the result stays fp32 through the gate / post-norm and is rounded only after
     # the residual add (bias_modulate_add works in x's dtype, then `.to(params_dtype)`, :1306-1308)
     pdt = hidden.dtype
-    h = F.linear(attn.float(), sd[p + "self_attention.linear_proj.weight"].float())
+    # adapt_linear_quant (:1288-1289): the quantised projection runs outside the autocast region and returns bf16
+    h = qlinear(sd, p + "self_attention.linear_proj", attn, fp32_autocast=True)
     gate = F.linear(F.silu(condition), sd[p + "ada_modulate_layer.proj.0.weight"],
                     sd[p + "ada_modulate_layer.proj.0.bias"])                                       # :196-198
     gate_msa, gate_mlp = softcap(gate, 1.0).chunk(2, dim=-1)                                        # :1300-1303
@@ -222,9 +253,9 @@ def layer_forward(sd, layer: int, cfg: MagiConfig, hidden, condition, condition_
     residual = h
     m = F.layer_norm(h, (cfg.hidden_size,), sd[p + "mlp.layer_norm.weight"], sd[p + "mlp.layer_norm.bias"],
                      cfg.layernorm_epsilon)                                                         # CustomMLP :545-556
-    m = F.linear(m, sd[p + "mlp.linear_fc1.weight"])
+    m = qlinear(sd, p + "mlp.linear_fc1", m)
     m = silu_and_mul(m) if cfg.gated_linear_unit else F.gelu(m)
-    m = F.linear(m, sd[p + "mlp.linear_fc2.weight"])
+    m = qlinear(sd, p + "mlp.linear_fc2", m)
     return bias_modulate_add(m, residual, condition_map, gate_mlp, sd[p + "mlp_post_norm.weight"],
                              sd[p + "mlp_post_norm.bias"], cfg)
 

@@ -253,6 +253,78 @@ def test_layer_at_magi_4p5b_width():
         assert gap_ours <= 1.5 * gap_ref + 1e-3
 
 
+@pytest.mark.parametrize("glu", [False, True])
+def test_fp8_quant_block_matches_oracle(glu):
+    """engine_config.fp8_quant: the middle layers run the reference's quantised linears (dit_module.py:410,525,538,865):
+    PerTensorQuantizedFp8Linear for q / k / v / qx / fc1 (per-input-channel divisor, per-tensor GEMM scales) and
+    PerChannelQuantizedFp8Linear for linear_proj / fc2 (smooth_scale divisor); first and last layer stay bf16.  Four
+    layers at small widths, 2 forwards sharing the KV cache, against the oracle's restatement (magi_oracle.qlinear)
+    on the SAME quantised parameters: the e4m3 codes are bit-exact per linear, so the distance is the bf16 one."""
+    from inferix_b200.kvcache_manager.model import InferenceParams
+    cfgd = dict(hidden_size=512, ffn_hidden_size=1024, num_attention_heads=4, num_query_groups=2, kv_channels=128,
+                num_layers=4, gated_linear_unit=glu)
+    cfg = mo.MagiConfig(**cfgd)
+    mc = types.SimpleNamespace(layernorm_epsilon=1e-6, apply_layernorm_1p=False, cond_hidden_ratio=0.25,
+                               cond_gating_ratio=1.0, xattn_cond_hidden_ratio=1.0, params_dtype=torch.bfloat16, **cfgd)
+    ec = types.SimpleNamespace(cp_size=1, cp_strategy="none", fp8_quant=True, kv_offload=False)
+    block = magi_layer.TransformerBlock(mc, ec)
+    sd = mo.synth_state_dict(cfg, seed=21)                      # bf16 weights under the reference names
+    g = torch.Generator().manual_seed(22)
+    # quantise the middle layers' linears from the bf16 weights (what a quantised checkpoint would contain)
+    for li in (1, 2):
+        layer = block.layers[li]
+        a, m = layer.self_attention, layer.mlp
+        for name, lin, pfx in [(n, getattr(a.linear_qkv, n), f"layers.{li}.self_attention.linear_qkv.{n}") for n in ("q", "k", "v", "qx")] + \
+                              [("proj", a.linear_proj, f"layers.{li}.self_attention.linear_proj"),
+                               ("fc1", m.linear_fc1, f"layers.{li}.mlp.linear_fc1"), ("fc2", m.linear_fc2, f"layers.{li}.mlp.linear_fc2")]:
+            w = sd.pop(pfx + ".weight")
+            if isinstance(lin, magi_layer.PerChannelQuantizedFp8Linear):
+                lin.quantize_from(w, input_amax=6.0, smooth=0.5 + torch.rand(w.shape[1], generator=g))
+            else:
+                lin.quantize_from(w, input_amax=6.0)
+                lin.input_scale.mul_(1.0 + 0.25 * torch.rand(w.shape[1], generator=g))   # a genuine per-channel vector
+            for pn, pv in lin.state_dict().items():
+                sd[f"{pfx}.{pn}"] = pv.clone()
+    block.load_state_dict(sd, strict=True)
+    block = block.to(DEV)
+    assert block.layers[1]._pack()["fp8"] and not block.layers[0]._pack()["fp8"]
+    clip = 256
+    ip = InferenceParams(1, 4 * clip, device=DEV)
+    cb = mo.OracleMagiCache(4 * clip)
+    plan = [(1, 0, [[0, clip]], [40], True, dict(extract_prefix_video_feature=True)),
+            (2, 1, [[0, 2 * clip], [clip, 3 * clip]], [33, 50], False, {})]
+    for ranges, sp, kr, ylens, update, flags in plan:
+        s = ranges * clip
+        hidden = torch.randn(s, 1, 512, generator=g).bfloat16()
+        cond = torch.randn(1, ranges, 128, generator=g).bfloat16()
+        cmap = torch.arange(ranges).repeat_interleave(clip).reshape(-1, 1)
+        y = torch.randn(sum(ylens), 512, generator=g).bfloat16()
+        ang = torch.randn(s, 48, generator=g) * 2
+        rope = torch.cat([ang.sin(), ang.cos()], -1)
+        cu_q = [i * clip for i in range(ranges + 1)]
+        cu_k = [0]
+        for n in ylens:
+            cu_k.append(cu_k[-1] + n)
+        meta = meta_from_plain(dict(slice_point=sp, denoising_range_num=ranges, clip_token_nums=clip,
+                                    extract_prefix_video_feature=flags.get("extract_prefix_video_feature", False),
+                                    fwd_extra_1st_chunk=False, distill_nearly_clean_chunk=False,
+                                    q_range=[[cu_q[i], cu_q[i + 1]] for i in range(ranges)], k_range=kr,
+                                    cu_seqlens_q=cu_q, cu_seqlens_kv=cu_k))
+        ip.update_kv_cache = cb.update_kv_cache = update
+        out = block(hidden.to(DEV), cond.to(DEV), cmap.to(DEV), y.to(DEV), rope.to(DEV), ip, meta)
+        ref = mo.block_forward(sd, cfg, hidden.clone(), cond, cmap, y, rope, cb, meta)
+        err = rel_l2(out, ref)
+        print(f"fp8_quant block ({'glu' if glu else 'gelu'}), {ranges} range(s): ours-vs-oracle {err:.2e}")
+        assert bool(torch.isfinite(out).all()) and err <= 2.5e-2
+    # one quantised linear on its own: codes bit-exact, product within the fp32 summation order
+    lin = block.layers[1].mlp.linear_fc2
+    x = (torch.randn(300, cfgd["ffn_hidden_size"], generator=g) * 2).bfloat16()
+    pfx = "layers.1.mlp.linear_fc2"
+    codes = ops.quantize_fp8_cols(x.to(DEV), lin.smooth_scale.reshape(-1).contiguous())
+    assert torch.equal(codes.cpu().view(torch.uint8), mo.div_clamp_to(x, sd[pfx + ".smooth_scale"]).view(torch.uint8))
+    assert rel_l2(lin(x.to(DEV)), mo.qlinear(sd, pfx, x)) <= 1e-3
+
+
 # ----------------------------------------------------------------------------------------------- the whole model
 def test_video_dit_model_and_cfg_dispatcher_match_reference(golden_dir):
     """VideoDiTModel.forward (3 forwards sharing a cache) and forward_dispatcher (cfg_number 3 and 1, incl. the batched

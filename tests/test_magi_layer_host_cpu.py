@@ -73,8 +73,15 @@ def test_kernel_sequence_and_unsupported_configs(golden_dir, monkeypatch):
                                    "attention_gqa", "gemm", "gate_norm_residual", "ln_modulate", "gemm", "gemm",
                                    "gate_norm_residual"]
     mc, ec = block.model_config, block.engine_config
-    with pytest.raises(NotImplementedError):
-        magi_layer.TransformerLayer(mc, types.SimpleNamespace(cp_size=1, cp_strategy="none", fp8_quant=True), 0)
+    # fp8_quant: first / last layers stay bf16, the middle ones carry the reference's quantised linear types
+    ec8 = types.SimpleNamespace(cp_size=1, cp_strategy="none", fp8_quant=True)
+    assert isinstance(magi_layer.TransformerLayer(mc, ec8, 0).mlp.linear_fc1, torch.nn.Linear)
+    if mc.num_layers > 2:
+        mid = magi_layer.TransformerLayer(mc, ec8, 1)
+        assert isinstance(mid.mlp.linear_fc1, magi_layer.PerTensorQuantizedFp8Linear)
+        assert isinstance(mid.mlp.linear_fc2, magi_layer.PerChannelQuantizedFp8Linear)
+        assert isinstance(mid.self_attention.linear_proj, magi_layer.PerChannelQuantizedFp8Linear)
+        assert isinstance(mid.self_attention.linear_qkv.q, magi_layer.PerTensorQuantizedFp8Linear)
     with pytest.raises(NotImplementedError):
         magi_layer.TransformerLayer(mc, types.SimpleNamespace(cp_size=2, cp_strategy="cp_shuffle_overlap",
                                                               fp8_quant=False), 0)

@@ -382,6 +382,41 @@ ifx_status ifx_silu_mul(const void* x, int64_t ldx, void* out, int64_t ldo, int6
                         void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Prologue / epilogue of one DiT forward: the ~45 eager ops between the latent tensor and the first
+ * block, and between the last block and the denoised latent, as five small kernels.
+ * ------------------------------------------------------------------------------------------------ */
+
+/* Patch gather: x is the latent [c_in, F, H, W] addressed through element strides (any permuted view); out receives
+ * this rank's token rows [frames * hw_count, c_in*pt*ph*pw] bf16, column k = ((c*pt + dt)*ph + dy)*pw + dx — the
+ * flattening of Conv3d's weight — so that ifx_gemm_bf16(out, weight.view(dim, k), bias) is the patch embedding of
+ * causal_model.py:916-921 with the sequence-parallel scatter of :939-942 folded in. */
+ifx_status ifx_patchify(const void* x, int64_t stride_c, int64_t stride_f, int64_t stride_h, int64_t stride_w,
+                        int32_t c_in, int32_t pt, int32_t ph, int32_t pw, int32_t frames, int32_t grid_h, int32_t grid_w,
+                        int32_t hw_offset, int32_t hw_count, void* out, void* stream);
+/* sinusoidal_embedding_1d (wan_base/components.py:11-31): out[n, dim] = bf16([cos | sin](pos * 10000^(-j/half))), fp64. */
+ifx_status ifx_sinusoidal_embedding(const double* positions, int32_t n, int32_t dim, void* out, void* stream);
+/* nn.Linear on M <= 8 rows (the time MLP of causal_model.py:922-936): out[m, :] = bf16(in[m, :] @ W^T + b), optional
+ * SiLU (rounded to bf16) on the input.  With mod_table (bf16 [layers, N]) the result is not stored as such: out is
+ * [layers, M, N] and receives bf16(mod_table[l, n] + bf16(acc + b[n])) — every layer's `modulation + e0` (:412). */
+ifx_status ifx_linear_small(const void* x, int64_t ldx, const void* w, int64_t ldw, const void* bias, void* out,
+                            int64_t ldo, int32_t M, int32_t N, int32_t K, int32_t silu_input, const void* mod_table,
+                            int32_t layers, int64_t mod_layer_stride, int64_t out_layer_stride, void* stream);
+/* Unpatchify (causal_model.py:1196-1219) + flow -> x0 (wrapper.py:259-283): head_tokens [F*grid_h*grid_w, ph*pw*C]
+ * -> flow_out (optional) and x0_out, both contiguous [F, C, grid_h*ph, grid_w*pw] bf16;
+ * x0 = bf16(x_t - sigma_t * flow) in fp64 with sigma_t = sigmas[argmin_i |timesteps[i] - t_f|].  xt is addressed
+ * through element strides.  timestep: fp64 [frames] on the device (the reference's timestep tensor, `.double()`). */
+ifx_status ifx_unpatchify_x0(const void* head_tokens, const void* xt, int64_t xt_stride_f, int64_t xt_stride_c,
+                             int64_t xt_stride_h, int64_t xt_stride_w, const double* timestep,
+                             const float* table_timesteps, const float* table_sigmas, int32_t table_len, int32_t frames,
+                             int32_t channels, int32_t grid_h, int32_t grid_w, int32_t ph, int32_t pw, void* flow_out,
+                             void* x0_out, void* stream);
+/* FlowMatchScheduler.add_noise (schedulers/flow_match.py:159-176): out = bf16((1 - sigma_f) * x0 + sigma_f * noise),
+ * fp32 arithmetic, contiguous [frames, per_frame] bf16 tensors. */
+ifx_status ifx_add_noise(const void* x0, const void* noise, const double* timestep, const float* table_timesteps,
+                         const float* table_sigmas, int32_t table_len, int32_t frames, int64_t per_frame, void* out,
+                         void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Whole DiT block: CausalWanAttentionBlock.forward  causal_model.py:384-484  in one call (13 launches).
  * ------------------------------------------------------------------------------------------------ */
 typedef struct ifx_wan_block_weights {

@@ -152,6 +152,12 @@ SIGNATURES = {
     "ifx_gate_norm_residual": (C.c_int, [_vp, _i64, _i32, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _i64,
                                          _i32, _f32, _vp]),
     "ifx_silu_mul": (C.c_int, [_vp, _i64, _vp, _i64, _i64, _i32, _vp]),
+    "ifx_patchify": (C.c_int, [_vp, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "ifx_sinusoidal_embedding": (C.c_int, [_vp, _i32, _i32, _vp, _vp]),
+    "ifx_linear_small": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _i32, _i64, _i64, _vp]),
+    "ifx_unpatchify_x0": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32,
+                                    _i32, _vp, _vp, _vp]),
+    "ifx_add_noise": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i64, _vp, _vp]),
     "ifx_wan_block_forward": (C.c_int, [C.POINTER(WanBlockWeights), C.POINTER(WanBlockIO), C.POINTER(KvPlan), _vp]),
     "ifx_wan_block_forward_sp": (C.c_int, [C.POINTER(WanBlockWeights), C.POINTER(WanBlockIO), C.POINTER(PeerDst), _i32,
                                            _i32, _i32, C.POINTER(KvPlan), _vp]),

@@ -18,7 +18,7 @@ __all__ = [
     "quantize_weight_per_channel", "Q8_E4M3", "Q8_INT8", "ln_modulate_fp8", "gemm_fp8", "attention", "attention_gqa", "attention_ranges", "attention_partial", "attention_combine",
     "attention_workspace_bytes", "attention_extents", "attention_lse", "qk_norm_rope_append", "PagedKV", "rope_table",
     "EPI_BIAS", "EPI_BIAS_GELU", "EPI_BIAS_GATE_RES", "EPI_BIAS_GELU_ERF", "EPI_BIAS_F32",
-    "qk_norm_rope_append_peers", "peer_push", "magi_qkv_post", "head_layernorm", "gate_norm_residual", "silu_mul",
+    "qk_norm_rope_append_peers", "peer_push", "patchify", "sinusoidal_embedding", "linear_small", "unpatchify_x0", "add_noise", "magi_qkv_post", "head_layernorm", "gate_norm_residual", "silu_mul",
 ]
 
 
@@ -660,4 +660,105 @@ def silu_mul(x, out=None):
     out = torch.empty((rows, two_f // 2), dtype=torch.bfloat16, device=x.device) if out is None else _bf16_2d(out, "out")
     _lib.check(_lib.load().ifx_silu_mul(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), rows, two_f // 2,
                                         _stream()))
+    return out
+
+
+# ----------------------------------------------------------------------------- forward prologue / epilogue
+def patchify(x, patch, hw_offset=0, hw_count=None, out=None):
+    """x: latent [C_in, F, H, W] bf16 (any strides) -> this rank's token rows [F/pt * hw_count, C_in*pt*ph*pw] (the A
+    operand of the patch-embedding GEMM; column order = Conv3d weight flattening)."""
+    if not x.is_cuda or x.dtype != torch.bfloat16 or x.dim() != 4:
+        raise ValueError("patchify: expected a CUDA bfloat16 [C_in, F, H, W] tensor")
+    c_in, f, hh, ww = x.shape
+    pt, ph, pw = patch
+    if f % pt or hh % ph or ww % pw:
+        raise ValueError("patchify: the latent must be a whole number of patches")
+    gh, gw = hh // ph, ww // pw
+    hw_count = gh * gw if hw_count is None else hw_count
+    rows, k = (f // pt) * hw_count, c_in * pt * ph * pw
+    out = torch.empty((rows, k), dtype=torch.bfloat16, device=x.device) if out is None else out
+    _lib.check(_lib.load().ifx_patchify(x.data_ptr(), x.stride(0), x.stride(1), x.stride(2), x.stride(3), c_in, pt, ph, pw,
+                                        f // pt, gh, gw, hw_offset, hw_count, out.data_ptr(), _stream()))
+    return out
+
+
+def _f64_vec(t, name):
+    if not t.is_cuda or t.dtype != torch.float64 or not t.is_contiguous() or t.dim() != 1:
+        raise ValueError(f"{name}: expected a contiguous 1-D CUDA float64 tensor")
+    return t
+
+
+def sinusoidal_embedding(positions, dim):
+    """wan_base/components.py:11-31: positions fp64 [n] -> bf16 [n, dim] = [cos | sin]."""
+    positions = _f64_vec(positions, "positions")
+    out = torch.empty((positions.numel(), dim), dtype=torch.bfloat16, device=positions.device)
+    _lib.check(_lib.load().ifx_sinusoidal_embedding(positions.data_ptr(), positions.numel(), dim, out.data_ptr(), _stream()))
+    return out
+
+
+def linear_small(x, w, bias=None, *, silu_input=False, mod_table=None):
+    """nn.Linear on <= 8 rows: bf16(SiLU?(x) @ w.T + bias).  mod_table [layers, N]: returns [layers, M, N] =
+    bf16(mod_table[l] + that)."""
+    x, w = _bf16_2d(x, "x"), _bf16_2d(w, "w")
+    m, k = x.shape
+    n = w.shape[0]
+    if w.shape[1] != k:
+        raise ValueError("linear_small: shape mismatch")
+    if mod_table is None:
+        out = torch.empty((m, n), dtype=torch.bfloat16, device=x.device)
+        layers, ms, os_ = 0, 0, 0
+    else:
+        mod_table = _bf16_2d(mod_table, "mod_table")
+        if mod_table.shape[1] != n or not mod_table.is_contiguous():
+            raise ValueError("mod_table must be contiguous [layers, N]")
+        layers = mod_table.shape[0]
+        out = torch.empty((layers, m, n), dtype=torch.bfloat16, device=x.device)
+        ms, os_ = n, m * n
+    _lib.check(_lib.load().ifx_linear_small(x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0),
+                                            _ptr(_bf16_vec(bias, n, "bias")), out.data_ptr(), n, m, n, k, int(silu_input),
+                                            _ptr(mod_table), layers, ms, os_, _stream()))
+    return out
+
+
+def _sigma_tables(timesteps, sigmas):
+    for t, name in ((timesteps, "timesteps"), (sigmas, "sigmas")):
+        if not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous() or t.dim() != 1:
+            raise ValueError(f"{name}: expected a contiguous 1-D CUDA float32 tensor (the scheduler's table)")
+    if timesteps.numel() != sigmas.numel():
+        raise ValueError("timesteps / sigmas tables differ in length")
+    return timesteps, sigmas
+
+
+def unpatchify_x0(head_tokens, xt, timestep, timesteps_table, sigmas_table, patch_hw, want_flow=True):
+    """head_tokens [F*gh*gw, ph*pw*C] bf16, xt [F, C, H, W] bf16 (any strides), timestep fp64 [F] ->
+    (flow [F, C, H, W] or None, x0 [F, C, H, W]): unpatchify + x0 = x_t - sigma_t * flow in fp64."""
+    head_tokens = _bf16_2d(head_tokens, "head_tokens")
+    if not head_tokens.is_contiguous():
+        raise ValueError("head_tokens must be contiguous")
+    f, c, hh, ww = xt.shape
+    ph, pw = patch_hw
+    gh, gw = hh // ph, ww // pw
+    if head_tokens.shape != (f * gh * gw, ph * pw * c) or xt.dtype != torch.bfloat16 or not xt.is_cuda:
+        raise ValueError("unpatchify_x0: head_tokens / xt shapes do not match")
+    timestep = _f64_vec(timestep, "timestep")
+    tt, ss = _sigma_tables(timesteps_table, sigmas_table)
+    x0 = torch.empty((f, c, hh, ww), dtype=torch.bfloat16, device=xt.device)
+    flow = torch.empty_like(x0) if want_flow else None
+    _lib.check(_lib.load().ifx_unpatchify_x0(head_tokens.data_ptr(), xt.data_ptr(), xt.stride(0), xt.stride(1), xt.stride(2),
+                                             xt.stride(3), timestep.data_ptr(), tt.data_ptr(), ss.data_ptr(), tt.numel(), f, c,
+                                             gh, gw, ph, pw, _ptr(flow), x0.data_ptr(), _stream()))
+    return flow, x0
+
+
+def add_noise(x0, noise, timestep, timesteps_table, sigmas_table):
+    """FlowMatchScheduler.add_noise: bf16((1 - sigma_f) * x0 + sigma_f * noise), x0 / noise [F, ...] contiguous bf16."""
+    if x0.shape != noise.shape or x0.dtype != torch.bfloat16 or noise.dtype != torch.bfloat16 or not x0.is_cuda:
+        raise ValueError("add_noise: x0 / noise must be CUDA bfloat16 tensors of one shape")
+    x0, noise = x0.contiguous(), noise.contiguous()
+    timestep = _f64_vec(timestep, "timestep")
+    tt, ss = _sigma_tables(timesteps_table, sigmas_table)
+    out = torch.empty_like(noise)
+    f = x0.shape[0]
+    _lib.check(_lib.load().ifx_add_noise(x0.data_ptr(), noise.data_ptr(), timestep.data_ptr(), tt.data_ptr(), ss.data_ptr(),
+                                         tt.numel(), f, x0.numel() // f, out.data_ptr(), _stream()))
     return out

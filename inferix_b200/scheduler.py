@@ -51,6 +51,15 @@ class FlowMatchScheduler:
 
     def add_noise(self, original_samples, noise, timestep):
         """(1 - sigma) x0 + sigma noise in fp32-promoted arithmetic, cast to noise's dtype (reference :159-176)."""
+        if (noise.is_cuda and noise.dtype == torch.bfloat16 and original_samples.dtype == torch.bfloat16
+                and original_samples.shape == noise.shape and self.sigmas.dtype == torch.float32):
+            from . import ops      # native kernel: sigma lookup + (1 - sigma) x0 + sigma noise in one launch
+            if timestep.ndim == 2:
+                timestep = timestep.flatten(0, 1)
+            self.sigmas = self.sigmas.to(noise.device)
+            self.timesteps = self.timesteps.to(noise.device)
+            return ops.add_noise(original_samples, noise, timestep.to(torch.float64).contiguous(),
+                                 self.timesteps.contiguous(), self.sigmas.contiguous())
         _, sigma = self._sigma_of(timestep, noise.device)
         return ((1 - sigma) * original_samples + sigma * noise).type_as(noise)
 

@@ -635,7 +635,7 @@ class CausalWanModel(nn.Module):
                                 rope_params(1024, 2 * (d // 6))], dim=1)          # complex128, causal_model.py:634-641
         self._freqs_table = None
         self._workspace = None
-        self._mod_table = None        # [layers, 1, 1, 6, C] stack of the blocks' modulation parameters
+        self._mod_table = None        # [layers, 6 * C] stack of the blocks' modulation parameters
         self.block_mask = None
         self.num_frame_per_block = 1
         self.independent_first_frame = False
@@ -690,9 +690,11 @@ class CausalWanModel(nn.Module):
 
     def forward(self, x, t, context, seq_len, clip_fea=None, y=None, kv_cache_meta: list = None,
                 crossattn_cache_meta: list = None, current_start: int = 0, cache_start: int = 0,
-                kv_cache_manager: Optional[KVCacheManager] = None, kv_cache_requests: Optional[list] = None):
+                kv_cache_manager: Optional[KVCacheManager] = None, kv_cache_requests: Optional[list] = None,
+                return_tokens: bool = False):
         """x: list of [C_in, F, H, W] (or a [B, C_in, F, H, W] tensor); t [B, F]; context: list of [L, text_dim]
-        (or [B, L, text_dim]).  Returns the flow prediction [B, C_out, F, H, W]."""
+        (or [B, L, text_dim]).  Returns the flow prediction [B, C_out, F, H, W]; with return_tokens (used by the
+        wrapper's fused unpatchify + x0 epilogue) the head output in token order [B, F*hw, ph*pw*C_out] and grid_sizes."""
         if kv_cache_meta is None:
             raise NotImplementedError("training forward (_forward_train) is out of scope")
         pc = self.parallel_config
@@ -701,16 +703,38 @@ class CausalWanModel(nn.Module):
             self._freqs_table = ops.rope_table(self.freqs, device)
 
         # embeddings (causal_model.py:916-936)
-        xs = [self.patch_embedding(u.unsqueeze(0)) for u in x]
-        grid_sizes = torch.stack([torch.tensor(u.shape[2:], dtype=torch.long) for u in xs])
-        xs = [u.flatten(2).transpose(1, 2) for u in xs]
-        assert max(u.size(1) for u in xs) <= seq_len
-        x = torch.cat(xs).contiguous()
-        frames = int(grid_sizes[0, 0])
-        e = self.time_embedding(sinusoidal_embedding_1d(self.freq_dim, t.flatten()).type_as(x))
-        e0 = self.time_projection(e).unflatten(1, (6, self.dim)).unflatten(dim=0, sizes=t.shape)
-
-        x = scatter_tokens(x, frames, pc.world_size, pc.rank).contiguous()           # :939-942
+        frames = x[0].shape[1] // self.patch_size[0]
+        gh, gw = x[0].shape[2] // self.patch_size[1], x[0].shape[3] // self.patch_size[2]
+        grid_sizes = torch.tensor([[frames, gh, gw]] * len(x), dtype=torch.long)
+        assert frames * gh * gw <= seq_len
+        fused = (len(x) * t.shape[1] <= 8 and all(u.is_cuda and u.dtype == torch.bfloat16 for u in x)
+                 and self.patch_embedding.weight.dtype == torch.bfloat16)
+        if fused:
+            # native prologue: patch gather (this rank's hw slice only) + GEMM, fp64 sinusoid, three small linears; the
+            # last one writes every layer's `modulation + e0` table (:412) directly
+            chunk = (gh * gw) // pc.world_size
+            pw_ = self.patch_embedding.weight.view(self.dim, -1)
+            x = torch.stack([ops.gemm(ops.patchify(u, self.patch_size, pc.rank * chunk, chunk), pw_,
+                                      self.patch_embedding.bias) for u in x])
+            if self._mod_table is None:
+                self._mod_table = torch.stack([blk.modulation.reshape(-1) for blk in self.blocks]).detach().contiguous()
+            tp, te = self.time_projection[1], self.time_embedding
+            sin = ops.sinusoidal_embedding(t.flatten().to(torch.float64), self.freq_dim)
+            e = ops.linear_small(ops.linear_small(sin, te[0].weight, te[0].bias), te[2].weight, te[2].bias, silu_input=True)
+            mods = ops.linear_small(e, tp.weight, tp.bias, silu_input=True, mod_table=self._mod_table)
+            mods = mods.view(len(self.blocks), *t.shape, 6, self.dim)
+            e0 = None
+        else:
+            xs = [self.patch_embedding(u.unsqueeze(0)) for u in x]
+            xs = [u.flatten(2).transpose(1, 2) for u in xs]
+            x = torch.cat(xs).contiguous()
+            e = self.time_embedding(sinusoidal_embedding_1d(self.freq_dim, t.flatten()).type_as(x))
+            e0 = self.time_projection(e).unflatten(1, (6, self.dim)).unflatten(dim=0, sizes=t.shape)
+            x = scatter_tokens(x, frames, pc.world_size, pc.rank).contiguous()           # :939-942
+            if self._mod_table is None:
+                self._mod_table = torch.stack([blk.modulation.reshape(-1) for blk in self.blocks]).detach().contiguous()
+            # every layer's `modulation + e0` (causal_model.py:412) in one launch: [layers, B, F, 6, C]
+            mods = self._mod_table.view(len(self.blocks), 1, 1, 6, self.dim) + e0.unsqueeze(0)
 
         # text embedding only when some layer still has to build its cross-attention K/V (reference: every call)
         ctx = None
@@ -719,12 +743,9 @@ class CausalWanModel(nn.Module):
                 [torch.cat([u, u.new_zeros(self.text_len - u.size(0), u.size(1))]) for u in context]))
 
         ws = self._get_workspace(x.shape[1], device)
-        # every layer's `modulation + e` (causal_model.py:412) in one launch: [layers, B, F, 6, C]
-        if self._mod_table is None:
-            self._mod_table = torch.stack([blk.modulation for blk in self.blocks]).unsqueeze(2).detach()
-        mods = self._mod_table + e0.unsqueeze(0)
+        e_blk = mods[0] if e0 is None else e0          # the blocks read only its shape when `mod` is given
         for i, block in enumerate(self.blocks):
-            x = block(x, e=e0, seq_lens=None, grid_sizes=grid_sizes, freqs=self._freqs_table, context=ctx,
+            x = block(x, e=e_blk, seq_lens=None, grid_sizes=grid_sizes, freqs=self._freqs_table, context=ctx,
                       context_lens=None, block_mask=None, kv_cache_meta=kv_cache_meta[i],
                       crossattn_cache_meta=crossattn_cache_meta[i], current_start=current_start,
                       cache_start=cache_start, kv_cache_manager=kv_cache_manager,
@@ -744,6 +765,8 @@ class CausalWanModel(nn.Module):
         x = self.head(x, e.unflatten(dim=0, sizes=t.shape).unsqueeze(2))             # [B, F, hw/P, 64]
         x = x.flatten(1, 2)
         x = all_gather_tokens(x, frames, pc)                                         # :1008-1022
+        if return_tokens:
+            return x, grid_sizes
         return torch.stack(self.unpatchify(x, grid_sizes))
 
     def unpatchify(self, x, grid_sizes):

@@ -55,6 +55,29 @@ class WanDiffusionWrapper(torch.nn.Module):
         if kv_cache_meta is None:
             raise NotImplementedError("only the KV-cached inference branch is built")
         prompt_embeds = conditional_dict["prompt_embeds"]
+        x = noisy_image_or_video
+        if x.is_cuda and x.dtype == torch.bfloat16 and getattr(self.model, "patch_size", (1, 2, 2))[0] == 1:
+            # native epilogue: unpatchify + fp64 flow -> x0 in one kernel straight from the head's token output
+            from . import ops
+            tokens, _grid = self.model(
+                x.permute(0, 2, 1, 3, 4), t=timestep, context=prompt_embeds, seq_len=self.seq_len,
+                kv_cache_meta=kv_cache_meta, crossattn_cache_meta=crossattn_cache_meta, current_start=current_start,
+                cache_start=cache_start, kv_cache_manager=kv_cache_manager, kv_cache_requests=kv_cache_requests,
+                return_tokens=True)
+            dev = x.device
+            if self.scheduler.sigmas.device != dev or self.scheduler.timesteps.device != dev:
+                self.scheduler.sigmas = self.scheduler.sigmas.to(dev)
+                self.scheduler.timesteps = self.scheduler.timesteps.to(dev)
+            tt = self.scheduler.timesteps.float().contiguous()
+            ss = self.scheduler.sigmas.float().contiguous()
+            ps = self.model.patch_size
+            flows, x0s = [], []
+            for b in range(x.shape[0]):
+                fl, x0 = ops.unpatchify_x0(tokens[b].contiguous(), x[b], timestep[b].to(torch.float64).contiguous(), tt, ss,
+                                           (ps[1], ps[2]))
+                flows.append(fl)
+                x0s.append(x0)
+            return torch.stack(flows), torch.stack(x0s)
         flow_pred = self.model(
             noisy_image_or_video.permute(0, 2, 1, 3, 4), t=timestep, context=prompt_embeds, seq_len=self.seq_len,
             kv_cache_meta=kv_cache_meta, crossattn_cache_meta=crossattn_cache_meta, current_start=current_start,

@@ -269,6 +269,7 @@ def test_fp8_quant_block_matches_oracle(glu):
     ec = types.SimpleNamespace(cp_size=1, cp_strategy="none", fp8_quant=True, kv_offload=False)
     block = magi_layer.TransformerBlock(mc, ec)
     sd = mo.synth_state_dict(cfg, seed=21)                      # bf16 weights under the reference names
+    sd_bf16 = dict(sd)
     g = torch.Generator().manual_seed(22)
     # quantise the middle layers' linears from the bf16 weights (what a quantised checkpoint would contain)
     for li in (1, 2):
@@ -288,9 +289,17 @@ def test_fp8_quant_block_matches_oracle(glu):
     block.load_state_dict(sd, strict=True)
     block = block.to(DEV)
     assert block.layers[1]._pack()["fp8"] and not block.layers[0]._pack()["fp8"]
+    # each quantised linear type on its own first: codes bit-exact, product within the fp32 summation order
+    for pfx, lin in (("layers.1.mlp.linear_fc2", block.layers[1].mlp.linear_fc2),
+                     ("layers.2.self_attention.linear_qkv.k", block.layers[2].self_attention.linear_qkv.k)):
+        xin = (torch.randn(300, lin.in_features, generator=g) * 2).bfloat16()
+        div = sd[pfx + (".smooth_scale" if pfx.endswith("fc2") else ".input_scale")]
+        codes = ops.quantize_fp8_cols(xin.to(DEV), lin.divisor().reshape(-1).contiguous())
+        assert torch.equal(codes.cpu().view(torch.uint8), mo.div_clamp_to(xin, div).view(torch.uint8)), pfx
+        assert rel_l2(lin(xin.to(DEV)), mo.qlinear(sd, pfx, xin)) <= 1e-3, pfx
     clip = 256
     ip = InferenceParams(1, 4 * clip, device=DEV)
-    cb = mo.OracleMagiCache(4 * clip)
+    cb, cb16 = mo.OracleMagiCache(4 * clip), mo.OracleMagiCache(4 * clip)
     plan = [(1, 0, [[0, clip]], [40], True, dict(extract_prefix_video_feature=True)),
             (2, 1, [[0, 2 * clip], [clip, 3 * clip]], [33, 50], False, {})]
     for ranges, sp, kr, ylens, update, flags in plan:
@@ -310,19 +319,17 @@ def test_fp8_quant_block_matches_oracle(glu):
                                     fwd_extra_1st_chunk=False, distill_nearly_clean_chunk=False,
                                     q_range=[[cu_q[i], cu_q[i + 1]] for i in range(ranges)], k_range=kr,
                                     cu_seqlens_q=cu_q, cu_seqlens_kv=cu_k))
-        ip.update_kv_cache = cb.update_kv_cache = update
+        ip.update_kv_cache = cb.update_kv_cache = cb16.update_kv_cache = update
         out = block(hidden.to(DEV), cond.to(DEV), cmap.to(DEV), y.to(DEV), rope.to(DEV), ip, meta)
         ref = mo.block_forward(sd, cfg, hidden.clone(), cond, cmap, y, rope, cb, meta)
-        err = rel_l2(out, ref)
-        print(f"fp8_quant block ({'glu' if glu else 'gelu'}), {ranges} range(s): ours-vs-oracle {err:.2e}")
-        assert bool(torch.isfinite(out).all()) and err <= 2.5e-2
-    # one quantised linear on its own: codes bit-exact, product within the fp32 summation order
-    lin = block.layers[1].mlp.linear_fc2
-    x = (torch.randn(300, cfgd["ffn_hidden_size"], generator=g) * 2).bfloat16()
-    pfx = "layers.1.mlp.linear_fc2"
-    codes = ops.quantize_fp8_cols(x.to(DEV), lin.smooth_scale.reshape(-1).contiguous())
-    assert torch.equal(codes.cpu().view(torch.uint8), mo.div_clamp_to(x, sd[pfx + ".smooth_scale"]).view(torch.uint8))
-    assert rel_l2(lin(x.to(DEV)), mo.qlinear(sd, pfx, x)) <= 1e-3
+        ref16 = mo.block_forward(sd_bf16, cfg, hidden.clone(), cond, cmap, y, rope, cb16, meta)
+        err, quant_effect = rel_l2(out, ref), rel_l2(ref, ref16)
+        print(f"fp8_quant block ({'glu' if glu else 'gelu'}), {ranges} range(s): ours-vs-oracle {err:.2e}  "
+              f"(quantisation itself moves the oracle by {quant_effect:.2e})")
+        # Two bf16 executions of the same quantised stack differ where an activation lands on the other side of an e4m3
+        # rounding boundary (3 mantissa bits: a flipped code moves that input by 6 %); the distance stays a fraction of
+        # what quantisation itself does to the output.
+        assert bool(torch.isfinite(out).all()) and err <= 4e-2 and err <= 0.6 * quant_effect
 
 
 # ----------------------------------------------------------------------------------------------- the whole model

@@ -56,10 +56,12 @@ class FlowMatchScheduler:
             from . import ops      # native kernel: sigma lookup + (1 - sigma) x0 + sigma noise in one launch
             if timestep.ndim == 2:
                 timestep = timestep.flatten(0, 1)
-            self.sigmas = self.sigmas.to(noise.device)
-            self.timesteps = self.timesteps.to(noise.device)
-            return ops.add_noise(original_samples, noise, timestep.to(torch.float64).contiguous(),
-                                 self.timesteps.contiguous(), self.sigmas.contiguous())
+            n = original_samples.shape[0]
+            if timestep.numel() in (1, n):      # one sigma per leading-dim slice, or one for all (broadcast, :170-172)
+                self.sigmas = self.sigmas.to(noise.device)
+                self.timesteps = self.timesteps.to(noise.device)
+                t64 = timestep.reshape(-1).to(torch.float64).expand(n).contiguous()
+                return ops.add_noise(original_samples, noise, t64, self.timesteps.contiguous(), self.sigmas.contiguous())
         _, sigma = self._sigma_of(timestep, noise.device)
         return ((1 - sigma) * original_samples + sigma * noise).type_as(noise)
 

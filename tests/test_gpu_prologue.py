@@ -32,7 +32,15 @@ def test_patch_embedding_equals_conv3d(hw, dim, world, rank):
     ref = ref.view(3, ghw, dim)[:, rank * chunk:(rank + 1) * chunk].reshape(-1, dim)
     a = ops.patchify(x, (1, 2, 2), rank * chunk, chunk)
     out = ops.gemm(a, w.view(dim, -1), b)
-    assert out.shape == ref.shape and rel_l2(out, ref) <= 1e-3
+    # exact statement in fp32 (what the oracle's CPU conv3d accumulates in): ours must be one bf16 rounding away from
+    # it, and at least as close as cuDNN's bf16 Conv3d (measured 2.8e-3 from ours: cuDNN is the less exact of the two)
+    ref32 = F.conv3d(x.unsqueeze(0).float(), w.float(), b.float(), stride=(1, 2, 2)).flatten(2).transpose(1, 2)[0]
+    ref32 = ref32.view(3, ghw, dim)[:, rank * chunk:(rank + 1) * chunk].reshape(-1, dim)
+    ours, cudnn = rel_l2(out, ref32), rel_l2(ref, ref32)
+    print(f"patch embedding vs fp32 conv3d: ours {ours:.2e}, cuDNN bf16 {cudnn:.2e}; ours vs cuDNN {rel_l2(out, ref):.2e}")
+    assert out.shape == ref.shape and ours <= 2.5e-3 and ours <= cudnn + 2e-4
+    assert torch.equal(a.view(3, chunk, 16, 2, 2)[1, 5, :, 1, 0],
+                       x[:, 1, 2 * ((rank * chunk + 5) // (hw[1] // 2)) + 1, 2 * ((rank * chunk + 5) % (hw[1] // 2))])
 
 
 def test_sinusoid_and_time_mlp():
@@ -92,3 +100,6 @@ def test_add_noise_bit_exact():
         _, sigma = sched._sigma_of(t, DEV)
         ref = ((1 - sigma) * x0 + sigma * noise).type_as(noise)                        # the reference's eager arithmetic
         assert torch.equal(out, ref)
+    t1 = torch.full((1,), 522, dtype=torch.long, device=DEV)                           # CausVid passes ONE timestep (:233-236)
+    _, sigma = sched._sigma_of(t1, DEV)
+    assert torch.equal(sched.add_noise(x0, noise, t1), ((1 - sigma) * x0 + sigma * noise).type_as(noise))

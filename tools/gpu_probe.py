@@ -235,6 +235,50 @@ def check_gemm_once():
         ops.gemm(x, w, b, out=out, epilogue=ops.EPI_BIAS_GELU)
 
 
+def check_gemm_fp8_once():
+    """FFN1 GEMM with e4m3 operands at the config-2 shape (target of `ncu -k regex:gemm2_tn`)."""
+    S, C, F_ = 10800, 1536, 8960
+    x = torch.randn(S, C, device=dev).bfloat16()
+    w = (torch.randn(F_, C, device=dev) / math.sqrt(C)).bfloat16()
+    b = torch.randn(F_, device=dev).bfloat16()
+    wq, ws = ops.quantize_weight_per_channel(w, ops.Q8_E4M3)
+    out = torch.empty(S, F_, device=dev, dtype=torch.bfloat16)
+    for _ in range(4):
+        aq, a_s = ops.quantize_rows(x, ops.Q8_E4M3)
+        ops.gemm_q8(aq, wq, a_s, ws, ops.Q8_E4M3, b, out, epilogue=ops.EPI_BIAS_GELU)
+
+
+def check_gemm_small_once():
+    """FFN2 GEMM at the 8-way sequence-parallel shard shape (M = 1350, K = 8960): the 128-wide cluster tile."""
+    S, C, F_ = 1350, 1536, 8960
+    x = torch.randn(S, F_, device=dev).bfloat16()
+    w = (torch.randn(C, F_, device=dev) / math.sqrt(F_)).bfloat16()
+    b = torch.randn(C, device=dev).bfloat16()
+    res = torch.randn(S, C, device=dev).bfloat16()
+    gate = torch.randn(3, C, device=dev).bfloat16()
+    for _ in range(4):
+        ops.gemm(x, w, b, res, epilogue=ops.EPI_BIAS_GATE_RES, residual=res, gate=gate, tokens_per_frame=S // 3)
+
+
+def check_rows_once():
+    """The HBM-bound row kernels at the config-2 shape: LN + modulate, and QK-RMSNorm + fp64 RoPE + paged append."""
+    from inferix_b200._lib import RopeGrid
+    S, C, H = 10800, 1536, 12
+    x = torch.randn(S, C, device=dev).bfloat16()
+    mod = (torch.randn(3, 6, C, device=dev) * 0.3).bfloat16()
+    qkv = torch.randn(S, 3 * C, device=dev).bfloat16()
+    nq, nk = torch.rand(C, device=dev).bfloat16() + 0.5, torch.rand(C, device=dev).bfloat16() + 0.5
+    freqs = torch.view_as_real(torch.polar(torch.ones(1024, 64, dtype=torch.float64),
+                                           torch.randn(1024, 64, dtype=torch.float64))).contiguous().to(dev)
+    store = ops.PagedKV(24, 3600, H, 128, dev)
+    h = torch.empty_like(x)
+    q = torch.empty_like(x)
+    for i in range(4):
+        ops.ln_modulate(x, h, shift=mod[:, 0], scale=mod[:, 1], tokens_per_frame=3600)
+        plan = store.plan_append(i * S, S, 0, True)
+        ops.qk_norm_rope_append(qkv, nq, nk, freqs, RopeGrid(3, 45, 80, 3 * i, 0, 3600), H, 128, kv=store, plan=plan, q_out=q)
+
+
 if __name__ == "__main__":
     name = sys.argv[1]
     t0 = time.time()

@@ -89,6 +89,10 @@ ifx_status ifx_kv_map(ifx_kv* kv, int64_t tokens, void** k_rows, void** v_rows);
 
 ifx_status ifx_kv_create(ifx_kv** out, void* k_base, void* v_base, int32_t num_pages, int32_t page_tokens,
                          int32_t heads, int32_t head_dim);
+/* Point the handle at other buffers of the same geometry; table and indices are kept.  This is what the offload tier
+ * (reference kvcache_manager.py:222-244: kv_offload -> pinned CPU tensors, copied to the GPU by get()) is built on: the
+ * window of a layer lives in pinned host memory and is staged into one of a few device slots before its block runs. */
+ifx_status ifx_kv_rebind(ifx_kv* kv, void* k_base, void* v_base);
 ifx_status ifx_kv_destroy(ifx_kv* kv);
 /* Reference: pipeline resets global_end_index/local_end_index to 0 (CausalInferencePipeline.py:193-199). */
 ifx_status ifx_kv_reset(ifx_kv* kv);

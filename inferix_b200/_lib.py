@@ -104,6 +104,7 @@ SIGNATURES = {
     "ifx_prof_read": (C.c_int, [C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "ifx_prof_labels": (C.c_int, [C.c_char_p, _i32]),
     "ifx_kv_create": (C.c_int, [C.POINTER(_vp), _vp, _vp, _i32, _i32, _i32, _i32]),
+    "ifx_kv_rebind": (C.c_int, [_vp, _vp, _vp]),
     "ifx_kv_destroy": (C.c_int, [_vp]),
     "ifx_kv_reset": (C.c_int, [_vp]),
     "ifx_kv_plan_append": (C.c_int, [_vp, _i64, _i64, _i64, _i32, C.POINTER(KvPlan)]),

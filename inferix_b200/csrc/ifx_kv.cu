@@ -59,6 +59,17 @@ extern "C" ifx_status ifx_kv_create(ifx_kv** out, void* k_base, void* v_base, in
     return IFX_OK;
 }
 
+extern "C" ifx_status ifx_kv_rebind(ifx_kv* kv_, void* k_base, void* v_base) {
+    KvImpl* kv = kv_cast(kv_);
+    if (!kv) return set_error(IFX_ERR_HANDLE, "ifx_kv_rebind: bad kv handle");
+    IFX_CHECK_ARG(k_base && v_base, "ifx_kv_rebind: null pointer");
+    IFX_CHECK_ARG((reinterpret_cast<uintptr_t>(k_base) & 15) == 0 && (reinterpret_cast<uintptr_t>(v_base) & 15) == 0,
+                  "ifx_kv_rebind: buffers must be 16-byte aligned");
+    kv->k_base = k_base;
+    kv->v_base = v_base;
+    return IFX_OK;
+}
+
 extern "C" ifx_status ifx_kv_destroy(ifx_kv* kv_) {
     KvImpl* kv = kv_cast(kv_);
     if (!kv) return set_error(IFX_ERR_HANDLE, "ifx_kv_destroy: bad kv handle");

@@ -6,17 +6,23 @@ layer is a ``PagedKV`` (two bf16 buffers ``[num_blocks * block_size, H*D]`` plus
 hot path appends / evicts / attends through the C ABI without ever materialising the reference layout, and the
 tensor-returning methods (get / get_range / select / get_raw) gather a copy in the reference's logical order.
 
-``kv_offload=True`` (the reference's pinned-CPU tier, :222-244) is accepted but the cache stays in HBM: a B200 holds
-the whole window (15.9 GB for Self-Forcing 720p x 8 blocks); the offload tier is SURVEY §8f rank 4, not built.
+``kv_offload=True`` (the reference's pinned-CPU tier, :222-244; its model default).  A B200 holds the whole window
+(15.9 GB for Self-Forcing 720p x 8 blocks of 180 GB), so by default the request is NOT honoured: the cache stays in HBM
+and a one-time warning says so.  ``KVCacheManager(device, offload_tier=True)`` (or IFX_KV_OFFLOAD=1) honours it: paged
+layer caches then live in pinned host memory and are staged through ``offload_slots`` device slots — layer i + 1 is
+copied in on a side stream while layer i computes, the pages a forward writes are copied back (ops.PagedKV.stage /
+write_back).  HBM use drops from all layers to `offload_slots` layers; PCIe carries the window once per layer per forward.
 """
 from __future__ import annotations
 
+import os
+import warnings
 from dataclasses import dataclass
-from typing import KeysView, List, Sequence, Union
+from typing import KeysView, List, Optional, Sequence, Union
 
 import torch
 
-from ..ops import PagedKV
+from ..ops import OffloadSlots, PagedKV
 
 
 def cdiv(a: int, b: int) -> int:
@@ -68,12 +74,19 @@ class KVCaches:
 
 
 class KVCacheManager:
-    def __init__(self, device: Union[str, torch.device, int]):
+    def __init__(self, device: Union[str, torch.device, int], offload_tier: Optional[bool] = None,
+                 offload_slots: int = 2):
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise ValueError(f"inferix_b200.KVCacheManager needs a CUDA device, got {self.device} (no CPU path)")
         self.offload_device = torch.device("cpu")
         self.request_to_kv_caches: dict = {}
+        self.offload_tier = (os.environ.get("IFX_KV_OFFLOAD", "0") == "1") if offload_tier is None else bool(offload_tier)
+        if offload_slots < 2:
+            raise ValueError("offload_slots must be >= 2 (one layer computing, one being staged)")
+        self.offload_slots = offload_slots
+        self._slots: dict = {}          # (rows, width) -> OffloadSlots
+        self._warned_offload = False
 
     # ------------------------------------------------------------------ allocation (reference :62-125)
     def allocate_slots(self, req: KVCacheRequest, spec: KVCacheRequestSpec) -> KVCaches:
@@ -91,8 +104,20 @@ class KVCacheManager:
             size = 2 * num_tokens_aligned * s.num_kv_heads * s.head_size * get_dtype_size(s.dtype)
             kv_caches.specs[layer_name] = KVCacheTensorSpec(size=size, num_tokens=num_tokens_aligned,
                                                             num_blocks=num_blocks, block_size=spec.block_size, spec=s)
+            slots = None
+            if s.kv_offload and spec.block_size > 1:          # paged (frame-sized pages) layer caches only
+                if self.offload_tier:
+                    key = (num_blocks * spec.block_size, s.num_kv_heads * s.head_size)
+                    slots = self._slots.get(key)
+                    if slots is None:
+                        slots = self._slots[key] = OffloadSlots(self.offload_slots, key[0], key[1], self.device)
+                elif not self._warned_offload:
+                    self._warned_offload = True
+                    warnings.warn("inferix_b200: kv_offload=True requested but the KV window stays in HBM (it fits a "
+                                  "B200); pass KVCacheManager(device, offload_tier=True) or IFX_KV_OFFLOAD=1 to keep it "
+                                  "in pinned host memory with device staging slots", stacklevel=2)
             kv_caches.tensors[layer_name] = PagedKV(num_blocks, spec.block_size, s.num_kv_heads, s.head_size,
-                                                    self.device)
+                                                    self.device, offload=slots)
         return kv_caches
 
     def free(self, req: KVCacheRequest):

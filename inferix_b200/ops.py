@@ -397,15 +397,47 @@ def attention_workspace_bytes(q_rows: int, heads: int, pieces_per_item: int) -> 
     return heads * ((q_rows + 255) // 256) * pieces_per_item * 256 * 130 * 4
 
 
-class PagedKV:
-    """One layer's self-attention cache: two bf16 buffers + the native block table (ifx_kv)."""
+class OffloadSlots:
+    """Device staging slots of the KV offload tier: `count` (K, V) buffer pairs of one layer's geometry shared by all
+    layers of a request group, a copy stream, and per-slot events.  Layers take slots round-robin: while layer i
+    computes out of slot i % count, layer i + 1 is staged into the next slot on the copy stream."""
 
-    def __init__(self, num_pages: int, page_tokens: int, heads: int, head_dim: int, device):
+    def __init__(self, count: int, rows: int, width: int, device):
+        self.count, self.device = count, torch.device(device)
+        self.k = [torch.empty((rows, width), dtype=torch.bfloat16, device=device) for _ in range(count)]
+        self.v = [torch.empty((rows, width), dtype=torch.bfloat16, device=device) for _ in range(count)]
+        self.stream = torch.cuda.Stream(device=device)
+        self.owner = [None] * count                  # PagedKV currently staged in the slot
+        self.free_event = [None] * count             # recorded when the slot's last user finished (compute + write-back)
+        self.next = 0
+
+    def take(self):
+        i = self.next
+        self.next = (self.next + 1) % self.count
+        return i
+
+
+class PagedKV:
+    """One layer's self-attention cache: two bf16 buffers + the native block table (ifx_kv).
+
+    offload=OffloadSlots: the reference's kv_offload tier (kvcache_manager.py:222-244 pinned CPU tensors, get() copies
+    them to the GPU).  The window lives in pinned host memory; `stage()` copies its valid prefix into a device slot on
+    the copy stream and re-points the native handle at it, `write_back()` copies the pages a block forward wrote back
+    to the host.  HBM then holds `slots.count` layers instead of all of them."""
+
+    def __init__(self, num_pages: int, page_tokens: int, heads: int, head_dim: int, device, offload: "OffloadSlots" = None):
         self.num_pages, self.page_tokens, self.heads, self.head_dim = num_pages, page_tokens, heads, head_dim
         width = heads * head_dim
-        # like the reference (torch.empty, kvcache_manager.py:232) the memory starts uninitialised
-        self.k = torch.empty((num_pages * page_tokens, width), dtype=torch.bfloat16, device=device)
-        self.v = torch.empty_like(self.k)
+        self.offload, self.slot = offload, None
+        if offload is None:
+            # like the reference (torch.empty, kvcache_manager.py:232) the memory starts uninitialised
+            self.k = torch.empty((num_pages * page_tokens, width), dtype=torch.bfloat16, device=device)
+            self.v = torch.empty_like(self.k)
+        else:
+            self.host_k = torch.empty((num_pages * page_tokens, width), dtype=torch.bfloat16, pin_memory=True)
+            self.host_v = torch.empty_like(self.host_k).pin_memory()
+            self.k, self.v = offload.k[0], offload.v[0]      # re-pointed by stage()
+            self._ready = None                               # event: staging copy done
         h = C.c_void_p()
         _lib.check(_lib.load().ifx_kv_create(C.byref(h), self.k.data_ptr(), self.v.data_ptr(), num_pages, page_tokens,
                                              heads, head_dim))
@@ -422,6 +454,10 @@ class PagedKV:
             _lib.check(_lib.load().ifx_kv_destroy(self._h))
             self._h = None
             self.k = self.v = None
+            if self.offload is not None:
+                if self.slot is not None and self.offload.owner[self.slot] is self:
+                    self.offload.owner[self.slot] = None
+                self.host_k = self.host_v = None
 
     def __del__(self):
         try:
@@ -431,6 +467,53 @@ class PagedKV:
 
     def reset(self) -> None:
         _lib.check(_lib.load().ifx_kv_reset(self.handle))
+
+    # ------------------------------------------------------------------ offload tier
+    def stage(self) -> None:
+        """Make this layer's window resident in a device slot (no-op for HBM-resident caches and when already staged).
+        The copy runs on the slots' stream; `wait_staged()` orders the caller's stream after it."""
+        sl = self.offload
+        if sl is None or (self.slot is not None and sl.owner[self.slot] is self):
+            return
+        i = sl.take()
+        prev = sl.owner[i]
+        if prev is not None:
+            prev.slot = None
+        with torch.cuda.stream(sl.stream):
+            if sl.free_event[i] is not None:
+                sl.stream.wait_event(sl.free_event[i])       # the slot's previous layer has computed and written back
+            _, local_end, table = self.state()
+            rows = len(table) * self.page_tokens            # mapped pages = physical prefix (allocator invariant)
+            if rows:
+                sl.k[i][:rows].copy_(self.host_k[:rows], non_blocking=True)
+                sl.v[i][:rows].copy_(self.host_v[:rows], non_blocking=True)
+            self._ready = torch.cuda.Event()
+            self._ready.record(sl.stream)
+        sl.owner[i], self.slot = self, i
+        self.k, self.v = sl.k[i], sl.v[i]
+        _lib.check(_lib.load().ifx_kv_rebind(self.handle, self.k.data_ptr(), self.v.data_ptr()))
+
+    def wait_staged(self) -> None:
+        if self.offload is not None and self._ready is not None:
+            torch.cuda.current_stream().wait_event(self._ready)
+
+    def write_back(self, pages) -> None:
+        """Copy the given physical pages (those a block forward just wrote) from the device slot to the host tier and
+        mark the slot reusable once that is done."""
+        sl = self.offload
+        if sl is None:
+            return
+        done = torch.cuda.Event()
+        done.record(torch.cuda.current_stream())
+        pt = self.page_tokens
+        with torch.cuda.stream(sl.stream):
+            sl.stream.wait_event(done)
+            for r0, n in _coalesce_pages(pages, pt):
+                self.host_k[r0:r0 + n].copy_(self.k[r0:r0 + n], non_blocking=True)
+                self.host_v[r0:r0 + n].copy_(self.v[r0:r0 + n], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(sl.stream)
+        sl.free_event[self.slot] = ev
 
     def plan_append(self, current_start: int, num_new: int, sink_tokens: int = 0, windowed: bool = True) -> KvPlan:
         plan = KvPlan()
@@ -444,12 +527,20 @@ class PagedKV:
         _lib.check(_lib.load().ifx_kv_state(self.handle, C.byref(g), C.byref(l), C.byref(n), table, self.num_pages))
         return g.value, l.value, list(table[: n.value])
 
+    def _resident(self) -> None:
+        """offload tier: stage the window into a device slot and order the current stream after the copy"""
+        if self.offload is not None:
+            self.stage()
+            self.wait_staged()
+
     def append(self, plan: KvPlan, k_rows: torch.Tensor, v_rows: torch.Tensor) -> None:
         k_rows, v_rows = _bf16_2d(k_rows, "k_rows"), _bf16_2d(v_rows, "v_rows")
         if k_rows.stride(0) != v_rows.stride(0) or k_rows.shape != v_rows.shape:
             raise ValueError("k_rows / v_rows must share shape and stride")
+        self._resident()
         _lib.check(_lib.load().ifx_kv_append(self.handle, C.byref(plan), k_rows.data_ptr(), v_rows.data_ptr(),
                                              k_rows.stride(0), k_rows.shape[0], _stream()))
+        self.write_back(list(plan.pages[: plan.num_pages]))
 
     def append_sp(self, plan: KvPlan, k_gathered: torch.Tensor, v_gathered: torch.Tensor, frames: int) -> None:
         """k/v_gathered: [world, frames*chunk, H*D] rank-major views (rows contiguous, any common rank stride — e.g.
@@ -483,15 +574,22 @@ class PagedKV:
         width = self.heads * self.head_dim
         k = torch.empty((length, width), dtype=torch.bfloat16, device=self.k.device)
         v = torch.empty_like(k)
+        self._resident()
         _lib.check(_lib.load().ifx_kv_export(self.handle, k.data_ptr(), v.data_ptr(), start, length, _stream()))
+        self.write_back([])            # nothing written; releases the slot after this read
         return k, v
 
     def import_(self, start: int, k_rows: torch.Tensor, v_rows: torch.Tensor) -> None:
         k_rows, v_rows = _bf16_2d(k_rows, "k_rows"), _bf16_2d(v_rows, "v_rows")
         if not (k_rows.is_contiguous() and v_rows.is_contiguous()) or k_rows.shape != v_rows.shape:
             raise ValueError("import_: contiguous [length, H*D] tensors expected")
+        self._resident()
         _lib.check(_lib.load().ifx_kv_import(self.handle, k_rows.data_ptr(), v_rows.data_ptr(), start,
                                              k_rows.shape[0], _stream()))
+        if self.offload is not None:
+            _, _, table = self.state()
+            pt = self.page_tokens
+            self.write_back(table[start // pt:(start + k_rows.shape[0] + pt - 1) // pt])
 
     def attention(self, q: torch.Tensor, out=None, *, softmax_scale=None, fresh: Optional[KvPlan] = None,
                   flags: Optional[torch.Tensor] = None, epoch: int = 0, timeout_ms: int = 60000):

@@ -266,6 +266,11 @@ class CausalWanAttentionBlock(nn.Module):
             xb = x[bi]
             if not xb.is_contiguous():
                 raise ValueError("x must be contiguous per sample")
+            if store.offload is not None:           # offload tier: the window must sit in a device slot
+                if world > 1:
+                    raise NotImplementedError("the KV offload tier is single-GPU (peer-mapped caches cannot move)")
+                store.stage()
+                store.wait_staged()
             peer_dst = getattr(store, "peer", None) if world > 1 else None
             native_block = getattr(self, "_fp8", None) is None and self._amax is None and self._q8 is None
             if native_block and (world == 1 or (peer_dst is not None and _SP_MODE in ("overlap", "store"))):
@@ -297,6 +302,8 @@ class CausalWanAttentionBlock(nn.Module):
                 kv_cache_meta["global_end_index"].fill_(plan.global_end)
                 kv_cache_meta["local_end_index"].fill_(plan.local_end)
             kv_cache_meta["_ifx_plan"] = (plan.local_start, plan.local_end, plan.global_end, plan.num_evicted)
+            if store.offload is not None:
+                store.write_back(list(plan.pages[: plan.num_pages]))
         if crossattn_cache_meta is not None:
             crossattn_cache_meta["is_init"] = True
         return x
@@ -744,7 +751,15 @@ class CausalWanModel(nn.Module):
 
         ws = self._get_workspace(x.shape[1], device)
         e_blk = mods[0] if e0 is None else e0          # the blocks read only its shape when `mod` is given
+        def stage_layer(li):                           # offload tier: copy a layer's window into a device slot
+            for req in kv_cache_requests:
+                st = self.blocks[li].kv_cache_manager.store(kv_cache_manager, req)
+                if st.offload is not None:
+                    st.stage()
+        stage_layer(0)
         for i, block in enumerate(self.blocks):
+            if i + 1 < len(self.blocks):                # ... the next layer's, while this one runs
+                stage_layer(i + 1)
             x = block(x, e=e_blk, seq_lens=None, grid_sizes=grid_sizes, freqs=self._freqs_table, context=ctx,
                       context_lens=None, block_mask=None, kv_cache_meta=kv_cache_meta[i],
                       crossattn_cache_meta=crossattn_cache_meta[i], current_start=current_start,

@@ -402,6 +402,39 @@ def pipeline_inference(sd, cfg: WanConfig, sched: FlowMatchSigmas, noise: torch.
     return out, caches
 
 
+def cfg_pipeline_inference(sd, cfg: WanConfig, sched: FlowMatchSigmas, noise, context, neg_context, scheduler_factory,
+                           guidance_scale: float, num_frame_per_block: int, frame_seq_length: int, cache_tokens: int,
+                           attn_dtype=None):
+    """CausalDiffusionInferencePipeline.inference (T2V, no initial latent),
+    pipeline/self_forcing/CausalDiffusionInferencePipeline.py:50-296: per block, for every sampler timestep a conditional
+    and an unconditional forward (separate caches), flow = uncond + g * (cond - uncond), one multistep-sampler step; then
+    the clean re-run of both branches.  `scheduler_factory()` returns a fresh sampler with `.timesteps` and
+    `.step(flow, t, latents, return_dict=False)` (the reference's FlowUniPCMultistepScheduler; its restatement in
+    inferix_b200/unipc.py is pinned bit-exact to the reference class by tests/golden/unipc.pt)."""
+    b, num_frames = noise.shape[:2]
+    caches = [new_cache(cfg, cache_tokens, b, noise.dtype) for _ in range(2)]
+    cross = [[dict(is_init=False) for _ in range(cfg.num_layers)] for _ in range(2)]
+    ctxs = (context, neg_context)
+    out = torch.zeros_like(noise)
+    start = 0
+    for _ in range(num_frames // num_frame_per_block):
+        n = num_frame_per_block
+        latents = noise[:, start:start + n]
+        s = scheduler_factory()
+        ts = None
+        for t in s.timesteps:
+            ts = t * torch.ones([b, n], dtype=torch.float32)
+            flows = [generator_forward(sd, cfg, sched, latents, ts, ctxs[k], caches[k], cross[k], start * frame_seq_length,
+                                       attn_dtype)[0] for k in range(2)]
+            flow = flows[1] + guidance_scale * (flows[0] - flows[1])
+            latents = s.step(flow, t, latents, return_dict=False)[0]
+        out[:, start:start + n] = latents
+        for k in range(2):
+            generator_forward(sd, cfg, sched, latents, ts * 0, ctxs[k], caches[k], cross[k], start * frame_seq_length, attn_dtype)
+        start += n
+    return out, caches
+
+
 # ----------------------------------------------------------------------------- CausVid
 def causvid_pipeline_inference(sd, cfg: WanConfig, sched: FlowMatchSigmas, noise: torch.Tensor, context: torch.Tensor,
                                denoising_steps: torch.Tensor, num_frame_per_block: int, frame_seq_length: int,

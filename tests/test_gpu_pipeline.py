@@ -367,3 +367,37 @@ def test_per_block_decode_overlaps_next_block():
     assert torch.equal(out_a, out_b) and sorted(dec_a) == sorted(dec_b) == list(range(6))
     assert all(torch.equal(dec_a[i], dec_b[i]) for i in range(6))
     assert t_serial - t_side >= 0.5 * t_decode * 5 / 6             # all but the last block's decode can hide
+
+
+def test_cfg_diffusion_pipeline_matches_oracle():
+    """CausalDiffusionInferencePipeline (many-step sampler + classifier-free guidance, two cache sets): 2 blocks x 6
+    UniPC steps x 2 branches + clean re-runs = 28 native forwards against the oracle's restatement of the reference
+    loop with the same (reference-pinned) sampler.  CFG (scale 3) amplifies the single-forward bf16 distance."""
+    from inferix_b200.diffusion_pipeline import CausalDiffusionInferencePipeline
+    from inferix_b200.synthetic import TINY
+    from inferix_b200.unipc import FlowUniPCMultistepScheduler
+    cfg_d = dict(TINY)
+    g = torch.Generator().manual_seed(31)
+    noise = torch.randn(1, 6, 16, 16, 16, generator=g).bfloat16()
+    context = torch.randn(1, 20, cfg_d["text_dim"], generator=g).bfloat16()
+    neg = torch.randn(1, 12, cfg_d["text_dim"], generator=g).bfloat16()
+    model = CausalWanModel(**cfg_d, local_attn_size=-1, sink_size=0)
+    model.load_state_dict(synth_state_dict(cfg_d, seed=0))
+    model = model.to(torch.bfloat16).to(DEV)
+    args = types.SimpleNamespace(num_train_timestep=1000, timestep_shift=5.0, num_frame_per_block=3, guidance_scale=3.0,
+                                 negative_prompt_embeds=neg.to(DEV), sampling_steps=6, kv_cache_frames=6)
+    pipe = CausalDiffusionInferencePipeline(args, DEV, generator=WanDiffusionWrapper(model=model, timestep_shift=5.0))
+    _, out = pipe.inference(noise.to(DEV), context.to(DEV), KVCacheManager(DEV), KVCacheManager(DEV),
+                            [KVCacheRequest("r")], return_latents=True)
+    cfg = wo.WanConfig(**cfg_d)
+    sd = {k: v.bfloat16() for k, v in synth_state_dict(cfg_d, seed=0).items()}
+    sched = wo.FlowMatchSigmas(shift=5.0)
+
+    def factory():
+        s = FlowUniPCMultistepScheduler(num_train_timesteps=1000, shift=1, use_dynamic_shifting=False)
+        s.set_timesteps(6, device="cpu", shift=5.0)
+        return s
+    ref, _ = wo.cfg_pipeline_inference(sd, cfg, sched, noise, context, neg, factory, 3.0, 3, 64, 6 * 64)
+    err = rel_l2(out, ref)
+    print(f"CFG diffusion pipeline (2 blocks, 6 UniPC steps, guidance 3): rel-L2 vs oracle {err:.3e}")
+    assert bool(torch.isfinite(out).all()) and err <= 2e-2

@@ -316,17 +316,6 @@ ifx_status ifx_attention_lse(const void* q, int64_t ldq, const void* k, const vo
                              int64_t ldo, float* lse, int64_t q_rows, int64_t kv_rows, int32_t heads, int32_t kv_heads,
                              int32_t head_dim, float softmax_scale, void* stream);
 
-/* Introspection (host only, no GPU needed): the slack-fill schedule ifx_attention* uses for q_rows x heads queries over
- * n_tiles 128-key tiles on `sms` SMs.  The plain schedule gives every (head, 256-row pair [, key piece]) its own CTA; on
- * the sequence-parallel shard shapes (1350 / 2700 rows per rank) that leaves SMs under-used, so every CTA above the mean
- * cost sheds its LAST key tiles as an extra segment that an under-loaded CTA (single-tile pieces, idle SMs) runs after
- * its own piece; the segments of an item are merged by the combine pass.  grid = 0: the plain schedule is kept (multi-
- * wave shapes, already balanced, or no gain).  Costs are in key tiles of a two-tile item.  `segments` (optional) receives
- * rows of 7 int32 (cta, item, r0_begin, r0_count, r1_begin, r1_count, partial slot or -1), terminated by cta = -1. */
-ifx_status ifx_attention_plan_info(int32_t q_rows, int32_t heads, int32_t n_tiles, int32_t n_old_tiles, int32_t sms,
-                                   int32_t* grid, double* makespan, double* base_makespan, double* mean_cost,
-                                   int32_t* segments, int32_t segments_cap);
-
 /* Attention over a LIST of key-row extents of k/v[0:kv_rows_total): up to IFX_ATTN_MAX_EXTENTS [row0, rows) pairs
  * (runs of physically consecutive cache pages).  Rows that follow an extent in memory are never attended: their
  * scores are masked and their V rows are zeroed in shared memory before the P V product, so unmapped pages may hold

@@ -142,8 +142,6 @@ SIGNATURES = {
                                         _f32, _vp, _i64, _i32, _i32, _i32, _vp]),
     "ifx_attention_combine": (C.c_int, [_vp, _i32, _vp, _i64, _i64, _i32, _i32, _vp]),
     "ifx_attention_kv": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _i64, _f32, _vp]),
-    "ifx_attention_plan_info": (C.c_int, [_i32, _i32, _i32, _i32, _i32, C.POINTER(_i32), C.POINTER(C.c_double),
-                                          C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_i32), _i32]),
     "ifx_attention_lse": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _f32, _vp]),
     "ifx_attention_extents": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _i64, C.POINTER(_i64), _i32, _vp, _i64, _i64, _i32,
                                         _i32, _i32, _f32, _vp]),

@@ -22,8 +22,6 @@
 // cross-attention (wan_base/model.py:94-95).  Numerics follow FlashAttention-2: fp32 scores and running
 // sum (of the un-rounded probabilities), bf16 P for the PV product, one division by l at the end.
 #include <algorithm>
-#include <cmath>
-#include <cstdlib>
 #include <vector>
 
 #include "ifx_internal.h"
@@ -46,20 +44,6 @@ constexpr int kMaxExt = IFX_ATTN_MAX_EXTENTS;  // key-row extents (runs of physi
 #define IFX_ATTN_POLY_EVERY 0
 #endif
 constexpr int kPolyEvery = IFX_ATTN_POLY_EVERY;  // 0: all exponentials on MUFU; n: one pair in n on the FMA pipe
-
-// One unit of work of a CTA: key tiles [r0_begin, +r0_count) then [r1_begin, +r1_count) of one (head, 256-row pair)
-// item.  Tile ids index the ORDERED tile sequence (resident tiles first, in-flight tiles last).
-struct AttnSeg {
-    int32_t item;
-    int32_t r0_begin, r0_count, r1_begin, r1_count;
-    int32_t slot;    // -1: the segment covers every key of the item -> normalise and write the output;
-                     // >= 0: un-normalised partial (O, max, sum) into this slot, merged by attn_combine_kernel
-};
-constexpr int kMaxSeg = 12;
-// an item whose keys were cut into several segments (planned schedule): its partial slots are consecutive
-struct CombineItem {
-    int32_t item, slot0, nslots;
-};
 
 struct AttnParams {
     int32_t q_rows;
@@ -96,11 +80,6 @@ struct AttnParams {
     int32_t no_dep_wait;     // 1: do not griddepcontrol.wait (see the kernel prologue)
     // ---- fused exchange: warp 2 of CTAs [0, push.n_ctas) ships this rank's rows of the fresh pages to the peers
     PeerPushParams push;
-    // ---- slack-fill schedule (attn_fwd_multi_kernel, host-planned): CTA b runs seg_table[b * kMaxSeg .. + seg_count[b])
-    const AttnSeg* seg_table;
-    const int32_t* seg_count;
-    const CombineItem* comb_items;   // items whose keys are spread over several partial slots
-    int32_t n_comb;
 };
 
 // Monotone cursor over the extent list: key tile j (over the concatenated extents) -> first key row and number of
@@ -570,434 +549,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
 }
 
-// ---------------------------------------------------------------------------------------------- multi-segment variant
-// Same pipeline as attn_fwd_kernel, but a CTA walks a LIST of segments (item, key tiles, partial slot) read from a
-// host-planned table: its own piece first, then pieces shed by busier CTAs ("slack fill", see plan_slack_fill).  Used
-// only where the plain schedule leaves SMs idle (the sequence-parallel shard shapes); the single-segment kernel above
-// stays the one the single-GPU roofline is measured on.
-__device__ __forceinline__ TileRange seg_tiles(const AttnSeg& sg) {
-    TileRange r;
-    r.old_begin = sg.r0_begin;
-    r.n_old = sg.r0_count;
-    r.new_begin = sg.r1_begin;
-    r.n_new = sg.r1_count;
-    return r;
-}
-
-__global__ void __launch_bounds__(kAttnThreads, 1)
-attn_fwd_multi_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sQ = smem;                    // [2][32 KiB]
-    uint8_t* sKV = smem + 2 * kTileBytes;  // [kSlots][32 KiB]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (2 + kSlots) * kTileBytes);
-    uint64_t* kv_full = bars;              // [kSlots]
-    uint64_t* kv_empty = bars + kSlots;    // [kSlots]
-    uint64_t* q_full = bars + 2 * kSlots;  // [1]
-    uint64_t* s_full = q_full + 1;         // [2]
-    uint64_t* p_full = s_full + 2;         // [2]
-    uint64_t* o_full = p_full + 2;         // [1]
-    uint64_t* v_fixed = o_full + 1;        // [kSlots]  warp 3 -> MMA (extent mode): V tile checked, stale rows zeroed
-    uint64_t* q_empty = v_fixed + kSlots;  // [1]  MMA -> producer: every MMA of the segment is done, sQ may be reloaded
-    uint64_t* o_empty = q_empty + 1;       // [2]  softmax -> MMA: the segment's O has been read out of TMEM
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 2);
-    // valid keys of the CTA's t-th tile at [t & 7], written by the producer before it arms the tile's K slot (release
-    // through the mbarrier chain kv_full -> s_full); the softmax warps read it after s_full.  The producer runs < 4
-    // tiles ahead.
-    volatile int32_t* tile_valid = reinterpret_cast<volatile int32_t*>(tmem_slot + 1);
-    __shared__ AttnSeg segs[kMaxSeg];
-    __shared__ int nseg_s;
-
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-
-    // ---- the CTA's work list: planned schedule (table) or one analytically derived segment
-    const int n_kv_all = p.n_ext ? p.ext_tile0[p.n_ext] : (p.kv_rows + kKT - 1) / kKT;
-    const int n_old_all = p.wait_flags ? p.n_old_tiles : n_kv_all;
-    if (threadIdx.x == 0) {
-        const int n = p.seg_count[blockIdx.x];
-        for (int i = 0; i < n; ++i) segs[i] = p.seg_table[blockIdx.x * kMaxSeg + i];
-        nseg_s = n;
-    }
-    // extent mode: a tile at the end of an extent is followed in memory by rows of OTHER pages (unmapped, or being
-    // written by a peer).  Their scores are masked, but 0 x NaN would still poison P V, so warp 3 zeroes those V rows
-    // in shared memory before the MMA warp may consume the tile (v_fixed barrier).  The dense mode needs none of
-    // this: its tensor map ends at kv_rows and TMA zero-fills.
-    const bool fix_tails = p.n_ext != 0;
-
-    if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmQ);
-        tma_prefetch_desc(&tmK);
-        tma_prefetch_desc(&tmV);
-    }
-    if (warp == 1 && lane == 0) {
-        for (int i = 0; i < kSlots; ++i) {
-            mbar_init(&kv_full[i], 1);
-            mbar_init(&kv_empty[i], 1);
-            mbar_init(&v_fixed[i], 1);
-        }
-        mbar_init(q_full, 1);
-        mbar_init(q_empty, 1);
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&s_full[i], 1);
-            mbar_init(&p_full[i], 128);
-            mbar_init(&o_empty[i], 128);
-        }
-        mbar_init(o_full, 1);
-        fence_barrier_init();
-    }
-    if (warp == 2) tmem_alloc<512>(tmem_slot);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const int nseg = nseg_s;
-    // each role re-reads the TMEM base from shared memory into its own registers (a single kernel-wide value gets
-    // spilled to local memory by ptxas and reloaded in front of every MMA)
-    auto tmem_base_of = [tmem_slot]() { return *reinterpret_cast<volatile uint32_t*>(tmem_slot); };
-    // Programmatic dependent launch.  Normal case: wait for the producer of q / K / V before the first global access.
-    // p.no_dep_wait: the preceding kernel on the stream is a peer-push grid this kernel deliberately overlaps (it
-    // released us only after the kernel that wrote q and the local rows had completed, see peer_push_kernel).
-    // The trigger for OUR dependents is issued at the very end of the kernel: this kernel runs for milliseconds and
-    // may spin on the peers' flags, so dependents that became resident early would only hold SM resources.
-    if (!p.no_dep_wait) griddep_wait();
-    // TMEM columns: S0 | S1 | O0 | O1 (128 each)
-
-    // register re-balancing: the producer / MMA warpgroup needs few registers, the softmax warps hold a whole
-    // 128-wide score row per thread (the CTA owns 384 x 168 = 64512 registers = 128 x 88 + 256 x 208; asking for more deadlocks the inc)
-    if (warp < 4) {
-      setmaxnreg_dec<88>();
-      if (warp == 0) {
-        if (lane == 0) {
-            int idx = 0;        // K / V ring counter over all segments
-            int t_run = 0;      // tiles issued so far (tile_valid ring)
-            bool waited = false;
-            for (int si = 0; si < nseg; ++si) {
-                const AttnSeg sg = segs[si];
-                const TileRange tiles = seg_tiles(sg);
-                const int head = sg.item / p.num_q_pairs;
-                const int q0 = (sg.item % p.num_q_pairs) * (2 * kQT);
-                const bool two = q0 + kQT < p.q_rows;  // second tile has at least one real row
-                if (si > 0) mbar_wait(q_empty, static_cast<uint32_t>((si - 1) & 1));
-                // Q: one or two tiles x two 64-wide halves
-                const int nq = two ? 2 : 1;
-                mbar_expect_tx(q_full, nq * kTileBytes);
-                for (int w = 0; w < nq; ++w)
-#pragma unroll
-                    for (int h = 0; h < 2; ++h)
-                        tma_load_2d_hint(sQ + w * kTileBytes + h * kHalfBytes, &tmQ, q_full, head * kHD + h * 64,
-                                         q0 + w * kQT, kEvictFirst);
-                TileCursor cur;
-                const int n_kv = tiles.count();
-                for (int i = 0; i < n_kv; ++i) {
-                    const int j = tiles.tile(i);
-                    if (!waited && p.wait_flags != nullptr && j >= n_old_all) {
-                        wait_peer_flags(p);
-                        waited = true;
-                    }
-                    int krow0, kvalid;
-                    cur.locate(p, j, krow0, kvalid);
-                    tile_valid[(t_run + i) & 7] = kvalid;
-#pragma unroll
-                    for (int kv = 0; kv < 2; ++kv, ++idx) {
-                        const int s = idx % kSlots;
-                        const uint32_t ph = (idx / kSlots) & 1;
-                        mbar_wait(&kv_empty[s], ph ^ 1);
-                        mbar_expect_tx(&kv_full[s], kTileBytes);
-                        const CUtensorMap* tm = kv == 0 ? &tmK : &tmV;
-#pragma unroll
-                        for (int h = 0; h < 2; ++h)
-                            tma_load_2d_hint(sKV + s * kTileBytes + h * kHalfBytes, tm, &kv_full[s],
-                                             (head / p.kv_group) * kHD + h * 64, krow0, kEvictLast);
-                    }
-                }
-                t_run += n_kv;
-            }
-        }
-      } else if (warp == 3) {
-        if (fix_tails) {
-            // every V tile passes through this warp on its way to the MMA warp (v_fixed instead of kv_full); tiles
-            // that end an extent get their rows past the extent zeroed first.  Same tile walk as the producer.
-            int t_run = 0;
-            for (int si = 0; si < nseg; ++si) {
-                const TileRange tiles = seg_tiles(segs[si]);
-                TileCursor cur;
-                const int n_kv = tiles.count();
-                for (int i = 0; i < n_kv; ++i) {
-                    int krow0, kvalid;
-                    cur.locate(p, tiles.tile(i), krow0, kvalid);
-                    const int vi = 2 * (t_run + i) + 1;
-                    const int slot = vi % kSlots;
-                    mbar_wait(&kv_full[slot], static_cast<uint32_t>((vi / kSlots) & 1));
-                    if (kvalid < kKT) {
-                        uint8_t* vt = sKV + slot * kTileBytes;
-                        // row r of the tile = 128 bytes at r * 128 in each 64-dim half (the swizzle permutes 16-byte
-                        // chunks inside the row only)
-                        const int n16 = (kKT - kvalid) * 8;   // 16-byte chunks per half
-                        for (int c = lane; c < 2 * n16; c += 32) {
-                            const int h = c / n16, o = c % n16;
-                            *reinterpret_cast<uint4*>(vt + h * kHalfBytes + kvalid * 128 + o * 16) = make_uint4(0, 0, 0, 0);
-                        }
-                        fence_proxy_async();
-                    }
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&v_fixed[slot]);
-                }
-                t_run += n_kv;
-            }
-        }
-      }
-      if (warp == 2 && p.push.n_ctas > 0 && static_cast<int>(blockIdx.x) < p.push.n_ctas)
-          push_slice(p.push, static_cast<int>(blockIdx.x), lane);
-      if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t tmem_base = tmem_base_of();
-            auto tS = [tmem_base](int w) { return tmem_base + static_cast<uint32_t>(w) * 128u; };
-            auto tO = [tmem_base](int w) { return tmem_base + 256u + static_cast<uint32_t>(w) * 128u; };
-            // S = Q K^T : A = Q (K-major), B = K (K-major), M = N = 128
-            constexpr uint32_t idesc_qk = make_idesc_bf16(kQT, kKT, 0, 0);
-            // O += P V  : A = P (TMEM),   B = V (MN-major: dims contiguous), M = 128, N = head_dim
-            constexpr uint32_t idesc_pv = make_idesc_bf16(kQT, kHD, 0, 1);
-            auto issue_qk = [&](int w, int slot) {
-                const uint32_t qa = smem_u32(sQ + w * kTileBytes);
-                const uint32_t ka = smem_u32(sKV + slot * kTileBytes);
-#pragma unroll
-                for (int k = 0; k < kHD / 16; ++k) {
-                    const uint32_t off = (k >> 2) * kHalfBytes + (k & 3) * 32;
-                    umma_ss(tS(w), make_smem_desc_sw128(qa + off, 16, 1024), make_smem_desc_sw128(ka + off, 16, 1024),
-                            idesc_qk, k != 0);
-                }
-            };
-            auto issue_pv = [&](int w, int slot, bool accumulate) {
-                const uint32_t va = smem_u32(sKV + slot * kTileBytes);
-#pragma unroll
-                for (int k = 0; k < kKT / 16; ++k) {
-                    // 16 keys = 16 rows of 128 bytes; the two 64-dim halves are kHalfBytes apart (LBO), 8-key
-                    // groups 1024 bytes apart (SBO).  P: 16 bf16 = 8 TMEM columns per step.
-                    umma_ts(tO(w), tS(w) + k * 8, make_smem_desc_sw128(va + k * 16 * 128, kHalfBytes, 1024), idesc_pv,
-                            accumulate || k != 0);
-                }
-            };
-            auto slot_of = [](int idx) { return idx % kSlots; };
-            auto phase_of = [](int idx) { return static_cast<uint32_t>((idx / kSlots) & 1); };
-
-            int t_run = 0;              // tiles of all segments so far (K / V ring position)
-            int cnt0 = 0, cnt1 = 0;     // tiles processed per query tile (s_full / p_full phases)
-            int sg0 = 0, sg1 = 0;       // segments per query tile (o_empty phase)
-            for (int si = 0; si < nseg; ++si) {
-                const AttnSeg sg = segs[si];
-                const int q0 = (sg.item % p.num_q_pairs) * (2 * kQT);
-                const bool two = q0 + kQT < p.q_rows;
-                const int n_kv = sg.r0_count + sg.r1_count;
-                const int k0 = 2 * t_run;
-                mbar_wait(q_full, static_cast<uint32_t>(si & 1));
-                mbar_wait(&kv_full[slot_of(k0)], phase_of(k0));
-                tc_fence_after();
-                issue_qk(0, slot_of(k0));
-                umma_commit(&s_full[0]);
-                if (two) {
-                    issue_qk(1, slot_of(k0));
-                    umma_commit(&s_full[1]);
-                }
-                umma_commit(&kv_empty[slot_of(k0)]);
-                for (int j = 0; j < n_kv; ++j) {
-                    const int vi = 2 * (t_run + j) + 1;
-                    const int kn = 2 * (t_run + j) + 2;
-                    const bool more = (j + 1 < n_kv);
-                    mbar_wait(fix_tails ? &v_fixed[slot_of(vi)] : &kv_full[slot_of(vi)], phase_of(vi));
-                    mbar_wait(&p_full[0], static_cast<uint32_t>((cnt0 + j) & 1));
-                    // the first P V of a segment overwrites O: the previous segment's epilogue must have read it
-                    if (j == 0 && sg0 > 0) mbar_wait(&o_empty[0], static_cast<uint32_t>((sg0 - 1) & 1));
-                    tc_fence_after();
-                    issue_pv(0, slot_of(vi), j > 0);
-                    if (more) {
-                        mbar_wait(&kv_full[slot_of(kn)], phase_of(kn));
-                        tc_fence_after();
-                        issue_qk(0, slot_of(kn));
-                        umma_commit(&s_full[0]);
-                    }
-                    if (two) {
-                        mbar_wait(&p_full[1], static_cast<uint32_t>((cnt1 + j) & 1));
-                        if (j == 0 && sg1 > 0) mbar_wait(&o_empty[1], static_cast<uint32_t>((sg1 - 1) & 1));
-                        tc_fence_after();
-                        issue_pv(1, slot_of(vi), j > 0);
-                    }
-                    umma_commit(&kv_empty[slot_of(vi)]);
-                    if (more) {
-                        if (two) {
-                            issue_qk(1, slot_of(kn));
-                            umma_commit(&s_full[1]);
-                        }
-                        umma_commit(&kv_empty[slot_of(kn)]);
-                    }
-                }
-                umma_commit(o_full);
-                umma_commit(q_empty);
-                t_run += n_kv;
-                cnt0 += n_kv;
-                ++sg0;
-                if (two) {
-                    cnt1 += n_kv;
-                    ++sg1;
-                }
-            }
-        }
-      }
-    } else {
-        setmaxnreg_inc<208>();
-        const int w = (warp - 4) >> 2;  // which query tile
-        const int quad = warp & 3;      // TMEM lane quadrant
-        const uint32_t lane_sel = static_cast<uint32_t>(quad * 32) << 16;
-        const uint32_t tmem_base = tmem_base_of();
-        const uint32_t tS_row = tmem_base + static_cast<uint32_t>(w) * 128u + lane_sel;
-        const uint32_t tO_row = tmem_base + 256u + static_cast<uint32_t>(w) * 128u + lane_sel;
-        const float sl2 = p.scale_log2;
-        int t_run = 0;   // tiles of all segments so far (tile_valid ring)
-        int cnt = 0;     // tiles this query tile has processed (s_full / p_full phases)
-        for (int si = 0; si < nseg; ++si) {
-            const int item = segs[si].item;
-            const int n_kv = segs[si].r0_count + segs[si].r1_count;
-            const int piece = segs[si].slot;
-            const int head = item / p.num_q_pairs;
-            const int q0 = (item % p.num_q_pairs) * (2 * kQT);
-            const bool two = q0 + kQT < p.q_rows;
-            if (w == 0 || two) {
-                const int row_in_pair = w * kQT + quad * 32 + lane;
-                const int row = q0 + row_in_pair;
-
-                float m_used = -INFINITY;  // max (raw score units) the probabilities are currently referenced to
-                float l = 0.f;
-                for (int j = 0; j < n_kv; ++j) {
-                    mbar_wait(&s_full[w], static_cast<uint32_t>((cnt + j) & 1));
-                    tc_fence_after();
-                    uint32_t s[4][32];
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) tmem_ld32(tS_row + c * 32, s[c]);
-                    tmem_wait_ld();
-                    const int valid = tile_valid[(t_run + j) & 7];
-                    if (valid < kKT) {
-#pragma unroll
-                        for (int c = 0; c < 4; ++c)
-#pragma unroll
-                            for (int i = 0; i < 32; ++i)
-                                if (c * 32 + i >= valid) s[c][i] = __float_as_uint(-INFINITY);
-                    }
-                    float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll
-                    for (int c = 0; c < 4; ++c)
-#pragma unroll
-                        for (int i = 0; i < 32; i += 4) {
-                            mx0 = fmaxf(mx0, __uint_as_float(s[c][i]));
-                            mx1 = fmaxf(mx1, __uint_as_float(s[c][i + 1]));
-                            mx2 = fmaxf(mx2, __uint_as_float(s[c][i + 2]));
-                            mx3 = fmaxf(mx3, __uint_as_float(s[c][i + 3]));
-                        }
-                    const float m_new = fmaxf(fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)), m_used);
-                    if (j == 0) {
-                        m_used = m_new;
-                    } else {
-                        const bool need = (m_new - m_used) * sl2 > kRescaleThreshold;
-                        if (__any_sync(0xffffffffu, need)) {
-                            // whole warp rescales (tcgen05.ld/st are warp-collective); rows that did not need it use
-                            // their exact (possibly tiny) correction as well, which keeps every row consistent.
-                            const float alpha = ex2_approx((m_used - m_new) * sl2);
-                            m_used = m_new;
-                            l *= alpha;
-#pragma unroll
-                            for (int c = 0; c < 4; ++c) {
-                                uint32_t o[32];
-                                tmem_ld32(tO_row + c * 32, o);
-                                tmem_wait_ld();
-#pragma unroll
-                                for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                                tmem_st32(tO_row + c * 32, o);
-                            }
-                        }
-                    }
-                    const float ms = m_used * sl2;
-                    float l0 = 0.f, l1 = 0.f;
-                    uint32_t pk[2][32];
-#pragma unroll
-                    for (int c = 0; c < 4; ++c)
-#pragma unroll
-                        for (int i = 0; i < 32; i += 2) {
-                            const float x0 = fmaf(__uint_as_float(s[c][i]), sl2, -ms);
-                            const float x1 = fmaf(__uint_as_float(s[c][i + 1]), sl2, -ms);
-                            // every kPolyEvery-th pair takes the FMA-pipe polynomial instead of MUFU.EX2
-                            const bool poly = kPolyEvery > 0 && ((i >> 1) % (kPolyEvery > 0 ? kPolyEvery : 1)) == kPolyEvery - 1;
-                            const float p0 = poly ? ex2_poly(x0) : ex2_approx(x0);
-                            const float p1 = poly ? ex2_poly(x1) : ex2_approx(x1);
-                            l0 += p0;
-                            l1 += p1;
-                            pk[c >> 1][(c & 1) * 16 + (i >> 1)] = pack_bf16x2(p0, p1);
-                        }
-                    l += l0 + l1;
-                    tmem_st32(tS_row, pk[0]);
-                    tmem_st32(tS_row + 32, pk[1]);
-                    tmem_wait_st();
-                    tc_fence_before();
-                    mbar_arrive(&p_full[w]);
-                }
-
-                mbar_wait(o_full, static_cast<uint32_t>(si & 1));
-                tc_fence_after();
-                if (piece < 0) {
-                    // epilogue: O / l -> bf16 -> global
-                    const float inv_l = 1.0f / l;
-                    if (p.lse != nullptr && row < p.q_rows)
-                        p.lse[static_cast<int64_t>(head) * p.q_rows + row] = (m_used * sl2 + log2f(l)) * 0.6931471805599453f;
-                    __nv_bfloat16* optr = p.out + static_cast<int64_t>(row) * p.ldo + head * kHD;
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        uint32_t o[32];
-                        tmem_ld32(tO_row + c * 32, o);
-                        tmem_wait_ld();
-                        if (row < p.q_rows) {
-#pragma unroll
-                            for (int v = 0; v < 4; ++v) {
-                                uint4 pkt;
-                                pkt.x = pack_bf16x2(__uint_as_float(o[v * 8 + 0]) * inv_l, __uint_as_float(o[v * 8 + 1]) * inv_l);
-                                pkt.y = pack_bf16x2(__uint_as_float(o[v * 8 + 2]) * inv_l, __uint_as_float(o[v * 8 + 3]) * inv_l);
-                                pkt.z = pack_bf16x2(__uint_as_float(o[v * 8 + 4]) * inv_l, __uint_as_float(o[v * 8 + 5]) * inv_l);
-                                pkt.w = pack_bf16x2(__uint_as_float(o[v * 8 + 6]) * inv_l, __uint_as_float(o[v * 8 + 7]) * inv_l);
-                                *reinterpret_cast<uint4*>(optr + c * 32 + v * 8) = pkt;
-                            }
-                        }
-                    }
-                } else {
-                    // partial: un-normalised O, reference max (log2 units) and sum
-                    float* po = p.part_o + (static_cast<int64_t>(piece) * (2 * kQT) + row_in_pair) * kHD;
-                    float* pml = p.part_ml + (static_cast<int64_t>(piece) * (2 * kQT) + row_in_pair) * 2;
-                    pml[0] = m_used * sl2;
-                    pml[1] = l;
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        uint32_t o[32];
-                        tmem_ld32(tO_row + c * 32, o);
-                        tmem_wait_ld();
-#pragma unroll
-                        for (int v = 0; v < 8; ++v)
-                            *reinterpret_cast<uint4*>(po + c * 32 + v * 4) = make_uint4(o[v * 4], o[v * 4 + 1], o[v * 4 + 2], o[v * 4 + 3]);
-                    }
-                }
-                // O has been read: the next segment's first P V may overwrite it
-                tc_fence_before();
-                mbar_arrive(&o_empty[w]);
-                cnt += n_kv;
-            }
-            t_run += n_kv;
-        }
-    }
-
-    tc_fence_before();
-    __syncthreads();
-    griddep_launch();
-    if (warp == 2) {
-        tc_fence_after();
-        tmem_dealloc<512>(tmem_base_of());
-    }
-}
-
 // Merge the key-range pieces of the split items: one warp per query row, lane owns 4 of the 128 dims.
 __global__ void __launch_bounds__(256)
 attn_combine_kernel(const AttnParams p) {
@@ -1007,26 +558,17 @@ attn_combine_kernel(const AttnParams p) {
     const int gw = blockIdx.x * 8 + warp;  // (split item, row in pair)
     const int sitem = gw / (2 * kQT);
     const int r = gw % (2 * kQT);
-    int item, slot0, nslots;
-    if (p.comb_items != nullptr) {         // planned schedule: the item's partial slots are listed
-        item = p.comb_items[sitem].item;
-        slot0 = p.comb_items[sitem].slot0;
-        nslots = p.comb_items[sitem].nslots;
-    } else {                               // analytic schedule: `split` pieces per item of the tail wave
-        item = p.n_whole + sitem;
-        slot0 = sitem * p.split;
-        nslots = p.split;
-    }
+    const int item = p.n_whole + sitem;
     const int head = item / p.num_q_pairs;
     const int row = (item % p.num_q_pairs) * (2 * kQT) + r;
     if (row >= p.q_rows) return;
     float m = -INFINITY;
-    for (int s = 0; s < nslots; ++s)
-        m = fmaxf(m, p.part_ml[(static_cast<int64_t>(slot0 + s) * (2 * kQT) + r) * 2]);
+    for (int s = 0; s < p.split; ++s)
+        m = fmaxf(m, p.part_ml[((static_cast<int64_t>(sitem) * p.split + s) * (2 * kQT) + r) * 2]);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     float l = 0.f;
-    for (int s = 0; s < nslots; ++s) {
-        const int64_t base = static_cast<int64_t>(slot0 + s) * (2 * kQT) + r;
+    for (int s = 0; s < p.split; ++s) {
+        const int64_t base = (static_cast<int64_t>(sitem) * p.split + s) * (2 * kQT) + r;
         const float a = ex2_approx(p.part_ml[base * 2] - m);
         l += p.part_ml[base * 2 + 1] * a;
         const float4 o = *reinterpret_cast<const float4*>(p.part_o + base * kHD + lane * 4);
@@ -1042,215 +584,6 @@ attn_combine_kernel(const AttnParams p) {
     pkt.x = pack_bf16x2(acc.x * inv, acc.y * inv);
     pkt.y = pack_bf16x2(acc.z * inv, acc.w * inv);
     *reinterpret_cast<uint2*>(p.out + static_cast<int64_t>(row) * p.ldo + head * kHD + lane * 4) = pkt;
-}
-
-// ---------------------------------------------------------------------------------------------- slack-fill schedule
-// The plain schedule gives every (item, key piece) its own CTA, all starting at the same key tiles — which is what
-// keeps the CTAs of one head in lock-step and the K / V tiles shared through L2.  On the sequence-parallel shard shapes
-// it leaves SMs under-used: 8 ranks = 120 two-tile pieces + 24 cheaper single-tile pieces on 148 SMs; 4 ranks = 132
-// pieces on 148 SMs.  (Cutting ALL work into equal shares was tried and lost: pieces of one head drift apart, K / V is
-// re-read from HBM per row pair — profiles/r02d_sp_shape_planned_schedule.jsonl.)  Slack fill keeps the lock-step bulk
-// and moves only the excess: every piece that costs more than the mean sheds its LAST tiles as a small extra segment,
-// and the under-loaded CTAs (single-tile pieces, idle SMs) run those after their own piece.  Built on the host, once
-// per shape; segments of an item are merged by attn_combine_kernel.
-struct PlanKey {
-    int q_rows, heads, n_tiles, n_old_tiles, sms;
-    bool operator==(const PlanKey& o) const {
-        return q_rows == o.q_rows && heads == o.heads && n_tiles == o.n_tiles && n_old_tiles == o.n_old_tiles && sms == o.sms;
-    }
-};
-struct HostPlan {
-    int grid = 0, n_slots = 0;
-    std::vector<AttnSeg> segs;          // [grid][kMaxSeg]
-    std::vector<int32_t> counts;        // [grid]
-    std::vector<CombineItem> comb;
-    double base_makespan = 0.0, makespan = 0.0, total = 0.0;   // in two-tile key-tile units
-};
-// cost of one key tile of a single-tile item relative to a two-tile (ping-pong) item
-constexpr double kSingleTileCost = 0.62;
-constexpr int kMinShed = 8;             // do not move fewer key tiles than this
-
-// host mirror of make_tile_range
-static void host_tile_range(int n_all, int n_old, int sub, int n, int& ob, int& no, int& nb, int& nn) {
-    const int n_new = n_all - n_old;
-    ob = static_cast<int>(static_cast<int64_t>(n_old) * sub / n);
-    no = static_cast<int>(static_cast<int64_t>(n_old) * (sub + 1) / n) - ob;
-    nb = n_old + static_cast<int>(static_cast<int64_t>(n_new) * sub / n);
-    nn = n_old + static_cast<int>(static_cast<int64_t>(n_new) * (sub + 1) / n) - nb;
-}
-
-// keep the first `keep` tiles of the sequence r0 ++ r1 in `head`, the rest in `tail`
-static void split_seq(const AttnSeg& sg, int keep, AttnSeg& head, AttnSeg& tail) {
-    head = tail = sg;
-    if (keep <= sg.r0_count) {
-        head.r0_count = keep;
-        head.r1_count = 0;
-        tail.r0_begin = sg.r0_begin + keep;
-        tail.r0_count = sg.r0_count - keep;
-    } else {
-        head.r1_count = keep - sg.r0_count;
-        tail.r0_begin = sg.r1_begin + head.r1_count;
-        tail.r0_count = sg.r1_count - head.r1_count;
-        tail.r1_begin = tail.r0_begin + tail.r0_count;
-        tail.r1_count = 0;
-    }
-    if (tail.r0_count == 0 && tail.r1_count > 0) {      // normalise: r0 is never empty when r1 is not
-        tail.r0_begin = tail.r1_begin;
-        tail.r0_count = tail.r1_count;
-        tail.r1_count = 0;
-    }
-}
-
-// Returns false when the shape does not qualify (more pieces than SMs, nothing to gain, segment limit).
-bool plan_slack_fill(int q_rows, int heads, int n_tiles, int n_old_tiles, int sms, int split, HostPlan& out) {
-    const int pairs = (q_rows + 2 * kQT - 1) / (2 * kQT);
-    const int items = pairs * heads;
-    if (split < 1 || items * split > sms || n_tiles < 8 * kMinShed) return false;
-    auto unit = [&](int item) { return ((item % pairs) * 2 * kQT + kQT < q_rows) ? 1.0 : kSingleTileCost; };
-    struct Cta {
-        std::vector<AttnSeg> segs;
-        double cost = 0.0;
-    };
-    std::vector<Cta> cta(sms);
-    int n_base = 0;
-    double total = 0.0, base_makespan = 0.0;
-    for (int it = 0; it < items; ++it)
-        for (int sub = 0; sub < split; ++sub) {
-            AttnSeg sg;
-            sg.item = it;
-            sg.slot = -1;
-            host_tile_range(n_tiles, n_old_tiles, sub, split, sg.r0_begin, sg.r0_count, sg.r1_begin, sg.r1_count);
-            if (sg.r0_count == 0) {
-                sg.r0_begin = sg.r1_begin;
-                sg.r0_count = sg.r1_count;
-                sg.r1_count = 0;
-            }
-            Cta& c = cta[n_base++];
-            c.segs.push_back(sg);
-            c.cost = (sg.r0_count + sg.r1_count) * unit(it);
-            total += c.cost;
-            base_makespan = std::max(base_makespan, c.cost);
-        }
-    const double mean = total / sms;
-    if (base_makespan < 1.04 * mean) return false;          // already balanced
-    // shed the excess of every piece above the target, largest chunks first to the emptiest CTA
-    double target = mean * 1.01;
-    for (int attempt = 0; attempt < 12; ++attempt, target *= 1.01) {
-        std::vector<Cta> w = cta;
-        struct Chunk {
-            AttnSeg seg;
-            double cost;
-        };
-        std::vector<Chunk> chunks;
-        for (int b = 0; b < n_base; ++b) {
-            const AttnSeg sg = w[b].segs[0];
-            const double u = unit(sg.item);
-            const int n = sg.r0_count + sg.r1_count;
-            int shed = static_cast<int>(std::ceil((w[b].cost - target) / u));
-            if (shed < kMinShed) continue;
-            if (n - shed < kMinShed) shed = n - kMinShed;
-            if (shed < kMinShed) continue;
-            AttnSeg head, tail;
-            split_seq(sg, n - shed, head, tail);
-            w[b].segs[0] = head;
-            w[b].cost -= shed * u;
-            chunks.push_back(Chunk{tail, shed * u});
-        }
-        std::sort(chunks.begin(), chunks.end(), [](const Chunk& a, const Chunk& b) { return a.cost > b.cost; });
-        bool ok = true;
-        for (const Chunk& ch : chunks) {
-            int best = -1;
-            for (int b = 0; b < sms; ++b) {
-                if (static_cast<int>(w[b].segs.size()) >= kMaxSeg) continue;
-                if (w[b].cost + ch.cost > target + 1e-9) continue;
-                if (best < 0 || w[b].cost < w[best].cost) best = b;
-            }
-            if (best < 0) {
-                ok = false;
-                break;
-            }
-            w[best].segs.push_back(ch.seg);
-            w[best].cost += ch.cost;
-        }
-        if (!ok) continue;
-        // compact: drop CTAs without work, number the partial slots item by item
-        std::vector<std::vector<std::pair<int, int>>> by_item(items);   // (cta, seg index)
-        int grid = 0;
-        std::vector<int> remap(sms, -1);
-        for (int b = 0; b < sms; ++b)
-            if (!w[b].segs.empty()) remap[b] = grid++;
-        out = HostPlan{};
-        out.grid = grid;
-        out.segs.assign(static_cast<size_t>(grid) * kMaxSeg, AttnSeg{0, 0, 0, 0, 0, -1});
-        out.counts.assign(grid, 0);
-        double makespan = 0.0;
-        for (int b = 0; b < sms; ++b) {
-            if (remap[b] < 0) continue;
-            makespan = std::max(makespan, w[b].cost);
-            out.counts[remap[b]] = static_cast<int32_t>(w[b].segs.size());
-            for (size_t i = 0; i < w[b].segs.size(); ++i) {
-                out.segs[static_cast<size_t>(remap[b]) * kMaxSeg + i] = w[b].segs[i];
-                by_item[w[b].segs[i].item].push_back({remap[b], static_cast<int>(i)});
-            }
-        }
-        int slot = 0;
-        for (int it = 0; it < items; ++it) {
-            if (by_item[it].size() == 1) continue;           // one segment covers the item: direct output (slot -1)
-            out.comb.push_back(CombineItem{it, slot, static_cast<int32_t>(by_item[it].size())});
-            for (auto& cs : by_item[it]) out.segs[static_cast<size_t>(cs.first) * kMaxSeg + cs.second].slot = slot++;
-        }
-        out.n_slots = slot;
-        out.base_makespan = base_makespan;
-        out.makespan = makespan;
-        out.total = total;
-        return makespan < 0.97 * base_makespan;
-    }
-    return false;
-}
-
-struct DevicePlan {
-    PlanKey key;
-    int dev, split;
-    int grid, n_comb, n_slots;
-    AttnSeg* segs;
-    int32_t* counts;
-    CombineItem* comb;
-};
-static std::vector<DevicePlan> g_plans;
-
-// Looks the shape up in the per-process plan cache; builds + uploads it on first use.  nullptr: plain schedule.
-static const DevicePlan* get_plan(int q_rows, int heads, int n_tiles, int n_old_tiles, int sms, int split) {
-    static const bool enabled = [] {
-        const char* e = getenv("IFX_ATTN_SLACK_FILL");
-        return e == nullptr || e[0] != '0';
-    }();
-    if (!enabled) return nullptr;
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
-    const PlanKey key{q_rows, heads, n_tiles, n_old_tiles, sms};
-    for (const DevicePlan& d : g_plans)
-        if (d.dev == dev && d.split == split && d.key == key) return d.grid > 0 ? &d : nullptr;
-    DevicePlan d{};
-    d.key = key;
-    d.dev = dev;
-    d.split = split;
-    HostPlan hp;
-    if (g_plans.size() < 512 && plan_slack_fill(q_rows, heads, n_tiles, n_old_tiles, sms, split, hp)) {
-        bool ok = cudaMalloc(&d.segs, hp.segs.size() * sizeof(AttnSeg)) == cudaSuccess &&
-                  cudaMalloc(&d.counts, hp.counts.size() * sizeof(int32_t)) == cudaSuccess &&
-                  cudaMalloc(&d.comb, std::max<size_t>(1, hp.comb.size()) * sizeof(CombineItem)) == cudaSuccess;
-        ok = ok && cudaMemcpy(d.segs, hp.segs.data(), hp.segs.size() * sizeof(AttnSeg), cudaMemcpyHostToDevice) == cudaSuccess &&
-             cudaMemcpy(d.counts, hp.counts.data(), hp.counts.size() * sizeof(int32_t), cudaMemcpyHostToDevice) == cudaSuccess &&
-             (hp.comb.empty() || cudaMemcpy(d.comb, hp.comb.data(), hp.comb.size() * sizeof(CombineItem),
-                                            cudaMemcpyHostToDevice) == cudaSuccess);
-        if (ok) {
-            d.grid = hp.grid;
-            d.n_comb = static_cast<int>(hp.comb.size());
-            d.n_slots = hp.n_slots;
-        }
-    }
-    g_plans.push_back(d);       // grid == 0 records "plain schedule for this shape"
-    return g_plans.back().grid > 0 ? &g_plans.back() : nullptr;
 }
 
 // Which key rows a launch attends, and (sequence parallel) which of them are still in flight from the peers.
@@ -1285,10 +618,6 @@ static void fill_defaults(AttnParams& p) {
     p.wait_timeout_ns = 0;
     p.no_dep_wait = 0;
     p.push = PeerPushParams{};
-    p.seg_table = nullptr;
-    p.seg_count = nullptr;
-    p.comb_items = nullptr;
-    p.n_comb = 0;
 }
 
 // returns the total number of key tiles
@@ -1328,16 +657,6 @@ static ifx_status launch_attn_kernel(int grid, const CUtensorMap& tmQ, const CUt
     // IFX_PDL=0 the launch is an ordinary one (stream order), which is still correct — only the overlap is lost.
     AttnParams pp = p;
     pp.no_dep_wait = overlap_prev ? 1 : 0;
-    if (p.seg_table != nullptr) {
-        static uint64_t configured_multi = 0;
-        if (dev >= 64 || !(configured_multi & (1ull << dev))) {
-            IFX_CUDA_OK(cudaFuncSetAttribute(attn_fwd_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
-            if (dev < 64) configured_multi |= 1ull << dev;
-        }
-        IFX_CUDA_OK(launch_kernel(attn_fwd_multi_kernel, dim3(static_cast<unsigned>(grid)), dim3(kAttnThreads), kAttnSmem,
-                                  stream, true, tmQ, tmK, tmV, pp));
-        return IFX_OK;
-    }
     IFX_CUDA_OK(launch_kernel(attn_fwd_kernel, dim3(static_cast<unsigned>(grid)), dim3(kAttnThreads), kAttnSmem, stream,
                               true, tmQ, tmK, tmV, pp));
     return IFX_OK;
@@ -1415,22 +734,7 @@ static ifx_status attention_launch(const void* q, int64_t ldq, const void* k, co
     if (split == 1) rem = 0;
     p.n_whole = items - rem;
     p.split = split;
-    int pieces = rem * split;
-    int n_comb = rem;                       // items merged by the combine kernel
-    int planned_grid = 0;
-    // single-wave shapes (all pieces resident at once): move the excess of the busy CTAs to the idle ones
-    const DevicePlan* plan = (items * split <= sms && (rem == 0 || rem == items))
-                                 ? get_plan(p.q_rows, heads, n_kv, p.wait_flags ? p.n_old_tiles : n_kv, sms, split)
-                                 : nullptr;
-    if (plan != nullptr) {
-        p.seg_table = plan->segs;
-        p.seg_count = plan->counts;
-        p.comb_items = plan->comb;
-        p.n_comb = plan->n_comb;
-        pieces = plan->n_slots;
-        n_comb = plan->n_comb;
-        planned_grid = plan->grid;
-    }
+    const int pieces = rem * split;
     if (pieces > 0) {
         int dev = 0;
         IFX_CUDA_OK(cudaGetDevice(&dev));
@@ -1447,7 +751,7 @@ static ifx_status attention_launch(const void* q, int64_t ldq, const void* k, co
         p.part_o = sc.ptr;
         p.part_ml = sc.ptr + static_cast<size_t>(pieces) * (2 * kQT) * kHD;
     }
-    const int grid = planned_grid > 0 ? planned_grid : p.n_whole + pieces;
+    const int grid = p.n_whole + pieces;
     if (keys != nullptr && keys->push != nullptr) {
         // The CTAs that carry a slice of the exchange must all be resident before any CTA can be blocked on the peers'
         // flags: keep them inside the first wave (lowest block indices are dispatched first) with some margin.
@@ -1475,11 +779,11 @@ static ifx_status attention_launch(const void* q, int64_t ldq, const void* k, co
         ProfScope prof(label, stream);
         st = launch_attn_kernel(grid, tmQ, tmK, tmV, p, keys != nullptr && keys->pdl, stream);
         if (st != IFX_OK) return st;
-        if (n_comb > 0)
-            IFX_CUDA_OK(launch_kernel(attn_combine_kernel, dim3(n_comb * (2 * kQT) / 8), dim3(256), 0, stream, true, p));
+        if (pieces > 0)
+            IFX_CUDA_OK(launch_kernel(attn_combine_kernel, dim3(rem * (2 * kQT) / 8), dim3(256), 0, stream, true, p));
     }
     IFX_LAUNCH_OK("attn_fwd_kernel");
-    if (n_comb > 0) count_launch();
+    if (pieces > 0) count_launch();
     return IFX_OK;
 }
 
@@ -1593,50 +897,6 @@ extern "C" ifx_status ifx_attention_partial(const void* q, int64_t ldq, const vo
         if (st != IFX_OK) return st;
     }
     IFX_LAUNCH_OK("attn_fwd_kernel<partial>");
-    return IFX_OK;
-}
-
-extern "C" ifx_status ifx_attention_plan_info(int32_t q_rows, int32_t heads, int32_t n_tiles, int32_t n_old_tiles,
-                                              int32_t sms, int32_t* grid, double* makespan, double* base_makespan,
-                                              double* mean_cost, int32_t* segments, int32_t segments_cap) {
-    IFX_CHECK_ARG(q_rows > 0 && heads > 0 && n_tiles > 0 && n_old_tiles >= 0 && n_old_tiles <= n_tiles && sms > 0,
-                  "ifx_attention_plan_info: bad shape");
-    IFX_CHECK_ARG(grid && makespan && base_makespan && mean_cost, "ifx_attention_plan_info: null pointer");
-    const int pairs = (q_rows + 2 * kQT - 1) / (2 * kQT);
-    const int items = pairs * heads;
-    int rem = items % sms, split = 1;
-    if (rem != 0 && n_tiles >= 2 * kMaxSplit) {
-        double best = 1.0;
-        for (int s = 2; s <= kMaxSplit; ++s) {
-            const double cost = static_cast<double>((rem * s + sms - 1) / sms) / s;
-            if (cost < best - 1e-9) {
-                best = cost;
-                split = s;
-            }
-        }
-    }
-    HostPlan hp;
-    *grid = 0;
-    *makespan = *base_makespan = *mean_cost = 0.0;
-    if (!(items * split <= sms && (split == 1 || rem == items)) ||
-        !plan_slack_fill(q_rows, heads, n_tiles, n_old_tiles, sms, split, hp))
-        return IFX_OK;
-    *grid = hp.grid;
-    *makespan = hp.makespan;
-    *base_makespan = hp.base_makespan;
-    *mean_cost = hp.total / sms;
-    if (segments != nullptr) {
-        int n = 0;
-        for (int b = 0; b < hp.grid; ++b)
-            for (int i = 0; i < hp.counts[b]; ++i) {
-                IFX_CHECK_ARG(n < segments_cap, "ifx_attention_plan_info: segments_cap too small");
-                const AttnSeg& sg = hp.segs[static_cast<size_t>(b) * kMaxSeg + i];
-                int32_t* o = segments + 7 * n++;
-                o[0] = b; o[1] = sg.item; o[2] = sg.r0_begin; o[3] = sg.r0_count; o[4] = sg.r1_begin; o[5] = sg.r1_count;
-                o[6] = sg.slot;
-            }
-        if (n < segments_cap) segments[7 * n] = -1;
-    }
     return IFX_OK;
 }
 

@@ -476,7 +476,7 @@ ifx_status ifx_wan_block_forward(const ifx_wan_block_weights* w, const ifx_wan_b
  *   mode IFX_SP_STORE   : the norm + RoPE kernel stores K / V into every rank's cache, ifx_peer_wait, attention.
  *   mode IFX_SP_OVERLAP : the norm + RoPE kernel writes the local cache only; the ATTENTION KERNEL itself performs the
  *                         exchange: an otherwise idle warp of each of its first CTAs (at most `push_ctas`, 0 = default
- *                         7/8 of the SMs) copies a slice of this rank's new rows to the same cache rows of every peer
+ *                         32) copies a slice of this rank's new rows to the same cache rows of every peer
  *                         over NVLink and the last one publishes the epoch, while the MMA / softmax warps attend the
  *                         cached pages; every CTA acquires the peers' epoch flags only before its first fresh-page tile
  *                         (ifx_attention_kv_wait).  Compute and collective are one kernel; the exchange costs no SM and

@@ -238,7 +238,8 @@ typedef struct ifx_peer_dst {
     int64_t* flags[IFX_MAX_PEERS];   /* every rank's flag array, int64[world]; this rank writes element `rank` */
     int64_t epoch;                   /* > 0, increases by one per call, identical on all ranks */
     int32_t local_only;              /* ifx_qk_norm_rope_append_peers: 1 = write this rank's cache only and publish  */
-                                     /* nothing; ifx_peer_push performs the exchange (overlap variant)               */
+                                     /* nothing (the exchange then happens in ifx_peer_push or, in the shipped path,  */
+                                     /* inside the attention kernel of ifx_wan_block_forward_sp / IFX_SP_OVERLAP)     */
 } ifx_peer_dst;
 
 /* CUDA IPC: handle of the allocation containing ptr (+ ptr's offset inside it), to be shipped to the other processes
@@ -258,7 +259,9 @@ ifx_status ifx_qk_norm_rope_append_peers(const void* qkv, int64_t ld_qkv, const 
 /* Exchange half of ifx_qk_norm_rope_append_peers as its own small grid (`ctas` CTAs of 1024 threads): copies this rank's
  * rows of the block's new pages from its cache to every other rank's cache and publishes `peers->epoch`.  Meant for a
  * side stream, next to the attention over the pages that were already cached (which needs no new K / V); the
- * attention over the new pages then follows an ifx_peer_wait.  Experimental: built, not yet measured. */
+ * attention over the new pages then follows an ifx_peer_wait.  A/B variant only: measured at 106 GB/s on the SMs the
+ * attention leaves free (8 CTAs) and it delays the attention's tail, so the shipped path copies from inside the
+ * attention kernel instead (IFX_SP_OVERLAP below). */
 ifx_status ifx_peer_push(ifx_kv* kv, const ifx_kv_plan* plan, const ifx_peer_dst* peers, int32_t frames, int32_t chunk,
                          int32_t ctas, void* stream);
 /* Stream-ordered wait until flags[s] >= epoch for every s < world; traps after timeout_ms instead of hanging. */

@@ -420,40 +420,10 @@ class CausalWanAttentionBlock(nn.Module):
             # attention is ordered after all ranks' epoch flags (inferix_b200/peer.py) — no collective in the layer
             pg = store.peer_group
             peer_dst.epoch = pg.next_epoch()
-            old_ext, new_ext = store.split_extents(plan) if _SP_PUSH_OVERLAP else ((), ())
-            if _SP_PUSH_OVERLAP and 1 <= len(old_ext) <= 4 and 1 <= len(new_ext) <= 4:
-                # EXPERIMENTAL (IFX_SP_PUSH_OVERLAP=1; built, not yet measured): the kernel writes this rank's cache
-                # only; a 4-CTA push grid on a side stream ships the rows to the peers while the local queries attend
-                # the pages that were already cached (phase 1 leaves >= 4 SMs free at 4-8 ranks), then the new pages
-                # (phase 2, after every rank's epoch flag), merged by attn_combine_kernel
-                peer_dst.local_only = 1
-                ops.qk_norm_rope_append_peers(ws.qkv, sa.norm_q.weight, sa.norm_k.weight, freqs, grid, heads, hd,
-                                              store, plan, peer_dst, q_out=ws.q, eps=self.eps)
-                peer_dst.local_only = 0
-                main, side = torch.cuda.current_stream(), ws.side_stream
-                ready = torch.cuda.Event()
-                ready.record(main)
-                with torch.cuda.stream(side):
-                    side.wait_event(ready)
-                    ops.peer_push(store, plan, peer_dst, frames, rows // frames, ctas=4)
-                    pushed = torch.cuda.Event()
-                    pushed.record(side)
-                items = heads * ((rows + 255) // 256)
-                old_tiles = sum((n + 127) // 128 for _, n in old_ext)
-                new_tiles = sum((n + 127) // 128 for _, n in new_ext)
-                n_old = min(8, old_tiles, max(1, (ws.sm_count - 4) // items))
-                n_new = min(8, new_tiles, max(1, ws.sm_count // items))
-                part = ws.partials(rows, heads, n_old + n_new)
-                ops.attention_partial(ws.q, store.k, store.v, old_ext, heads, part, n_old + n_new, 0, n_old)
-                pg.wait(peer_dst.epoch)
-                main.wait_event(pushed)          # this rank's push has read its rows before anything rewrites them
-                ops.attention_partial(ws.q, store.k, store.v, new_ext, heads, part, n_old + n_new, n_old, n_new)
-                ops.attention_combine(part, n_old + n_new, ws.attn, heads)
-            else:
-                ops.qk_norm_rope_append_peers(ws.qkv, sa.norm_q.weight, sa.norm_k.weight, freqs, grid, heads, hd,
-                                              store, plan, peer_dst, q_out=ws.q, eps=self.eps)
-                pg.wait(peer_dst.epoch)
-                store.attention(ws.q, ws.attn)
+            ops.qk_norm_rope_append_peers(ws.qkv, sa.norm_q.weight, sa.norm_k.weight, freqs, grid, heads, hd,
+                                          store, plan, peer_dst, q_out=ws.q, eps=self.eps)
+            pg.wait(peer_dst.epoch)
+            store.attention(ws.q, ws.attn)
         elif world > 1:
             ops.qk_norm_rope_append(ws.qkv, sa.norm_q.weight, sa.norm_k.weight, freqs, grid, heads, hd, q_out=ws.q,
                                     k_out=ws.kv_new[0], v_out=ws.kv_new[1], eps=self.eps)
@@ -510,11 +480,13 @@ class CausalWanAttentionBlock(nn.Module):
 _SP_MODE = __import__("os").environ.get("IFX_SP_MODE", "overlap")
 if _SP_MODE not in ("overlap", "store", "ops"):
     raise ValueError(f"IFX_SP_MODE={_SP_MODE!r}: expected overlap, store or ops")
-# measured on B200 boxes (profiles/r02*_sp*): 8 ranks 988 ms / block fused vs 1028 ms store + wait; 2 ranks 3266 vs 3216
+# measured on B200 boxes (profiles/r02*_sp*): 8 ranks 966 ms / block fused (32 copy CTAs) vs 1028 ms store + wait;
+# 2 ranks 3266 vs 3216.  A third variant (a separate copy grid on a side stream next to the attention) reached only
+# 106 GB/s on the SMs the attention leaves free and delayed its tail; it was dropped for the in-kernel copy.
 
 
 def _sp_push_ctas(world: int) -> int:
-    """Cap on the attention CTAs that share the fused K/V exchange (0 = the library default, 7/8 of the SMs)."""
+    """Cap on the attention CTAs that share the fused K/V exchange (0 = the library default, 32)."""
     return max(0, int(__import__("os").environ.get("IFX_SP_PUSH_CTAS", "0")))
 
 
@@ -524,9 +496,6 @@ def _sp_push_ctas(world: int) -> int:
 # ~50 us there and the second launch + partial traffic cost more); it targets 4-8 ranks where the gather is 10 % of
 # the layer, which this round could not re-measure.
 _SP_OVERLAP = __import__("os").environ.get("IFX_SP_OVERLAP", "0") == "1"
-# IFX_SP_PUSH_OVERLAP=1: the same idea on the peer-memory path (see the branch in _forward_ops).  Off by default: built
-# at the end of round 1 after the GPU budget was spent, so it has not run on hardware yet.
-_SP_PUSH_OVERLAP = __import__("os").environ.get("IFX_SP_PUSH_OVERLAP", "0") == "1"
 
 
 def _pieces_for(q_rows: int, heads: int, sms: int) -> int:

@@ -9,7 +9,6 @@ echo "=== parity"; timeout 400 python -m pytest tests/test_gpu_sp.py -q 2>&1 | t
 for variant in peer push_overlap nccl; do
   case $variant in
     peer) ENVV="";;
-    push_overlap) ENVV="IFX_SP_PUSH_OVERLAP=1";;
     nccl) ENVV="IFX_SP_PEER=0";;
   esac
   echo "=== bench $variant"

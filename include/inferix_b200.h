@@ -10,7 +10,11 @@
  * Conventions
  *   - activations are bf16, row-major [tokens, channels]; "ld*" arguments are row strides in ELEMENTS
  *   - all kernels are enqueued on the caller's stream; nothing here synchronises the device
- *   - handles are not thread-safe; one host thread drives one GPU (process per GPU)
+ *   - handles are not thread-safe; one host thread drives one GPU (process per GPU).  Library-internal device state
+ *     (opt-in shared-memory attributes, the split-attention partial buffer, arrival counters) is kept PER DEVICE, so a
+ *     process may drive several GPUs in turn; it is not kept per stream: launches that use the split-attention path
+ *     (ifx_attention* with more work items than whole waves of SMs) must be ordered on ONE stream per device, or the
+ *     caller provides the partial buffer itself (ifx_attention_partial + ifx_attention_combine)
  *   - the library is CUDA-only: there is no CPU fallback, calls fail with IFX_ERR_CUDA without a device
  */
 #ifndef INFERIX_B200_H_

@@ -58,16 +58,30 @@ bool pdl_enabled() {
 }
 
 int sm_count() {
-    static int cached = 0;
-    if (cached == 0) {
-        int dev = 0, n = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess &&
-            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-            cached = n;
+    static int cached[64] = {0};       // per device: one process may drive several GPUs (tools/nvlink_probe.py)
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    if (cached[dev] == 0) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+            cached[dev] = n;
         else
-            cached = 148;
+            cached[dev] = 148;
     }
-    return cached;
+    return cached[dev];
+}
+
+// Zero-initialised device counter of the current device, allocated on first use (arrival counters of kernels whose
+// last CTA does something; launches on one device are stream-ordered by the callers).
+ifx_status device_counter(unsigned int* (&slots)[64], unsigned int** out) {
+    int dev = 0;
+    IFX_CUDA_OK(cudaGetDevice(&dev));
+    IFX_CHECK_ARG(dev >= 0 && dev < 64, "device index %d beyond 63", dev);
+    if (!slots[dev]) {
+        IFX_CUDA_OK(cudaMalloc(&slots[dev], sizeof(unsigned int)));
+        IFX_CUDA_OK(cudaMemset(slots[dev], 0, sizeof(unsigned int)));
+    }
+    *out = slots[dev];
+    return IFX_OK;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -172,13 +186,14 @@ extern "C" ifx_status ifx_prof_labels(char* buf, int32_t cap) {
     return IFX_OK;
 }
 
-#define IFX_TRY(expr)                     \
-    do {                                  \
-        ifx_status _s = (expr);           \
-        if (_s != IFX_OK) return _s;      \
-    } while (0)
-
 // Shared body of the single-GPU and the sequence-parallel block.  peers == nullptr: single GPU.
+static ifx_status wan_block_launches(const ifx_wan_block_weights* w, const ifx_wan_block_io* io,
+                                     const ifx_peer_dst* peers, int32_t sp_mode, int32_t push_ctas, int32_t timeout_ms,
+                                     const ifx_kv_plan& plan, void* stream);
+
+// Validates, plans the append (host integers only), launches the layer.  The plan advances the cache's block table and
+// end indices before anything runs on the device; if a launch is then refused (bad pointer alignment, launch failure)
+// the table and indices are put back, so a caught error leaves the native cache where kv_cache_meta still says it is.
 static ifx_status wan_block_forward_impl(const ifx_wan_block_weights* w, const ifx_wan_block_io* io,
                                          const ifx_peer_dst* peers, int32_t sp_mode, int32_t push_ctas,
                                          int32_t timeout_ms, ifx_kv_plan* plan_out, void* stream) {
@@ -190,7 +205,6 @@ static ifx_status wan_block_forward_impl(const ifx_wan_block_weights* w, const i
     IFX_CHECK_ARG(w->dim == w->heads * w->head_dim, "ifx_wan_block_forward: dim != heads*head_dim");
     if (!w->norm3_w || !w->norm3_b)
         return set_error(IFX_ERR_UNSUPPORTED, "ifx_wan_block_forward: cross_attn_norm=False is not built");
-    const int C = w->dim, F = w->ffn_dim;
     const int64_t S = io->rows, fs = io->tokens_per_frame;
     IFX_CHECK_ARG(S > 0 && fs > 0 && S % fs == 0, "ifx_wan_block_forward: rows must be whole frames");
     const int world = peers ? peers->world : 1;
@@ -201,15 +215,32 @@ static ifx_status wan_block_forward_impl(const ifx_wan_block_weights* w, const i
         IFX_CHECK_ARG(timeout_ms > 0 && push_ctas >= 0, "ifx_wan_block_forward_sp: timeout_ms must be positive");
         IFX_CHECK_ARG(peers->flags[peers->rank] != nullptr, "ifx_wan_block_forward_sp: null flag array");
     }
+    KvImpl* kv = kv_cast(io->kv);
+    if (!kv) return set_error(IFX_ERR_HANDLE, "ifx_wan_block_forward: bad kv handle");
+    const KvImpl before = *kv;
+    ifx_kv_plan plan;
+    IFX_TRY(ifx_kv_plan_append(io->kv, io->current_start, S * world, io->sink_tokens, io->windowed, &plan));
+    const ifx_status st = wan_block_launches(w, io, peers, sp_mode, push_ctas, timeout_ms, plan, stream);
+    if (st != IFX_OK) {
+        *kv = before;
+        return st;
+    }
+    if (plan_out) *plan_out = plan;
+    return IFX_OK;
+}
+
+static ifx_status wan_block_launches(const ifx_wan_block_weights* w, const ifx_wan_block_io* io,
+                                     const ifx_peer_dst* peers, int32_t sp_mode, int32_t push_ctas, int32_t timeout_ms,
+                                     const ifx_kv_plan& plan, void* stream) {
+    const int C = w->dim, F = w->ffn_dim;
+    const int64_t S = io->rows, fs = io->tokens_per_frame;
+    const int world = peers ? peers->world : 1;
     const __nv_bfloat16* mod = static_cast<const __nv_bfloat16*>(io->mod);
     const int64_t mstride = 6ll * C;  // per-frame stride of [frames, 6, C]
     const float scale = 1.0f / std::sqrt(static_cast<float>(w->head_dim));
     cudaStream_t cs = static_cast<cudaStream_t>(stream);
 
     // --- self-attention (causal_model.py:431-444)
-    ifx_kv_plan plan;
-    IFX_TRY(ifx_kv_plan_append(io->kv, io->current_start, S * world, io->sink_tokens, io->windowed, &plan));
-    if (plan_out) *plan_out = plan;
     IFX_TRY(ifx_ln_modulate(io->x, io->ws_h, nullptr, nullptr, mod + 0 * C, mod + 1 * C, mstride, S, C, fs, w->eps,
                             stream));
     IFX_TRY(ifx_gemm_bf16(io->ws_h, C, w->qkv_w, C, w->qkv_b, io->ws_qkv, 3 * C, S, 3 * C, C, IFX_EPI_BIAS, nullptr, 0,

@@ -1249,11 +1249,9 @@ static ifx_status norm_rope_append_entry(const void* qkv, int64_t ld_qkv, const 
         p.v_dst = static_cast<__nv_bfloat16*>(kv->v_base);
         p.paged = 1;
         if (peers) {
-            static unsigned int* g_done = nullptr;       // one arrival counter per process (launches are stream-ordered)
-            if (!g_done) {
-                IFX_CUDA_OK(cudaMalloc(&g_done, sizeof(unsigned int)));
-                IFX_CUDA_OK(cudaMemset(g_done, 0, sizeof(unsigned int)));
-            }
+            static unsigned int* g_done_dev[64] = {nullptr};   // one arrival counter per device (stream-ordered launches)
+            unsigned int* g_done = nullptr;
+            IFX_TRY(device_counter(g_done_dev, &g_done));
             IFX_CHECK_ARG(peers->world >= 1 && peers->world <= IFX_MAX_PEERS && peers->rank >= 0 &&
                               peers->rank < peers->world && peers->epoch > 0,
                           "ifx_qk_norm_rope_append_peers: bad world / rank / epoch");
@@ -1362,11 +1360,9 @@ extern "C" ifx_status ifx_peer_push(ifx_kv* kv_, const ifx_kv_plan* plan, const 
     KvImpl* kv = kv_cast(kv_);
     if (!kv) return set_error(IFX_ERR_HANDLE, "ifx_peer_push: bad kv handle");
     IFX_CHECK_ARG(ctas > 0 && ctas <= 1024, "ifx_peer_push: bad CTA count");
-    static unsigned int* g_done_push = nullptr;    // separate from the append kernel's counter: the two may overlap
-    if (!g_done_push) {
-        IFX_CUDA_OK(cudaMalloc(&g_done_push, sizeof(unsigned int)));
-        IFX_CUDA_OK(cudaMemset(g_done_push, 0, sizeof(unsigned int)));
-    }
+    static unsigned int* g_done_push_dev[64] = {nullptr};   // separate from the append kernel's: the two may overlap
+    unsigned int* g_done_push = nullptr;
+    IFX_TRY(device_counter(g_done_push_dev, &g_done_push));
     PeerPushParams p;
     ifx_status st = fill_peer_push(p, kv, plan, peers, frames, chunk);
     if (st != IFX_OK) return st;

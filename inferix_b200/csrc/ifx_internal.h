@@ -29,6 +29,12 @@ void count_launch(int n = 1);
             return ::ifx::set_error(IFX_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e));    \
     } while (0)
 
+#define IFX_TRY(expr)                     \
+    do {                                  \
+        ifx_status _s = (expr);           \
+        if (_s != IFX_OK) return _s;      \
+    } while (0)
+
 // After a kernel launch: surfaces launch-configuration errors without synchronising.
 #define IFX_LAUNCH_OK(name)                                                                          \
     do {                                                                                             \
@@ -55,6 +61,7 @@ ifx_status make_tmap_u8_2d(CUtensorMap* out, const void* base, uint64_t inner_el
                            uint64_t row_stride_elems, uint32_t box_inner, uint32_t box_rows);
 
 int sm_count();
+ifx_status device_counter(unsigned int* (&slots)[64], unsigned int** out);
 
 // Programmatic dependent launch (PDL).  Kernels of the DiT layer are launched with the programmatic-stream-
 // serialization attribute: their CTAs may become resident while the previous kernel on the stream is still draining,

@@ -86,3 +86,48 @@ def test_core_attention_local_with_cache():
     assert rel_l2(out[0], ref) <= 4e-3
     with pytest.raises(NotImplementedError):
         CoreAttention()(q, k, v, custom_mask=torch.ones(1))
+
+
+def test_block_forward_error_leaves_cache_untouched():
+    """A block forward whose launches are refused after the append was planned (here: a misaligned scratch buffer,
+    rejected by the QKV GEMM) must leave the native block table and end indices where kv_cache_meta says they are —
+    the plan is host-side state that was already advanced when the error is found."""
+    from inferix_b200.kvcache_manager import KVCacheManager, KVCacheRequest
+    from inferix_b200.wan_model import _Workspace
+    model = CausalWanModel(**TINY, local_attn_size=6, sink_size=0)
+    model.load_state_dict(synth_state_dict(TINY, seed=0))
+    model = model.to(torch.bfloat16).to(DEV)
+    blk = model.blocks[0]
+    frames, fs, C = 3, 64, TINY["dim"]
+    mgr, req = KVCacheManager(DEV), KVCacheRequest("rollback")
+    blk.kv_cache_manager.allocate_kv_cache(mgr, req, 6 * fs, torch.bfloat16, page_tokens=fs)
+    blk.kv_cache_manager.allocate_crossattn_cache(mgr, req, 512, torch.bfloat16)
+    store = blk.kv_cache_manager.store(mgr, req)
+    g = torch.Generator().manual_seed(9)
+    table = ops.rope_table(model.freqs, DEV)
+    meta = {"global_end_index": torch.zeros(1, dtype=torch.long, device=DEV),
+            "local_end_index": torch.zeros(1, dtype=torch.long, device=DEV)}
+    cmeta = {"is_init": False}
+    ctx = (torch.randn(1, 512, C, generator=g) * 0.5).bfloat16().to(DEV)
+    e0 = (torch.randn(1, frames, 6, C, generator=g) * 0.3).bfloat16().to(DEV)
+
+    def run(start, ws=None):
+        x = torch.randn(1, frames * fs, C, generator=g).bfloat16().to(DEV)
+        return blk(x, e0, None, torch.tensor([(frames, 8, 8)]), table, ctx, None, None, meta, cmeta,
+                   current_start=start, kv_cache_manager=mgr, kv_cache_requests=[req], workspace=ws)
+
+    run(0)
+    run(3 * fs)                                           # window full: the next append evicts (table rotation)
+    before = store.state()
+    bad = _Workspace(frames * fs, C, TINY["ffn_dim"], DEV)
+    bad.qkv = torch.empty(frames * fs * 3 * C + 8, dtype=torch.bfloat16, device=DEV)[1:1 + frames * fs * 3 * C].view(
+        frames * fs, 3 * C)                               # 2 bytes off a 16-byte boundary
+    with pytest.raises((ValueError, RuntimeError, NotImplementedError)):
+        run(6 * fs, bad)
+    assert store.state() == before
+    assert (int(meta["global_end_index"]), int(meta["local_end_index"])) == (6 * fs, 6 * fs)
+    out = run(6 * fs)                                     # the same block, now with sound buffers, proceeds normally
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all()
+    after = store.state()
+    assert after != before and int(meta["global_end_index"]) == 9 * fs

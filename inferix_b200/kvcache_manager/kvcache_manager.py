@@ -141,7 +141,7 @@ class KVCacheManager:
         bs, h, d = spec.block_size, spec.spec.num_kv_heads, spec.spec.head_size
         out = torch.zeros((2, num_blocks * bs, h * d), dtype=torch.bfloat16, device=self.device)
         _, _, table = store.state()
-        mapped = len(table) * bs
+        mapped = len(table) * store.page_tokens       # native pages (frame-sized after PagedKV.repage), not `bs`
         lo, hi = start_block * bs, min((start_block + num_blocks) * bs, mapped)
         if hi > lo:   # blocks never written are "uninitialised" in the reference; they read as zeros here
             k, v = store.export(lo, hi - lo)

@@ -468,6 +468,28 @@ class PagedKV:
     def reset(self) -> None:
         _lib.check(_lib.load().ifx_kv_reset(self.handle))
 
+    def repage(self, page_tokens: int) -> None:
+        """Re-cut the (still empty) cache into pages of `page_tokens` rows.  The reference's allocation call knows no
+        page size (block_size=1, self_forcing_kv_cache_manager.py:47); the block forward calls this with the frame
+        size the first time it sees such a cache, so the reference-shaped call stays usable.  Same buffers, new table."""
+        if page_tokens == self.page_tokens:
+            return
+        total = self.num_pages * self.page_tokens
+        g, l, table = self.state()
+        if g or l or table:
+            raise ValueError(f"cannot re-page a cache that already holds {l} tokens; allocate it with "
+                             f"page_tokens={page_tokens} (allocate_kv_cache(..., page_tokens=tokens per latent frame))")
+        if self.offload is not None:
+            raise ValueError("the KV offload tier needs page_tokens at allocation time")
+        if page_tokens <= 0 or total % page_tokens:
+            raise ValueError(f"cache of {total} tokens is not a whole number of {page_tokens}-token frames")
+        lib = _lib.load()
+        _lib.check(lib.ifx_kv_destroy(self._h))
+        h = C.c_void_p()
+        _lib.check(lib.ifx_kv_create(C.byref(h), self.k.data_ptr(), self.v.data_ptr(), total // page_tokens,
+                                     page_tokens, self.heads, self.head_dim))
+        self._h, self.num_pages, self.page_tokens = h, total // page_tokens, page_tokens
+
     # ------------------------------------------------------------------ offload tier
     def stage(self) -> None:
         """Make this layer's window resident in a device slot (no-op for HBM-resident caches and when already staged).

@@ -266,6 +266,8 @@ class CausalWanAttentionBlock(nn.Module):
             xb = x[bi]
             if not xb.is_contiguous():
                 raise ValueError("x must be contiguous per sample")
+            if store.page_tokens == 1 and frame_seqlen > 1:
+                store.repage(frame_seqlen)          # reference-shaped allocation (no page size): pages = latent frames
             if store.offload is not None:           # offload tier: the window must sit in a device slot
                 if world > 1:
                     raise NotImplementedError("the KV offload tier is single-GPU (peer-mapped caches cannot move)")

@@ -131,3 +131,45 @@ def test_block_forward_error_leaves_cache_untouched():
     assert torch.isfinite(out.float()).all()
     after = store.state()
     assert after != before and int(meta["global_end_index"]) == 9 * fs
+
+
+def test_reference_shaped_allocation_without_page_size():
+    """allocate_kv_cache exactly as the reference calls it (no page_tokens: block_size=1,
+    self_forcing_kv_cache_manager.py:33-60) must be usable: the first block forward re-cuts the empty cache into
+    frame-sized pages.  Same outputs and indices as the explicitly paged allocation, incl. eviction; a cache that
+    already holds tokens cannot be re-cut."""
+    from inferix_b200.kvcache_manager import KVCacheManager, KVCacheRequest
+    model = CausalWanModel(**TINY, local_attn_size=6, sink_size=0)
+    model.load_state_dict(synth_state_dict(TINY, seed=0))
+    model = model.to(torch.bfloat16).to(DEV)
+    blk = model.blocks[0]
+    frames, fs, C = 3, 64, TINY["dim"]
+    table = ops.rope_table(model.freqs, DEV)
+    outs = []
+    for paged in (True, False):
+        mgr, req = KVCacheManager(DEV), KVCacheRequest(f"alloc{int(paged)}")
+        kw = {"page_tokens": fs} if paged else {}
+        blk.kv_cache_manager.allocate_kv_cache(mgr, req, 6 * fs, torch.bfloat16, **kw)
+        blk.kv_cache_manager.allocate_crossattn_cache(mgr, req, 512, torch.bfloat16)
+        g = torch.Generator().manual_seed(11)
+        meta = {"global_end_index": torch.zeros(1, dtype=torch.long, device=DEV),
+                "local_end_index": torch.zeros(1, dtype=torch.long, device=DEV)}
+        cmeta = {"is_init": False}
+        ctx = (torch.randn(1, 512, C, generator=g) * 0.5).bfloat16().to(DEV)
+        e0 = (torch.randn(1, frames, 6, C, generator=g) * 0.3).bfloat16().to(DEV)
+        res = []
+        for start in (0, 3 * fs, 6 * fs):
+            x = torch.randn(1, frames * fs, C, generator=g).bfloat16().to(DEV)
+            res.append(blk(x, e0, None, torch.tensor([(frames, 8, 8)]), table, ctx, None, None, meta, cmeta,
+                           current_start=start, kv_cache_manager=mgr, kv_cache_requests=[req]).clone())
+        store = blk.kv_cache_manager.store(mgr, req)
+        assert store.page_tokens == fs
+        res.append(blk.kv_cache_manager.get_kv_cache(mgr, req).clone())      # reference-shaped read-out still works
+        outs.append((res, store.state(), int(meta["global_end_index"]), int(meta["local_end_index"])))
+        with pytest.raises(ValueError):
+            store.repage(2 * fs)
+        blk.kv_cache_manager.clear_cache(mgr, req)
+    (ra, sa, ga, la), (rb, sb, gb, lb) = outs
+    assert (sa, ga, la) == (sb, gb, lb)
+    for a, b in zip(ra, rb):
+        assert torch.equal(a, b)

@@ -234,7 +234,7 @@ def sp_exchange_name(pipe):
                        "epoch flags in-kernel before its first fresh-page tile; one C-ABI call per layer)",
             "store": "peer_memory_store (K/V stored into every rank's cache by the norm+RoPE kernel, wait kernel; one "
                      "C-ABI call per layer)",
-            "ops": "peer_memory_store, op by op from Python"}[wan_model._SP_MODE]
+            "ops": "peer_memory_store, op by op from Python"}[wan_model.sp_mode(pipe.parallel_config.world_size)]
 
 
 def run_ref_gpu():

@@ -275,7 +275,7 @@ class CausalWanAttentionBlock(nn.Module):
                 store.wait_staged()
             peer_dst = getattr(store, "peer", None) if world > 1 else None
             native_block = getattr(self, "_fp8", None) is None and self._amax is None and self._q8 is None
-            if native_block and (world == 1 or (peer_dst is not None and _SP_MODE in ("overlap", "store"))):
+            if native_block and (world == 1 or (peer_dst is not None and sp_mode(world) in ("overlap", "store"))):
                 io = WanBlockIO()
                 io.x, io.rows, io.tokens_per_frame = xb.data_ptr(), rows, fs
                 io.mod, io.freqs, io.grid = mod[bi].data_ptr(), freqs.data_ptr(), grid
@@ -290,7 +290,7 @@ class CausalWanAttentionBlock(nn.Module):
                     # sequence parallel: ONE call per layer, the K/V exchange over peer memory inside it
                     from . import peer as _peer
                     peer_dst.epoch = store.peer_group.next_epoch()
-                    mode = _lib.IFX_SP_OVERLAP if _SP_MODE == "overlap" else _lib.IFX_SP_STORE
+                    mode = _lib.IFX_SP_OVERLAP if sp_mode(world) == "overlap" else _lib.IFX_SP_STORE
                     _lib.check(lib.ifx_wan_block_forward_sp(C.byref(w), C.byref(io), C.byref(peer_dst), mode,
                                                             _sp_push_ctas(world), _peer.WAIT_TIMEOUT_MS,
                                                             C.byref(plan), stream))
@@ -476,15 +476,20 @@ class CausalWanAttentionBlock(nn.Module):
 
 # IFX_SP_MODE selects how the sequence-parallel layer exchanges the block's new K / V over peer memory:
 #   overlap (default) one C-ABI call per layer; the attention kernel itself ships the rows to the peers (an idle warp
-#                     of each CTA) while it attends the cached window, and waits for the peers' flags in-kernel
+#                     of its first CTAs) while it attends the cached window, and waits for the peers' flags in-kernel
 #   store             one C-ABI call per layer; the norm+RoPE kernel stores into every rank's cache, then a wait kernel
 #   ops               the round-1 op-by-op path below (also what FP8 / calibration / the NCCL fallback use)
+# Measured on B200 boxes, back to back (profiles/r02*_sp*, r02m_*): 8 ranks 966 ms / block fused (32 copy CTAs) vs
+# 1028 ms store + wait; 2 ranks 3242 fused vs 3249 store.  A third variant (a separate copy grid on a side stream next
+# to the attention) reached only 106 GB/s on the SMs the attention leaves free and delayed its tail; it was dropped.
 _SP_MODE = __import__("os").environ.get("IFX_SP_MODE", "overlap")
 if _SP_MODE not in ("overlap", "store", "ops"):
     raise ValueError(f"IFX_SP_MODE={_SP_MODE!r}: expected overlap, store or ops")
-# measured on B200 boxes (profiles/r02*_sp*): 8 ranks 966 ms / block fused (32 copy CTAs) vs 1028 ms store + wait;
-# 2 ranks 3266 vs 3216.  A third variant (a separate copy grid on a side stream next to the attention) reached only
-# 106 GB/s on the SMs the attention leaves free and delayed its tail; it was dropped for the in-kernel copy.
+
+
+def sp_mode(world: int) -> str:
+    """The exchange variant a `world`-rank sequence-parallel group runs."""
+    return _SP_MODE
 
 
 def _sp_push_ctas(world: int) -> int:

@@ -32,7 +32,10 @@ namespace ifx {
 constexpr int kQT = 128;         // query rows per tile
 constexpr int kKT = 128;         // keys per tile
 constexpr int kHD = 128;         // head dim
-constexpr int kSlots = 4;        // K/V ring slots
+#ifndef IFX_ATTN_SLOTS
+#define IFX_ATTN_SLOTS 4
+#endif
+constexpr int kSlots = IFX_ATTN_SLOTS;   // K/V ring slots (32 KiB each; 5 still fits 227 KiB with the two Q tiles)
 constexpr int kTileBytes = 128 * 128 * 2;  // 32 KiB
 constexpr int kHalfBytes = kTileBytes / 2; // one 64-wide SWIZZLE_128B box
 constexpr int kAttnThreads = 384;
@@ -43,6 +46,15 @@ constexpr int kMaxExt = IFX_ATTN_MAX_EXTENTS;  // key-row extents (runs of physi
 #ifndef IFX_ATTN_POLY_EVERY
 #define IFX_ATTN_POLY_EVERY 0
 #endif
+#ifndef IFX_ATTN_PCHUNKS
+#define IFX_ATTN_PCHUNKS 4
+#endif
+// P = exp(S - max) is handed to the PV MMA in kPChunks column chunks, each behind its own mbarrier: the MMA warp issues
+// the chunk's tcgen05.mma (2 of the 8 k-steps per 32-key chunk) as soon as that chunk is in TMEM, while the softmax
+// warps are still computing the exponentials of the next chunk.  With one chunk (the round-1 behaviour) the tensor
+// pipe sits behind the whole 128 x 128 exponentials (1024 MUFU clocks) of a tile before its 512-clock PV can start.
+constexpr int kPChunks = IFX_ATTN_PCHUNKS;
+static_assert(kPChunks == 1 || kPChunks == 2 || kPChunks == 4, "P chunks: 1, 2 or 4");
 constexpr int kPolyEvery = IFX_ATTN_POLY_EVERY;  // 0: all exponentials on MUFU; n: one pair in n on the FMA pipe
 
 struct AttnParams {
@@ -196,8 +208,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     uint64_t* kv_empty = bars + kSlots;    // [kSlots]
     uint64_t* q_full = bars + 2 * kSlots;  // [1]
     uint64_t* s_full = q_full + 1;         // [2]
-    uint64_t* p_full = s_full + 2;         // [2]
-    uint64_t* o_full = p_full + 2;         // [1]
+    uint64_t* p_full = s_full + 2;         // [2][kPChunks]
+    uint64_t* o_full = p_full + 2 * kPChunks;  // [1]
     uint64_t* v_fixed = o_full + 1;        // [kSlots]  warp 3 -> MMA (extent mode): V tile checked, stale rows zeroed
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(v_fixed + kSlots);
     // valid keys of tile i at [i & 7], written by the producer before it arms the tile's K slot (release through the
@@ -247,10 +259,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             mbar_init(&kv_empty[i], 1);
         }
         mbar_init(q_full, 1);
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&s_full[i], 1);
-            mbar_init(&p_full[i], 128);
-        }
+        for (int i = 0; i < 2; ++i) mbar_init(&s_full[i], 1);
+        for (int i = 0; i < 2 * kPChunks; ++i) mbar_init(&p_full[i], 128);
         mbar_init(o_full, 1);
         for (int i = 0; i < kSlots; ++i) mbar_init(&v_fixed[i], 1);
         fence_barrier_init();
@@ -355,14 +365,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                             idesc_qk, k != 0);
                 }
             };
-            auto issue_pv = [&](int w, int slot, bool accumulate) {
+            auto issue_pv = [&](int w, int slot, bool accumulate, uint32_t parity) {
                 const uint32_t va = smem_u32(sKV + slot * kTileBytes);
+                constexpr int kStepsPerChunk = (kKT / 16) / kPChunks;
 #pragma unroll
-                for (int k = 0; k < kKT / 16; ++k) {
-                    // 16 keys = 16 rows of 128 bytes; the two 64-dim halves are kHalfBytes apart (LBO), 8-key
-                    // groups 1024 bytes apart (SBO).  P: 16 bf16 = 8 TMEM columns per step.
-                    umma_ts(tO(w), tS(w) + k * 8, make_smem_desc_sw128(va + k * 16 * 128, kHalfBytes, 1024), idesc_pv,
-                            accumulate || k != 0);
+                for (int c = 0; c < kPChunks; ++c) {
+                    mbar_wait(&p_full[w * kPChunks + c], parity);    // this chunk of P is in TMEM
+                    tc_fence_after();
+#pragma unroll
+                    for (int kk = 0; kk < kStepsPerChunk; ++kk) {
+                        const int k = c * kStepsPerChunk + kk;
+                        // 16 keys = 16 rows of 128 bytes; the two 64-dim halves are kHalfBytes apart (LBO), 8-key
+                        // groups 1024 bytes apart (SBO).  P: 16 bf16 = 8 TMEM columns per step.
+                        umma_ts(tO(w), tS(w) + k * 8, make_smem_desc_sw128(va + k * 16 * 128, kHalfBytes, 1024),
+                                idesc_pv, accumulate || k != 0);
+                    }
                 }
             };
             auto slot_of = [](int idx) { return idx % kSlots; };
@@ -383,20 +400,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 const int kn = 2 * j + 2;
                 const bool more = (j + 1 < n_kv);
                 mbar_wait(fix_tails ? &v_fixed[slot_of(vi)] : &kv_full[slot_of(vi)], phase_of(vi));
-                mbar_wait(&p_full[0], j & 1);
                 tc_fence_after();
-                issue_pv(0, slot_of(vi), j > 0);
+                issue_pv(0, slot_of(vi), j > 0, j & 1);
                 if (more) {
                     mbar_wait(&kv_full[slot_of(kn)], phase_of(kn));
                     tc_fence_after();
                     issue_qk(0, slot_of(kn));
                     umma_commit(&s_full[0]);
                 }
-                if (two) {
-                    mbar_wait(&p_full[1], j & 1);
-                    tc_fence_after();
-                    issue_pv(1, slot_of(vi), j > 0);
-                }
+                if (two) issue_pv(1, slot_of(vi), j > 0, j & 1);
                 umma_commit(&kv_empty[slot_of(vi)]);
                 if (more) {
                     if (two) {
@@ -473,27 +485,65 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 }
                 const float ms = m_used * sl2;
                 float l0 = 0.f, l1 = 0.f;
-                uint32_t pk[2][32];
+                if constexpr (kPChunks == 4) {
+                    // 32 keys per chunk -> 16 packed TMEM columns.  The store of chunk c is followed by the
+                    // exponentials of chunk c + 1; only then does the thread wait for the store and publish chunk c,
+                    // so neither the TMEM store latency nor the barrier round trip sits on the MUFU stream.
 #pragma unroll
-                for (int c = 0; c < 4; ++c)
+                    for (int c = 0; c < 4; ++c) {
+                        uint32_t pk[16];
 #pragma unroll
-                    for (int i = 0; i < 32; i += 2) {
-                        const float x0 = fmaf(__uint_as_float(s[c][i]), sl2, -ms);
-                        const float x1 = fmaf(__uint_as_float(s[c][i + 1]), sl2, -ms);
-                        // every kPolyEvery-th pair takes the FMA-pipe polynomial instead of MUFU.EX2
-                        const bool poly = kPolyEvery > 0 && ((i >> 1) % (kPolyEvery > 0 ? kPolyEvery : 1)) == kPolyEvery - 1;
-                        const float p0 = poly ? ex2_poly(x0) : ex2_approx(x0);
-                        const float p1 = poly ? ex2_poly(x1) : ex2_approx(x1);
-                        l0 += p0;
-                        l1 += p1;
-                        pk[c >> 1][(c & 1) * 16 + (i >> 1)] = pack_bf16x2(p0, p1);
+                        for (int i = 0; i < 32; i += 2) {
+                            const float x0 = fmaf(__uint_as_float(s[c][i]), sl2, -ms);
+                            const float x1 = fmaf(__uint_as_float(s[c][i + 1]), sl2, -ms);
+                            const bool poly = kPolyEvery > 0 && ((i >> 1) % (kPolyEvery > 0 ? kPolyEvery : 1)) == kPolyEvery - 1;
+                            const float p0 = poly ? ex2_poly(x0) : ex2_approx(x0);
+                            const float p1 = poly ? ex2_poly(x1) : ex2_approx(x1);
+                            l0 += p0;
+                            l1 += p1;
+                            pk[i >> 1] = pack_bf16x2(p0, p1);
+                        }
+                        if (c > 0) {
+                            tmem_wait_st();
+                            tc_fence_before();
+                            mbar_arrive(&p_full[w * kPChunks + c - 1]);
+                        }
+                        tmem_st16(tS_row + c * 16, pk);
                     }
-                l += l0 + l1;
-                tmem_st32(tS_row, pk[0]);
-                tmem_st32(tS_row + 32, pk[1]);
-                tmem_wait_st();
-                tc_fence_before();
-                mbar_arrive(&p_full[w]);
+                    l += l0 + l1;
+                    tmem_wait_st();
+                    tc_fence_before();
+                    mbar_arrive(&p_full[w * kPChunks + 3]);
+                } else {
+                    uint32_t pk[2][32];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 2) {
+                            const float x0 = fmaf(__uint_as_float(s[c][i]), sl2, -ms);
+                            const float x1 = fmaf(__uint_as_float(s[c][i + 1]), sl2, -ms);
+                            // every kPolyEvery-th pair takes the FMA-pipe polynomial instead of MUFU.EX2
+                            const bool poly = kPolyEvery > 0 && ((i >> 1) % (kPolyEvery > 0 ? kPolyEvery : 1)) == kPolyEvery - 1;
+                            const float p0 = poly ? ex2_poly(x0) : ex2_approx(x0);
+                            const float p1 = poly ? ex2_poly(x1) : ex2_approx(x1);
+                            l0 += p0;
+                            l1 += p1;
+                            pk[c >> 1][(c & 1) * 16 + (i >> 1)] = pack_bf16x2(p0, p1);
+                        }
+                        if (kPChunks == 2 && c == 1) tmem_st32(tS_row, pk[0]);
+                        if (kPChunks == 2 && c == 3) {
+                            tmem_wait_st();                      // first half landed while the second was computed
+                            tc_fence_before();
+                            mbar_arrive(&p_full[w * kPChunks]);
+                        }
+                    }
+                    l += l0 + l1;
+                    if (kPChunks == 1) tmem_st32(tS_row, pk[0]);
+                    tmem_st32(tS_row + 32, pk[1]);
+                    tmem_wait_st();
+                    tc_fence_before();
+                    mbar_arrive(&p_full[w * kPChunks + kPChunks - 1]);
+                }
             }
 
             mbar_wait(o_full, 0);

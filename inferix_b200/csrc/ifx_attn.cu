@@ -47,7 +47,7 @@ constexpr int kMaxExt = IFX_ATTN_MAX_EXTENTS;  // key-row extents (runs of physi
 #define IFX_ATTN_POLY_EVERY 0
 #endif
 #ifndef IFX_ATTN_PCHUNKS
-#define IFX_ATTN_PCHUNKS 4
+#define IFX_ATTN_PCHUNKS 2
 #endif
 // P = exp(S - max) is handed to the PV MMA in kPChunks column chunks, each behind its own mbarrier: the MMA warp issues
 // the chunk's tcgen05.mma (2 of the 8 k-steps per 32-key chunk) as soon as that chunk is in TMEM, while the softmax
@@ -55,6 +55,10 @@ constexpr int kMaxExt = IFX_ATTN_MAX_EXTENTS;  // key-row extents (runs of physi
 // pipe sits behind the whole 128 x 128 exponentials (1024 MUFU clocks) of a tile before its 512-clock PV can start.
 constexpr int kPChunks = IFX_ATTN_PCHUNKS;
 static_assert(kPChunks == 1 || kPChunks == 2 || kPChunks == 4, "P chunks: 1, 2 or 4");
+#ifndef IFX_ATTN_LDSPLIT
+#define IFX_ATTN_LDSPLIT 0
+#endif
+constexpr bool kLdSplit = IFX_ATTN_LDSPLIT != 0;   // softmax: overlap the TMEM load of S's second half with the first half's max
 constexpr int kPolyEvery = IFX_ATTN_POLY_EVERY;  // 0: all exponentials on MUFU; n: one pair in n on the FMA pipe
 
 struct AttnParams {
@@ -434,26 +438,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             const int row = q0 + row_in_pair;
             const float sl2 = p.scale_log2;
 
+            const uint32_t tile_valid_addr = smem_u32(const_cast<int32_t*>(tile_valid));
             float m_used = -INFINITY;  // max (raw score units) the probabilities are currently referenced to
             float l = 0.f;
             for (int j = 0; j < n_kv; ++j) {
                 mbar_wait(&s_full[w], j & 1);
                 tc_fence_after();
                 uint32_t s[4][32];
-#pragma unroll
-                for (int c = 0; c < 4; ++c) tmem_ld32(tS_row + c * 32, s[c]);
-                tmem_wait_ld();
-                const int valid = tile_valid[j & 7];
-                if (valid < kKT) {
-#pragma unroll
-                    for (int c = 0; c < 4; ++c)
-#pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (c * 32 + i >= valid) s[c][i] = __float_as_uint(-INFINITY);
-                }
                 float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll
-                for (int c = 0; c < 4; ++c)
+                auto row_max = [&](int c) {
 #pragma unroll
                     for (int i = 0; i < 32; i += 4) {
                         mx0 = fmaxf(mx0, __uint_as_float(s[c][i]));
@@ -461,6 +454,35 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                         mx2 = fmaxf(mx2, __uint_as_float(s[c][i + 2]));
                         mx3 = fmaxf(mx3, __uint_as_float(s[c][i + 3]));
                     }
+                };
+                int valid;
+                asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(valid) : "r"(tile_valid_addr + (j & 7) * 4));
+                if (kLdSplit && valid >= kKT) {
+                    // second half of the scores is still on its way from TMEM while the first half's max is taken
+                    tmem_ld32(tS_row, s[0]);
+                    tmem_ld32(tS_row + 32, s[1]);
+                    tmem_wait_ld();
+                    tmem_ld32(tS_row + 64, s[2]);
+                    tmem_ld32(tS_row + 96, s[3]);
+                    row_max(0);
+                    row_max(1);
+                    tmem_wait_ld();
+                    row_max(2);
+                    row_max(3);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) tmem_ld32(tS_row + c * 32, s[c]);
+                    tmem_wait_ld();
+                    if (valid < kKT) {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+#pragma unroll
+                            for (int i = 0; i < 32; ++i)
+                                if (c * 32 + i >= valid) s[c][i] = __float_as_uint(-INFINITY);
+                    }
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) row_max(c);
+                }
                 const float m_new = fmaxf(fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)), m_used);
                 if (j == 0) {
                     m_used = m_new;

@@ -74,6 +74,8 @@ struct AttnParams {
     int64_t ldo;
     float* part_o;       // [pieces][256][128] un-normalised O
     float* part_ml;      // [pieces][256][2]   (max * scale_log2, sum)
+    unsigned int* combine_ctr;  // non-null: the last piece of an item to finish merges the item's partials in-kernel
+                                // ([split items][2] arrival counters, zero between launches) — no attn_combine_kernel
     float* lse;          // optional [heads][q_rows] natural-log softmax denominators (log-sum-exp of the scaled scores)
     // ---- partial mode (ifx_attention_partial): every CTA emits a partial; keys are a list of row extents
     int32_t partial;         // 1: blockIdx = item * piece_count + sub, slot = item * pieces_per_item + piece_first + sub
@@ -608,6 +610,62 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     for (int v = 0; v < 8; ++v)
                         *reinterpret_cast<uint4*>(po + c * 32 + v * 4) = make_uint4(o[v * 4], o[v * 4 + 1], o[v * 4 + 2], o[v * 4 + 3]);
                 }
+                if (p.combine_ctr != nullptr) {
+                    // Fused combine ("last block" pattern): every thread publishes its partial row, the 128 threads of
+                    // the query tile meet at a named barrier, one of them counts the tile's arrival; the piece that
+                    // arrives last reads all pieces of its rows back (L2) and writes the final bf16 rows.  Same
+                    // arithmetic, in the same order, as attn_combine_kernel.
+                    volatile int32_t* last_flag = tile_valid + 8;
+                    const int sitem = item - p.n_whole;
+                    __threadfence();
+                    asm volatile("bar.sync %0, 128;" ::"r"(1 + w) : "memory");
+                    if (quad == 0 && lane == 0) {
+                        __threadfence();
+                        const unsigned int old = atomicAdd(p.combine_ctr + sitem * 2 + w, 1u);
+                        const bool last = old == static_cast<unsigned int>(p.split - 1);
+                        if (last) p.combine_ctr[sitem * 2 + w] = 0;      // every piece has arrived: ready for the next launch
+                        last_flag[w] = last ? 1 : 0;
+                    }
+                    asm volatile("bar.sync %0, 128;" ::"r"(1 + w) : "memory");
+                    if (last_flag[w] != 0 && row < p.q_rows) {
+                        __threadfence();
+                        const int64_t base0 = static_cast<int64_t>(sitem) * p.split * (2 * kQT) + row_in_pair;
+                        float m = -INFINITY;
+                        for (int sp = 0; sp < p.split; ++sp)
+                            m = fmaxf(m, __ldcg(p.part_ml + (base0 + static_cast<int64_t>(sp) * (2 * kQT)) * 2));
+                        float lsum = 0.f;
+                        float acc[kHD];
+#pragma unroll
+                        for (int d = 0; d < kHD; ++d) acc[d] = 0.f;
+                        for (int sp = 0; sp < p.split; ++sp) {
+                            const int64_t base = base0 + static_cast<int64_t>(sp) * (2 * kQT);
+                            const float a = ex2_approx(__ldcg(p.part_ml + base * 2) - m);
+                            lsum += __ldcg(p.part_ml + base * 2 + 1) * a;
+                            const float4* src = reinterpret_cast<const float4*>(p.part_o + base * kHD);
+#pragma unroll
+                            for (int d = 0; d < kHD / 4; ++d) {
+                                const float4 o4 = __ldcg(src + d);
+                                acc[4 * d] += o4.x * a;
+                                acc[4 * d + 1] += o4.y * a;
+                                acc[4 * d + 2] += o4.z * a;
+                                acc[4 * d + 3] += o4.w * a;
+                            }
+                        }
+                        const float inv = 1.0f / lsum;
+                        if (p.lse != nullptr)
+                            p.lse[static_cast<int64_t>(head) * p.q_rows + row] = (m + log2f(lsum)) * 0.6931471805599453f;
+                        __nv_bfloat16* optr = p.out + static_cast<int64_t>(row) * p.ldo + head * kHD;
+#pragma unroll
+                        for (int v = 0; v < kHD / 8; ++v) {
+                            uint4 pkt;
+                            pkt.x = pack_bf16x2(acc[v * 8 + 0] * inv, acc[v * 8 + 1] * inv);
+                            pkt.y = pack_bf16x2(acc[v * 8 + 2] * inv, acc[v * 8 + 3] * inv);
+                            pkt.z = pack_bf16x2(acc[v * 8 + 4] * inv, acc[v * 8 + 5] * inv);
+                            pkt.w = pack_bf16x2(acc[v * 8 + 6] * inv, acc[v * 8 + 7] * inv);
+                            *reinterpret_cast<uint4*>(optr + v * 8) = pkt;
+                        }
+                    }
+                }
             }
         }
     }
@@ -677,6 +735,7 @@ struct KeySpec {
 
 static void fill_defaults(AttnParams& p) {
     p.lse = nullptr;
+    p.combine_ctr = nullptr;
     p.partial = 0;
     p.pieces_per_item = p.piece_count = 1;
     p.piece_first = 0;
@@ -732,6 +791,17 @@ static ifx_status launch_attn_kernel(int grid, const CUtensorMap& tmQ, const CUt
     IFX_CUDA_OK(launch_kernel(attn_fwd_kernel, dim3(static_cast<unsigned>(grid)), dim3(kAttnThreads), kAttnSmem, stream,
                               true, tmQ, tmK, tmV, pp));
     return IFX_OK;
+}
+
+// IFX_ATTN_FUSED_COMBINE=1: the last piece of a split item merges the item's partials inside the attention kernel
+// instead of a separate attn_combine_kernel launch (A/B switch)
+static bool fused_combine() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("IFX_ATTN_FUSED_COMBINE");
+        v = (e != nullptr && e[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
 }
 
 // scratch for the split partials of the tail wave, one per device (grown on demand; launches of one device are
@@ -822,6 +892,17 @@ static ifx_status attention_launch(const void* q, int64_t ldq, const void* k, co
         }
         p.part_o = sc.ptr;
         p.part_ml = sc.ptr + static_cast<size_t>(pieces) * (2 * kQT) * kHD;
+        if (fused_combine()) {
+            // arrival counters of the fused combine: two per split item (one per 128-row query tile), self-resetting
+            static unsigned int* g_ctr[64] = {nullptr};
+            constexpr int kMaxSplitItems = 4096;
+            IFX_CHECK_ARG(rem <= kMaxSplitItems, "ifx_attention: %d split items", rem);
+            if (!g_ctr[dev]) {
+                IFX_CUDA_OK(cudaMalloc(&g_ctr[dev], 2 * kMaxSplitItems * sizeof(unsigned int)));
+                IFX_CUDA_OK(cudaMemset(g_ctr[dev], 0, 2 * kMaxSplitItems * sizeof(unsigned int)));
+            }
+            p.combine_ctr = g_ctr[dev];
+        }
     }
     const int grid = p.n_whole + pieces;
     if (keys != nullptr && keys->push != nullptr) {
@@ -854,11 +935,11 @@ static ifx_status attention_launch(const void* q, int64_t ldq, const void* k, co
         ProfScope prof(label, stream);
         st = launch_attn_kernel(grid, tmQ, tmK, tmV, p, keys != nullptr && keys->pdl, stream);
         if (st != IFX_OK) return st;
-        if (pieces > 0)
+        if (pieces > 0 && p.combine_ctr == nullptr)
             IFX_CUDA_OK(launch_kernel(attn_combine_kernel, dim3(rem * (2 * kQT) / 8), dim3(256), 0, stream, true, p));
     }
     IFX_LAUNCH_OK("attn_fwd_kernel");
-    if (pieces > 0) count_launch();
+    if (pieces > 0 && p.combine_ctr == nullptr) count_launch();
     return IFX_OK;
 }
 

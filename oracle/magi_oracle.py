@@ -9,8 +9,12 @@ Parity status: PINNED to the reference's own modules.  `oracle/make_golden_magi_
 `TransformerBlock` / `cp_*` functions from /root/reference, runs them on CPU and stores the results under
 `tests/golden/magi_layer_*.pt` / `magi_cp.json`; `tests/test_magi_layer_cpu.py` checks this restatement against those
 files bit-for-bit.  The reference layer calls five CUDA-only third-party kernels; the golden run replaces each by the
-torch statement of its published algorithm, which is also what this file restates — so for these five the pin is to
-the algorithm, not to the vendor's binary ("parity unpinned" at that boundary).  The golden run also
+torch statement of its published algorithm, which is also what this file restates — so on the CPU host the pin for
+these five is to the algorithm, not to the vendor's binary.  That boundary is closed on the GPU box, where the
+libraries exist: `tests/test_gpu_zzz_thirdparty_pin.py` runs each restatement below against the library kernel itself
+(flashinfer silu_and_mul / bmm_fp8 and the reference's Triton range_mod: bit-exact; flash_attn rotary: 99.9996 %
+identical; flash_attn_func / _varlen_func: 2.2e-3 from this fp32 statement, the bf16-P kernel's own distance;
+profiles/r02z_pytest_thirdparty_pin.log).  The golden run also
 emulates CUDA autocast(dtype=float32) — inactive on a CPU-only host — by casting the operands of `F.linear` to fp32
 inside the reference's `torch.autocast("cuda", dtype=torch.float32)` regions, which is what CUDA autocast does:
   flash_attn.flash_attn_func / flash_attn_varlen_func  -> softmax(q k^T / sqrt(d)) v with grouped KV heads, fp32 math

@@ -90,6 +90,9 @@ def main():
     ap.add_argument("--blocks", type=int, default=10)
     ap.add_argument("--timesteps", type=int, default=30, help="T of the production block being extrapolated to")
     ap.add_argument("--tiny-cpu", action="store_true", help="plumbing dry run: tiny widths, CPU, SDPA fallback")
+    ap.add_argument("--parity", action="store_true",
+                    help="tiny widths on the GPU: the reference's own GPU path (FA2 + cuBLAS) and the native pipeline on "
+                         "the same weights / noise / re-noise stream; prints their distance instead of timings")
     ap.add_argument("--out", default=None)
     a = ap.parse_args()
 
@@ -114,6 +117,8 @@ def main():
         assert fa_mod.HAS_FLASH_ATTN, "flash-attn is not importable: the reference would fall back to SDPA"
         fa_mod.HAS_FLASH_ATTN_HOPPER = False        # FA3 (Hopper-only) is not installed / not applicable on sm_100
         dev, cfg, hw, window_frames = torch.device("cuda", 0), dict(synthetic.WAN_1_3B), (90, 160), 24
+        if a.parity:
+            cfg, hw, window_frames, a.blocks = dict(synthetic.TINY), (16, 16), 6, 4
     torch.set_grad_enabled(False)
 
     from inferix.core.types import DecodeMode
@@ -155,7 +160,7 @@ def main():
     pipe.parallel_config, pipe._profiler = pc, None
     pipe.generator, pipe.text_encoder, pipe.vae = gen, Text(), None
     pipe.scheduler = gen.scheduler
-    steps = [1000, 500]
+    steps = [1000, 750, 500, 250] if a.parity else [1000, 500]
     sched_ts = torch.cat((gen.scheduler.timesteps.cpu(), torch.tensor([0], dtype=torch.float32)))
     pipe.denoising_step_list = sched_ts[1000 - torch.tensor(steps, dtype=torch.long)]
     pipe.num_transformer_blocks = cfg["num_layers"]
@@ -195,8 +200,52 @@ def main():
     context = torch.randn(1, 20, cfg["text_dim"], generator=g).bfloat16().to(dev)
     mgr = KVCacheManager(dev)
     t0 = time.perf_counter()
-    pipe.inference(noise=noise, text_prompts=context, kv_cache_manager=mgr, kv_cache_requests=[KVCacheRequest("ref")],
-                   free_cache_before_vae=False, decode_mode=DecodeMode.NO_DECODE)
+    if a.parity:
+        # same re-noise stream on both sides: torch.randn_like (reference :307, ours pipeline.renoise_fn) drawn from a
+        # CPU generator with a fixed seed
+        true_randn_like = torch.randn_like
+
+        def seeded(seed):
+            rg = torch.Generator().manual_seed(seed)
+            return lambda x, **kw: torch.randn(x.shape, generator=rg, dtype=torch.float32).to(x.dtype).to(x.device)
+        torch.randn_like = seeded(5)
+    ref_out = pipe.inference(noise=noise, text_prompts=context, kv_cache_manager=mgr,
+                             kv_cache_requests=[KVCacheRequest("ref")], free_cache_before_vae=False,
+                             decode_mode=DecodeMode.NO_DECODE)
+    if a.parity:
+        torch.randn_like = true_randn_like
+        ref_idx = (int(pipe.kv_cache_meta[0]["global_end_index"]), int(pipe.kv_cache_meta[0]["local_end_index"]))
+        ref_lat = (ref_out[0] if isinstance(ref_out, (tuple, list)) else ref_out).float().cpu()
+        from inferix_b200.kvcache_manager import KVCacheManager as NKV, KVCacheRequest as NReq
+        from inferix_b200.pipeline import CausalInferencePipeline as NPipe, DecodeMode as NDecode
+        from inferix_b200.wan_model import CausalWanModel as NModel
+        from inferix_b200.wrapper import WanDiffusionWrapper as NWrap
+        nm = NModel(**cfg, local_attn_size=window_frames, sink_size=0)
+        nm.load_state_dict(synthetic.synth_state_dict(cfg, seed=0))
+        nm = nm.to(torch.bfloat16).to(dev)
+        nargs = types.SimpleNamespace(denoising_step_list=steps, warp_denoising_step=True, num_frame_per_block=3,
+                                      context_noise=0)
+        npipe = NPipe(nargs, dev, generator=NWrap(model=nm, timestep_shift=5.0))
+        npipe.renoise_fn = seeded(5)
+        ours = npipe.inference(noise=noise, text_prompts=context, kv_cache_manager=NKV(dev),
+                               kv_cache_requests=[NReq("ours")], decode_mode=NDecode.NO_DECODE,
+                               free_cache_before_vae=False)
+        ours_lat = (ours[0] if isinstance(ours, (tuple, list)) else ours).float().cpu()
+        our_idx = (int(npipe.kv_cache_meta[0]["global_end_index"]), int(npipe.kv_cache_meta[0]["local_end_index"]))
+        res = {"impl": "reference_gpu_parity",
+               "what": "unmodified reference (its FA2 + cuBLAS GPU path) vs the native pipeline, same synthetic weights, "
+                       "noise and re-noise stream, on this GPU",
+               "shape": f"tiny widths {cfg['dim']}/{cfg['num_heads']} heads, {a.blocks} blocks x {len(steps)} steps + clean "
+                        f"pass, window {window_frames} frames (eviction from block 3)",
+               "rel_l2": ((ours_lat - ref_lat).norm() / ref_lat.norm()).item(),
+               "max_abs": (ours_lat - ref_lat).abs().max().item(),
+               "end_indices_reference": ref_idx, "end_indices_native": our_idx, "index_equal": ref_idx == our_idx,
+               "finite": bool(torch.isfinite(ours_lat).all()), "gpu": torch.cuda.get_device_name(0)}
+        line = json.dumps(res)
+        print(line, flush=True)
+        if a.out:
+            Path(a.out).write_text(line + "\n")
+        return
     if use_ev:
         torch.cuda.synchronize()
         ms = [s.elapsed_time(e) for s, e in events]

@@ -14,7 +14,7 @@ Import map for a user of the reference:
     inferix.pipeline.magi.video_generate.SampleTransport (+ index helpers) -> inferix_b200.magi_pipeline / magi_schedule
     inferix.distributed.parallelism.context_parallel (Ulysses) -> inferix_b200.magi_cp
     inferix.distributed.parallel_state / dist_utils   -> inferix_b200.parallel_state / dist_utils
-    inferix.models.schedulers.fm_solvers_unipc.FlowUniPCMultistepScheduler -> inferix_b200.unipc
+    inferix.models.wan_base.utils.fm_solvers_unipc.FlowUniPCMultistepScheduler -> inferix_b200.unipc
     inferix.pipeline.self_forcing.CausalDiffusionInferencePipeline -> inferix_b200.diffusion_pipeline
     inferix.models.attention.{distributed.CoreAttention,backends.collect_supported_attn} -> inferix_b200.attention
 Everything computes through libinferix_b200.so (include/inferix_b200.h); there is no CPU fallback.

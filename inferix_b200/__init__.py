@@ -12,7 +12,7 @@ Import map for a user of the reference:
     inferix.models.magi.dit.dit_module.{TransformerLayer,TransformerBlock,...} -> inferix_b200.magi_layer.*
     inferix.models.magi.dit.dit_model.VideoDiTModel   -> inferix_b200.magi_model.VideoDiTModel
     inferix.pipeline.magi.video_generate.SampleTransport (+ index helpers) -> inferix_b200.magi_pipeline / magi_schedule
-    inferix.distributed.parallelism.context_parallel (Ulysses) -> inferix_b200.magi_cp
+    inferix.distributed.parallelism.context_parallel (Ulysses) -> inferix_b200.magi_cp, inferix_b200.ulysses_scheduler
     inferix.distributed.parallel_state / dist_utils   -> inferix_b200.parallel_state / dist_utils
     inferix.models.wan_base.utils.fm_solvers_unipc.FlowUniPCMultistepScheduler -> inferix_b200.unipc
     inferix.pipeline.self_forcing.CausalDiffusionInferencePipeline -> inferix_b200.diffusion_pipeline

@@ -43,3 +43,19 @@ def test_magi_ulysses_cp2_equals_single_gpu():
     res = json.loads([l for l in p.stdout.splitlines() if l.startswith("{")][-1])
     # per-row math and per-head attention are independent of the split; GEMM tile shapes differ with M
     assert res["worst_vs_single"] <= 1e-2 and res["worst_vs_golden"] <= 3e-2, res
+
+
+def test_core_attention_ring_strategies_two_gpus():
+    """CoreAttention pass-kv / pass-q (reference distributed.py:372-712) with the native (out, lse) kernel over 2 GPUs
+    vs one attention over the gathered keys: the LSE merge is exact, the partial outputs are bf16 (one extra rounding
+    per hop)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+           "127.0.0.1", "--master-port", "29523", str(ROOT / "tools" / "ring_check.py")]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    res = json.loads([l for l in p.stdout.splitlines() if l.startswith("{")][-1])
+    print(res)
+    assert res["pass_kv_out"] <= 4e-3 and res["pass_q_out"] <= 4e-3 and res["forward_pass_q_out"] <= 4e-3, res
+    assert res["pass_kv_lse"] <= 1e-5 and res["pass_q_lse_bf16"] <= 5e-3, res
